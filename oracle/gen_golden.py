@@ -1,0 +1,328 @@
+"""TEST INFRASTRUCTURE -- generate tests/golden/* by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):   python oracle/gen_golden.py
+The reference ships no golden vectors, so these files are the pin for
+the oracle: every array below is an output of reference code imported by path
+(oracle/ref_import.py) on deterministic synthetic inputs (video-3d-llm_b200/synthetic.py).
+Large outputs are stored as SHA-256 digests of their raw bytes (a bit-exact known answer)
+plus a strided sample for diagnosis; small ones in full.  Inputs are regenerated from seeds
+by the tests and their digests are stored here too, so an input drift is reported as such.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import platform
+import random
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.join(_ROOT, "tests"))
+sys.path.insert(0, _HERE)
+
+import cv2  # noqa: E402
+import torch  # noqa: E402
+
+import ref_import  # noqa: E402
+import fixtures  # noqa: E402
+from video_3d_llm_b200 import synthetic  # noqa: E402
+
+GOLDEN = os.path.join(_ROOT, "tests", "golden")
+
+
+def sha(a) -> str:
+    a = np.ascontiguousarray(a)
+    return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def versions() -> dict:
+    return {
+        "torch": torch.__version__, "numpy": np.__version__, "cv2": cv2.__version__,
+        "python": platform.python_version(), "cpu": platform.processor() or platform.machine(),
+        "mkl": torch.backends.mkl.is_available(),
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# A. in-memory front end: unproject -> resize/crop -> pool -> discretise -> PE -> add
+# ------------------------------------------------------------------------------------------
+def golden_frontend():
+    vu, pe_mod, shim = ref_import.video_utils(), ref_import.position_encoding(), ref_import.ArchShim()
+    sc = synthetic.make_scene(0, 2, n_total=30, H=480, W=640, device="cpu")
+    depth = sc.depth_u16()
+    V, H, W = depth.shape
+    g = {"meta": json.dumps(versions()), "in_depth_sha": sha(depth), "in_poses": sc.poses.numpy(),
+         "in_intr": sc.intrinsics.numpy()}
+
+    # llava/video_utils.py:230 -- the reference feeds depths.float() (from int32)
+    world = vu.unproject(sc.intrinsics, sc.poses, torch.from_numpy(depth.astype(np.int32)).float())
+    wn = world.numpy()
+    g["world_sha"] = sha(wn)
+    g["world_sample"] = wn[:, ::37, ::41].copy()
+    # independent float64 scalar twin (llava/video_utils.py:14-28) on a few pixels
+    uv = [(0, 0), (639, 479), (320, 240), (100, 400), (555, 17)]
+    g["uvd_px"] = np.array(uv, np.int32)
+    g["uvd_f64"] = np.array([[vu.convert_from_uvd(u, v, float(depth[f, v, u]), sc.intrinsics[f].double().numpy(),
+                                                  sc.poses[f].double().numpy()) for (u, v) in uv] for f in range(V)])
+
+    # llava/video_utils.py:273-277 boundary
+    flat = world.reshape(-1, 3)
+    g["boundry"] = np.array([flat[:, 0].min().item(), flat[:, 0].max().item(), flat[:, 1].min().item(),
+                             flat[:, 1].max().item(), flat[:, 2].min().item(), flat[:, 2].max().item()], np.float32)
+
+    # llava/video_utils.py:291-308, both strategies, through the same cv2 call the reference makes
+    crop = 384
+    new_w = int(W * (crop / H))
+    res = [cv2.resize(c.numpy(), (new_w, crop), interpolation=cv2.INTER_NEAREST) for c in world]
+    left = (new_w - crop) // 2
+    coords = np.stack([c[0:crop, left:left + crop, :] for c in res])
+    g["coords_sha"] = sha(coords)
+    g["coords_sample"] = coords[:, ::29, ::31].copy()
+    coords_rs = np.stack([cv2.resize(c.numpy(), (384, 384), interpolation=cv2.INTER_NEAREST) for c in world])
+    g["coords_resize_sha"] = sha(coords_rs)
+    # index maps recovered from cv2 itself (ramp image), for every geometry the tests use
+    for (h, w) in [(480, 640), (120, 160), (60, 80), (968, 1296)]:
+        for strat in ("center_crop", "resize"):
+            ramp_r = np.repeat(np.arange(h, dtype=np.float32)[:, None], w, 1)
+            ramp_c = np.repeat(np.arange(w, dtype=np.float32)[None, :], h, 0)
+            if strat == "resize":
+                rr = cv2.resize(ramp_r, (384, 384), interpolation=cv2.INTER_NEAREST)[:, 0]
+                cc = cv2.resize(ramp_c, (384, 384), interpolation=cv2.INTER_NEAREST)[0, :]
+            else:
+                nw = int(w * (384 / h))
+                lf = (nw - 384) // 2
+                rr = cv2.resize(ramp_r, (nw, 384), interpolation=cv2.INTER_NEAREST)[:, 0]
+                cc = cv2.resize(ramp_c, (nw, 384), interpolation=cv2.INTER_NEAREST)[0, lf:lf + 384]
+            g[f"rowmap_{h}x{w}_{strat}"] = rr.astype(np.int32)
+            g[f"colmap_{h}x{w}_{strat}"] = cc.astype(np.int32)
+
+    ct = torch.from_numpy(coords)
+    # llava/model/llava_arch.py:213-257
+    avg27 = shim.average_coordinate_in_patch(ct, 27)
+    avg14 = shim.average_coordinate_in_patch(ct, 14)
+    g["avg27"], g["avg14"] = avg27.numpy(), avg14.numpy()
+    g["minmax27"] = shim.minmax_coordinate_in_patch(ct, 27).numpy()
+    g["minmax14"] = shim.minmax_coordinate_in_patch(ct, 14).numpy()
+    for n in (9, 5, 1):
+        g[f"sample{n}"] = shim.sample_n_points(ct, n).numpy()
+    # llava/model/llava_arch.py:259-272
+    d27 = shim.discrete_coords(avg27, None)
+    d14 = shim.discrete_coords(avg14, None)
+    g["disc27"], g["disc14"] = d27.numpy(), d14.numpy()
+    g["disc_sample9"] = shim.discrete_coords(torch.from_numpy(g["sample9"]), None).numpy()
+    g["disc_minmax27"] = shim.discrete_coords(torch.from_numpy(g["minmax27"]), None).numpy()
+    # a stress vector for the discretiser: values on .5 ties, beyond the clamp, NaN
+    stress = torch.tensor([[-15.05, 0.05, -5.0], [15.0, 14.95, 5.05], [0.25, -0.35, 0.15], [100.0, -100.0, 0.0],
+                           [float("nan"), 1.0, 2.0], [7.25, -7.75, 2.5]], dtype=torch.float32)
+    g["disc_stress_in"], g["disc_stress_out"] = stress.numpy(), shim.discrete_coords(stress, None).numpy()
+
+    # llava/model/position_encoding.py:17-49
+    tok_sel = slice(None, None, 13)
+    pe3584 = pe_mod.PositionEmbeddingSine3D(3584)(d27.flatten(1, 2))
+    g["pe3584_sel"] = pe3584[:, tok_sel].numpy()
+    g["pe3584_bf16_sha"] = sha(pe3584.to(torch.bfloat16).view(torch.int16).numpy())
+    pe1152 = pe_mod.PositionEmbeddingSine3D(1152)(d14.flatten(1, 2))
+    g["pe1152_sel"] = pe1152[:, ::37].numpy()
+    g["pe1152_bf16_sha"] = sha(pe1152.to(torch.bfloat16).view(torch.int16).numpy())
+    g["pe1155_sel"] = pe_mod.PositionEmbeddingSine3D(1155)(d14.flatten(1, 2))[:, ::37].numpy()  # odd nf branch
+    g["pe3584_cont_sel"] = pe_mod.PositionEmbeddingSine3D(3584)(avg27.flatten(1, 2))[:, tok_sel].numpy()
+    s9 = torch.from_numpy(g["disc_sample9"]).flatten(1, 2)  # (V,196,9,3)
+    g["pe3584_n9_sel"] = pe_mod.PositionEmbeddingSine3D(3584, n_points=9)(s9)[:, tok_sel].numpy()
+    mm = torch.from_numpy(g["disc_minmax27"]).flatten(1, 2)  # (V,196,2,3)
+    g["pe3584_n2_sel"] = pe_mod.PositionEmbeddingSine3D(3584, n_points=2)(mm)[:, tok_sel].numpy()
+    # the full 301-row table behind the discrete PE
+    idx = torch.arange(301, dtype=torch.float32).view(1, 301, 1).repeat(1, 1, 3)
+    t3584 = pe_mod.PositionEmbeddingSine3D(3584)(idx)[0, :, :1194]
+    t1152 = pe_mod.PositionEmbeddingSine3D(1152)(idx)[0, :, :384]
+    g["pe_table_3584_rows7"] = t3584[::7].numpy()
+    g["pe_table_1152_rows7"] = t1152[::7].numpy()
+    g["pe_table_3584_bf16_sha"] = sha(t3584.to(torch.bfloat16).view(torch.int16).numpy())
+    g["pe_table_1152_bf16_sha"] = sha(t1152.to(torch.bfloat16).view(torch.int16).numpy())
+    for nf in (1194, 384, 385, 132, 597):
+        dt = torch.arange(nf, dtype=torch.float32)
+        g[f"dim_t_{nf}"] = (10000 ** (2 * (dt // 2) / nf)).numpy()
+
+    # llava/model/llava_arch.py:515 in bf16 (training dtype)
+    tokens = synthetic.make_tokens(0, V, 196, 3584)
+    g["in_tokens_sha"] = sha(tokens.view(torch.int16).numpy())
+    added = tokens + pe3584.to(torch.bfloat16)
+    g["added3584_bf16_sha"] = sha(added.view(torch.int16).numpy())
+    g["added3584_sel"] = added[:, tok_sel].float().numpy()
+
+    # llava/model/position_encoding.py:52-84 (MLP variant), seeded weights
+    torch.manual_seed(1234)
+    mlp = pe_mod.PositionEmbeddingMLP(192)
+    with torch.no_grad():
+        out = mlp(avg14.flatten(1, 2))
+    for k, v in mlp.state_dict().items():
+        g["mlp_" + k.replace(".", "_")] = v.numpy()
+    g["mlp_out_sel"] = out[:, ::37].numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "frontend.npz"), **g)
+    print("frontend.npz written:", len(g), "entries")
+
+
+# ------------------------------------------------------------------------------------------
+# B. on-disk dataset: reference VideoProcessor + reference max_coverage_sampling.main
+# ------------------------------------------------------------------------------------------
+MC_SCENES = [(1, 70, "train", 60, 80), (2, 24, "train", 120, 160), (3, 4, "val", 480, 640)]
+
+
+def _run_reference_mc(root: str, seed_of: dict) -> list:
+    """Run scripts/3d/preprocessing/max_coverage_sampling.py:main unmodified, one scene per
+    call, with (a) 'cuda' device moves turned into no-ops (no GPU here; CPU IEEE arithmetic is
+    the parity target) and (b) random.seed(scene seed) right before the call (the reference's
+    tie-break is unseeded, :84; this is the protocol SURVEY.md Appendix A-7 defines)."""
+    ref_import.llava_arch()  # registers the stub `llava` package so `from llava.video_utils import` works
+    mod = ref_import._load_by_path("_ref_mc", "scripts/3d/preprocessing/max_coverage_sampling.py")
+    orig_to = torch.Tensor.to
+
+    def to_cpu(self, *a, **k):
+        a = tuple("cpu" if (isinstance(x, str) and x.startswith("cuda")) else x for x in a)
+        return orig_to(self, *a, **k)
+
+    out = []
+    cwd = os.getcwd()
+    os.chdir(root)
+    torch.Tensor.to = to_cpu
+    try:
+        for name, seed in seed_of.items():
+            vd = os.path.join(root, "only_" + name)
+            os.makedirs(os.path.join(vd, name), exist_ok=True)
+            args = types.SimpleNamespace(voxel_size=0.1, video_dir=vd, output_file=os.path.join(root, f"sel_{name}.json"))
+            random.seed(seed)
+            mod.main(args)
+            with open(args.output_file) as f:
+                out.extend(json.load(f))
+    finally:
+        torch.Tensor.to = orig_to
+        os.chdir(cwd)
+    return out
+
+
+def golden_dataset():
+    vu = ref_import.video_utils()
+    res = {"meta": versions(), "scenes": {}}
+    with tempfile.TemporaryDirectory() as root:
+        scenes = {}
+        for seed, n_total, split, H, W in MC_SCENES:
+            # one dataset, mixed resolutions: write scene by scene
+            pass
+        # write_dataset handles one resolution; call per scene and merge the metadata
+        infos = {"train": [], "val": [], "test": []}
+        boxes = {"train": {}, "val": {}}
+        pcs = {}
+        import pickle
+        for seed, n_total, split, H, W in MC_SCENES:
+            info, bx, pc, sc = fixtures.write_scene(root, seed, n_total, H, W, split)
+            infos[split].append(info)
+            boxes["val" if split == "val" else "train"][info["sample_idx"]] = bx
+            pcs[fixtures.scene_name(seed)] = [tuple(int(t) for t in v) for v in pc]
+            scenes[fixtures.scene_name(seed)] = sc
+            res["scenes"][fixtures.scene_name(seed)] = {
+                "seed": seed, "n_total": n_total, "split": split, "H": H, "W": W,
+                "depth_sha": sha(sc.depth_u16()), "pc_sha": sha(pc), "n_pc": int(len(pc)),
+            }
+        os.makedirs(os.path.join(root, "data", "embodiedscan"), exist_ok=True)
+        os.makedirs(os.path.join(root, "data", "metadata"), exist_ok=True)
+        for split in infos:
+            with open(os.path.join(root, "data", "embodiedscan", f"embodiedscan_infos_{split}.pkl"), "wb") as f:
+                pickle.dump({"data_list": infos[split]}, f)
+        for k, fn in (("train", "scannet_train_gt_box.json"), ("val", "scannet_val_pred_box.json")):
+            with open(os.path.join(root, "data", "metadata", fn), "w") as f:
+                json.dump(boxes[k], f)
+        with open(os.path.join(root, "data", "metadata", "pcd_discrete_0.1.pkl"), "wb") as f:
+            pickle.dump(pcs, f)
+
+        # --- reference MC sampler -------------------------------------------------------
+        seed_of = {fixtures.scene_name(s[0]): s[0] for s in MC_SCENES}
+        sel = _run_reference_mc(root, seed_of)
+        with open(os.path.join(root, "data", "metadata", "scannet_select_frames.json"), "w") as f:
+            json.dump(sel, f)
+        res["select_frames"] = sel
+
+        # --- reference VideoProcessor ----------------------------------------------------
+        cwd = os.getcwd()
+        os.chdir(root)
+        try:
+            ip = fixtures.FakeImageProcessor(384)
+            vp_res = {}
+            for strat in ("uniform", "mc", "mc-ratio90", "mc-ratio95", "mc-ratio95-norm"):
+                vp = vu.VideoProcessor(video_folder="data", annotation_dir="data/embodiedscan/", voxel_size=0.1,
+                                       min_xyz_range=[-15, -15, -5], max_xyz_range=[15, 15, 5],
+                                       frame_sampling_strategy=strat)
+                entry = {}
+                for name in scenes:
+                    vid = f"scannet/{name}"
+                    e = {}
+                    if "mc" in strat:
+                        for ub in (32, 8, 3):
+                            e[f"files_ub{ub}"] = vp.sample_frame_files_mc(vid, frames_upbound=ub)
+                        e["pc_min"] = vp.pc_min[name].tolist()
+                        e["pc_max"] = vp.pc_max[name].tolist()
+                    else:
+                        e["files_force8"] = vp.sample_frame_files(vid, force_sample=True, frames_upbound=8)
+                        e["files_default"] = vp.sample_frame_files(vid, force_sample=False, frames_upbound=8)
+                    if name == fixtures.scene_name(3):  # the full-resolution scene: whole preprocess()
+                        d = vp.process_3d_video(vid, ip, force_sample=True, frames_upbound=3)
+                        wc = d["world_coords"].numpy()
+                        e["world_coords_shape"] = list(wc.shape)
+                        e["world_coords_sha"] = sha(wc)
+                        e["world_coords_sample"] = wc[:, ::61, ::67].tolist()
+                        e["boundry"] = d["boundry"].tolist()
+                        e["objects"] = d["objects"].tolist()
+                        e["video_size"] = d["video_size"]
+                        e["images_shape"] = list(d["images"].shape)
+                        d["box_input"] = None
+                        m = vu.merge_video_dict([d])
+                        e["merged_keys"] = sorted(m.keys())
+                        e["merged_world_shape"] = list(m["world_coords"].shape)
+                        e["merged_box_input_len"] = int(len(m["box_input"]))
+                    entry[name] = e
+                vp_res[strat] = entry
+            res["video_processor"] = vp_res
+            vp = vu.VideoProcessor(voxel_size=0.1, min_xyz_range=[-15, -15, -5], max_xyz_range=[15, 15, 5])
+            pts = [[0, 0, 0], [0.25, -0.35, 0.15], [20.0, -20.0, 7.0], [1.05, 2.15, -3.25]]
+            res["discrete_point"] = {"in": pts, "out": vp.discrete_point(pts)}
+            vp2 = vu.VideoProcessor(voxel_size=0.1)
+            res["discrete_point_norange"] = {"in": pts, "out": vp2.discrete_point(pts)}
+        finally:
+            os.chdir(cwd)
+    with open(os.path.join(GOLDEN, "dataset.json"), "w") as f:
+        json.dump(res, f)
+    print("dataset.json written")
+
+
+def golden_mt():
+    """CPython `random` known answers for the in-kernel MT19937 (tie-break protocol)."""
+    out = {}
+    for seed in (0, 1, 42, 1003, 2**32 + 5, 2**63 - 1):
+        random.seed(seed)
+        ns = [1, 1, 2, 3, 5, 7, 8, 16, 17, 31, 32, 33, 100, 149, 150, 1, 1, 1, 64, 2] * 40
+        out[str(seed)] = {"ns": ns, "picks": [random.choice(range(n)) for n in ns]}
+    with open(os.path.join(GOLDEN, "mt19937.json"), "w") as f:
+        json.dump(out, f)
+    print("mt19937.json written")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    if not ref_import.available():
+        sys.exit("reference not mounted at " + ref_import.REF_ROOT)
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    if a.only in ("", "mt"):
+        golden_mt()
+    if a.only in ("", "frontend"):
+        golden_frontend()
+    if a.only in ("", "dataset"):
+        golden_dataset()
