@@ -1,0 +1,199 @@
+/*
+ * v3d.h -- C ABI of the B200-native (sm_100a) position-aware video front end.
+ *
+ * The reference (zd11024/Video-3D-LLM) has no FFI seam for this path: its boundary is a set
+ * of Python call signatures.  The host mirror in video-3d-llm_b200/
+ * keeps those signatures and binds the entry points below through ctypes; each entry point
+ * cites the reference interface it replaces (paths relative to the upstream repo root).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host.
+ *   - the caller owns every buffer (inputs, outputs, workspace, tables); the library keeps no
+ *     state besides one-time per-device function attributes.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden sync.
+ *   - return value: V3D_OK or a negative V3D_E_* code; v3d_last_error() gives the message of
+ *     the calling thread's last failure.  Nothing throws or aborts across the ABI.
+ *   - outputs are fully overwritten (including the zero tail channels of the PE).
+ */
+#ifndef V3D_H_
+#define V3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define V3D_VERSION 100 /* 0.1.0 */
+
+enum v3d_status { V3D_OK = 0, V3D_E_ARG = -1, V3D_E_ALIGN = -2, V3D_E_UNSUPPORTED = -3, V3D_E_CUDA = -4 };
+
+/* depth element type: uint16 millimetres as stored in the ScanNet PNGs, int32 as the reference
+ * keeps it after np.int32 (llava/video_utils.py:217), or float32 (its .float(), :230). */
+enum v3d_depth_dtype { V3D_DEPTH_U16 = 0, V3D_DEPTH_I32 = 1, V3D_DEPTH_F32 = 2 };
+/* element type of PE / token buffers */
+enum v3d_dtype { V3D_BF16 = 0, V3D_F16 = 1, V3D_F32 = 2 };
+/* x / voxel_size: IEEE division (torch CPU, the parity target) or x * (1/voxel_size)
+ * (what ATen's CUDA kernel does for a scalar divisor). */
+enum v3d_div_mode { V3D_DIV_IEEE = 0, V3D_DIV_RECIPROCAL = 1 };
+/* per-patch pooling of the coordinates, selected by substring of
+ * world_position_embedding_type (llava/model/llava_arch.py:395-407). */
+enum v3d_pool_mode { V3D_POOL_AVG = 0, V3D_POOL_MINMAX = 1, V3D_POOL_SAMPLE9 = 2, V3D_POOL_SAMPLE5 = 3, V3D_POOL_SAMPLE1 = 4 };
+enum v3d_pe_mode { V3D_PE_NONE = 0, V3D_PE_SINE3D = 1 };
+
+typedef void* v3d_stream_t;
+
+int v3d_version(void);
+const char* v3d_last_error(void);
+/* number of points per token for a pool mode: avg 1, minmax 2, sample9/5/1 -> 9/5/1 */
+int v3d_pool_points(int pool_mode);
+
+/* ---- unprojection ------------------------------------------------------------------------
+ * Replaces llava/video_utils.py:38-68 `unproject(intrinsics, poses, depths)`.
+ *   depth (V,H,W) of depth_dtype; poses, intr (V,4,4) fp32 row-major; depth_scale = 1000.
+ * With row_map/col_map == NULL writes world (V,H,W,3) fp32.  With maps (int32, lengths
+ * out_h/out_w) it writes only the gathered pixels world[v,row_map[r],col_map[c]] as
+ * (V,out_h,out_w,3): the cv2.INTER_NEAREST resize + centre crop of :291-308 fused in.
+ * clamp_lo_hi_host: NULL or 6 floats {lo xyz, hi xyz}: the 'norm' clamp of :232-234. */
+int v3d_unproject(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
+                  float depth_scale, const int32_t* row_map, const int32_t* col_map, int out_h, int out_w,
+                  const float* clamp_lo_hi_host, float* world_out, v3d_stream_t stream);
+
+/* Scene AABB [xmin,xmax,ymin,ymax,zmin,zmax] over every pixel of every frame: the "boundry"
+ * entry of llava/video_utils.py:273-277, computed straight from depth.  out6: 6 floats. */
+int v3d_boundary(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
+                 float depth_scale, const float* clamp_lo_hi_host, float* out6, v3d_stream_t stream);
+
+/* ---- helpers on materialised coordinates (API parity with the reference's call structure) --
+ * v3d_pool_coords replaces llava/model/llava_arch.py:213-223 `average_coordinate_in_patch`,
+ * :225-239 `minmax_coordinate_in_patch`, :241-257 `sample_n_points`.
+ *   coords (V,S,S,3) fp32; rows/cols >= grid*patch are dropped (the [:-6,:-6] trim);
+ *   out (V,grid,grid,n_points,3) fp32.  Averages are sequential row-major fp32 sums / p^2,
+ *   bit-identical to ATen's CPU avg_pool2d. */
+int v3d_pool_coords(const float* coords, int V, int S, int patch, int grid, int pool_mode, float* out,
+                    v3d_stream_t stream);
+/* replaces llava/model/llava_arch.py:259-272 `discrete_coords` and
+ * llava/video_utils.py:348-358 `VideoProcessor.discrete_point`:
+ *   out = rint((min(max(c, lo), hi) - lo) / voxel), n_points*3 floats.  has_range = 0 skips
+ *   the clamp and the shift (discrete_point with min/max_xyz_range None). */
+int v3d_discretize(const float* coords, size_t n_points, const float* min_xyz_host, const float* max_xyz_host,
+                   int has_range, float voxel_size, int div_mode, float* out, v3d_stream_t stream);
+
+/* ---- sinusoidal 3D position encoding ------------------------------------------------------
+ * Lookup table behind the discretised PE: for slot s (= point*3 + axis) and
+ * integer coordinate r in [0, rows) the nf channels sin/cos(r / dim_t[j]), laid out as
+ * [n_slots][rows+1][Wt] elements of `dtype`, each slot shifted so that 16-byte chunks of the
+ * output row map to 16-byte chunks of the table; row `rows` holds NaN (non-finite input).
+ * dim_t: nf device floats = temperature ** (2*(j//2)/nf) (llava/model/position_encoding.py:24-25;
+ * taken from the caller because torch's pow is not correctly rounded). */
+size_t v3d_pe_table_bytes(int E, int n_points, int rows, int dtype);
+int v3d_pe_table_build(const float* dim_t, int E, int n_points, int rows, int dtype, void* table, v3d_stream_t stream);
+
+/* Replaces llava/model/position_encoding.py:17-49 `PositionEmbeddingSine3D.forward` (+ the add
+ * of llava/model/llava_arch.py:515 when tokens_in != NULL).
+ *   coords (n_tokens, n_points, 3) fp32; out (n_tokens, E) of `dtype`; channels past
+ *   3*nf*n_points are zero.  table/rows: optional LUT (v3d_pe_table_build); integer-valued
+ *   coordinates in [0,rows) are gathered from it, anything else is evaluated directly
+ *   (IEEE x/dim_t, sinf/cosf).  tokens_in (same shape/dtype as out, may alias out) is added
+ *   after the PE has been rounded to `dtype`. */
+int v3d_pe_sine3d(const float* coords, size_t n_tokens, int n_points, int E, const float* dim_t, const void* table,
+                  int rows, int dtype, const void* tokens_in, void* out, v3d_stream_t stream);
+
+/* ---- the fused front end -------------------------------------------------------------------
+ * depth/pose/intrinsics -> unproject -> nearest resample + crop -> per-patch pooling ->
+ * [clamp + discretise] -> sin-3D PE -> [+ tokens] in ONE kernel: the chain
+ * video_utils.py:230,296-308 -> llava_arch.py:396-420 -> position_encoding.py:17-49 ->
+ * llava_arch.py:515.  One CTA per (frame, patch row); depth rows are staged in shared memory
+ * by the TMA unit (cp.async.bulk), pooled sums keep ATen's sequential order. */
+typedef struct v3d_frontend_desc {
+  /* inputs */
+  const void* depth;      /* (n_frames,H,W) */
+  int depth_dtype;        /* v3d_depth_dtype */
+  const float* poses;     /* (n_frames,16) */
+  const float* intr;      /* (n_frames,16) */
+  int n_frames, H, W;
+  float depth_scale;      /* 1000 */
+  /* geometry: dst pixel (r,c) reads depth[row_map[r], col_map[c]]; the first grid*patch
+   * entries of each map are used */
+  const int32_t* row_map;
+  const int32_t* col_map;
+  int src_col_min;        /* smallest / largest source column among col_map[0 .. grid*patch): the */
+  int src_col_max;        /* host knows the maps; they bound the row segment the TMA unit stages */
+  int patch;              /* p */
+  int grid;               /* G: tokens per frame = G*G */
+  int pool_mode;          /* v3d_pool_mode; SAMPLE* need patch 27 / grid 14 */
+  int has_clamp;          /* 'norm': clamp world coords to clamp_lo/hi before pooling */
+  float clamp_lo[3], clamp_hi[3];
+  /* discretisation (the 'discrete' token) */
+  int discrete;
+  float min_xyz[3], max_xyz[3], voxel_size;
+  int div_mode;           /* v3d_div_mode */
+  /* position encoding */
+  int pe_mode;            /* v3d_pe_mode */
+  int E;                  /* embedding size */
+  const float* dim_t;     /* (E / (3*n_points)) floats */
+  const void* table;      /* LUT of v3d_pe_table_build in `dtype`, required when discrete */
+  int table_rows;
+  int dtype;              /* v3d_dtype of tokens_in / pe_out */
+  const void* tokens_in;  /* NULL or (n_frames, G*G, E): fused add; may alias pe_out */
+  void* pe_out;           /* (n_frames, G*G, E); NULL with pe_mode NONE */
+  /* optional side outputs, fp32 */
+  float* pooled_out;      /* (n_frames,G,G,n_points,3) pooled coordinates */
+  float* pe_coords_out;   /* same shape: what the PE was evaluated on (discretised or not) */
+} v3d_frontend_desc;
+
+int v3d_frontend_pe(const v3d_frontend_desc* desc, v3d_stream_t stream);
+
+/* ---- maximum-coverage frame sampler ---------------------------------------------------------
+ * Replaces scripts/3d/preprocessing/max_coverage_sampling.py:39-104 (voxelise + greedy set
+ * cover) for a batch of scenes.  See csrc/v3d_mc.cu. */
+typedef struct v3d_mc_scene {
+  const void* depth;        /* (n_frames,H,W) candidate frames */
+  const float* poses;       /* (n_frames,16) */
+  const float* intr;        /* (n_frames,16) */
+  const int32_t* pc_voxels; /* (n_pc,3) mesh universe, int triples (convert_pcd_to_voxel.py:69-82) */
+  int n_frames;
+  int n_pc;
+  uint64_t seed;            /* random.seed(seed) right before the greedy loop */
+  /* workspace, caller-owned */
+  int32_t* hash_table;      /* 4*hash_slots int32, 16-byte aligned: {i,j,k,index} per slot */
+  int hash_slots;           /* v3d_mc_hash_slots(n_pc): power of two >= 2*n_pc */
+  int pad_;
+  uint32_t* bitsets;        /* (n_frames, words), words = ceil(n_pc/32): frame coverage over pc order */
+  /* output */
+  int32_t* record;          /* V3D_MC_RECORD_INTS int32: order[32], gains[32] (-1 padded), n_picked, n_all, n_sel, 0 */
+} v3d_mc_scene;
+
+#define V3D_MC_MAX_PICK 32
+#define V3D_MC_RECORD_INTS (2 * V3D_MC_MAX_PICK + 4)
+
+/* hash_slots for a universe of n_pc voxels */
+int v3d_mc_hash_slots(int n_pc);
+/* scenes_host: array of n_scenes descriptors in HOST memory (device pointers inside).
+ * scratch: device buffer of at least n_scenes*sizeof(v3d_mc_scene) bytes the descriptors are
+ * staged in (stream-ordered copy).  All scenes share H, W, depth dtype, voxel size. */
+int v3d_mc_sample(const v3d_mc_scene* scenes_host, int n_scenes, int H, int W, int depth_dtype, float depth_scale,
+                  float voxel_size, int div_mode, int max_pick, void* scratch, v3d_stream_t stream);
+/* the two stages separately (tests, profiling) */
+int v3d_mc_voxelize(const v3d_mc_scene* scenes_host, int n_scenes, int H, int W, int depth_dtype, float depth_scale,
+                    float voxel_size, int div_mode, void* scratch, v3d_stream_t stream);
+int v3d_mc_greedy(const v3d_mc_scene* scenes_host, int n_scenes, int max_pick, void* scratch, v3d_stream_t stream);
+/* voxel ids of materialised world coordinates: int(round(w / voxel)) (max_coverage_sampling.py:44-45) */
+int v3d_mc_voxel_ids(const float* world, size_t n_points, float voxel_size, int div_mode, int32_t* ids, v3d_stream_t stream);
+
+/* ---- learned-projection PE (tensor cores) ----------------------------------------------------
+ * Replaces llava/model/position_encoding.py:52-84 `PositionEmbeddingMLP.forward` (+ the add of
+ * llava_arch.py:515): Linear(3,512) -> LayerNorm(512) -> ReLU -> Linear(512,E) (+ tokens).
+ * The 512-wide hidden activations are produced in-kernel and never touch HBM; the 512 -> E
+ * contraction runs on tcgen05 with TMEM accumulators, bias + token add in the epilogue.
+ *   coords (M,3) fp32; w1 (512,3), b1, gamma, beta (512) fp32; w2 (E,512) bf16 row-major
+ *   (nn.Linear weight layout), b2 (E) fp32; tokens_in NULL or (M,E) bf16; out (M,E) bf16. */
+int v3d_pe_mlp(const float* coords, int M, int E, const float* w1, const float* b1, const float* gamma,
+               const float* beta, float ln_eps, const void* w2_bf16, const float* b2, const void* tokens_in,
+               void* out, v3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V3D_H_ */

@@ -1,0 +1,452 @@
+"""GPU: parity of the CUDA path (through the host mirror -> ctypes -> C ABI) against the CPU oracle
+on the same seeded inputs, and against the golden vectors produced by the reference.
+
+Bar (BASELINE.json north_star): integer / index work and fp32 coordinates bit-exact; PE within bf16
+rounding of the reference's fp32 value (sin/cos come from different math libraries, so an element
+may land on the other side of a bf16 tie: we bound the fraction of such elements and their size).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import fixtures
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from video_3d_llm_b200 import cabi, coords as C, mc_sampling, synthetic, video_utils as VU  # noqa: E402
+from video_3d_llm_b200.frontend import FrontEnd  # noqa: E402
+from video_3d_llm_b200.position_encoding import PositionEmbeddingSine3D  # noqa: E402
+
+DEV = torch.device("cuda:0")
+BF16_ULP_TOL = 1  # at most one bf16 ulp on the rare element that flips
+
+
+def bf16_bits(t: torch.Tensor) -> np.ndarray:
+    return t.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+def assert_bf16_close(got_bits: np.ndarray, ref_bits: np.ndarray, max_frac=2e-4):
+    """Equal except for at most max_frac of the elements, which may differ by one bf16 ulp."""
+    assert got_bits.shape == ref_bits.shape
+    diff = got_bits != ref_bits
+    frac = float(diff.mean())
+    assert frac <= max_frac, f"{frac:.3e} of the bf16 elements differ"
+    if diff.any():
+        g = got_bits[diff].astype(np.int32)
+        r = ref_bits[diff].astype(np.int32)
+        # same sign: adjacent bit patterns; across zero (+-tiny) compare values instead
+        same_sign = (g >> 15) == (r >> 15)
+        assert np.all(np.abs(g[same_sign] - r[same_sign]) <= BF16_ULP_TOL)
+        gv, rv = O.bf16_bits_to_f32(got_bits[diff][~same_sign]), O.bf16_bits_to_f32(ref_bits[diff][~same_sign])
+        assert np.all(np.abs(gv - rv) < 1e-6)
+
+
+@pytest.fixture(scope="module")
+def scene():
+    return synthetic.make_scene(11, 3, n_total=40, device="cpu")
+
+
+@pytest.fixture(scope="module")
+def G(golden_dir):
+    return np.load(os.path.join(golden_dir, "frontend.npz"))
+
+
+def _dev(sc):
+    return sc.depth.to(DEV), sc.poses.to(DEV), sc.intrinsics.to(DEV)
+
+
+# ---------------------------------------------------------------------------------------------
+# unprojection
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["u16", "i32", "f32"])
+def test_unproject_bit_exact(scene, dtype):
+    d, p, k = _dev(scene)
+    du = scene.depth_u16()
+    if dtype == "i32":
+        d = torch.from_numpy(du.astype(np.int32)).to(DEV)
+    elif dtype == "f32":
+        d = torch.from_numpy(du.astype(np.float32)).to(DEV)
+    got = VU.unproject(k, p, d).cpu().numpy()
+    ref = O.unproject(scene.intrinsics.numpy(), scene.poses.numpy(), du)
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_unproject_golden(G):
+    sc = synthetic.make_scene(0, 2, n_total=30, device="cpu")
+    got = VU.unproject(sc.intrinsics.to(DEV), sc.poses.to(DEV), sc.depth.to(DEV)).cpu().numpy()
+    np.testing.assert_array_equal(got[:, ::37, ::41], G["world_sample"])
+    import hashlib
+    assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == str(G["world_sha"])
+
+
+def test_unproject_accepts_cpu_inputs_and_odd_shapes():
+    sc = synthetic.make_scene(3, 2, n_total=9, H=37, W=53, device="cpu")  # W*2 not a multiple of 16, sizes not /4
+    got = VU.unproject(sc.intrinsics, sc.poses, sc.depth)
+    assert got.is_cuda and got.shape == (2, 37, 53, 3)
+    np.testing.assert_array_equal(got.cpu().numpy(), O.unproject(sc.intrinsics.numpy(), sc.poses.numpy(), sc.depth_u16()))
+
+
+def test_unproject_non_rigid_pose_and_nonfinite(scene):
+    d, p, k = _dev(scene)
+    p = p.clone()
+    p[0, 3] = torch.tensor([0.01, -0.02, 0.03, 1.5], device=DEV)  # projective bottom row -> true division by w
+    p[1, 0, 3] = float("inf")
+    got = VU.unproject(k, p, d).cpu().numpy()
+    ref = O.unproject(scene.intrinsics.numpy(), p.cpu().numpy(), scene.depth_u16())
+    np.testing.assert_array_equal(got, ref)  # NaN/Inf compare equal position-wise in assert_array_equal
+
+
+def test_unproject_resampled_and_clamped(scene):
+    d, p, k = _dev(scene)
+    from video_3d_llm_b200 import geometry
+    rm, cm = geometry.resample_maps(480, 640, 384, "center_crop", DEV)
+    lo, hi = [-1.0, -1.5, 0.2], [1.2, 1.0, 2.0]
+    got = VU.unproject(k, p, d, row_map=rm, col_map=cm, clamp=(lo, hi)).cpu().numpy()
+    world = O.clamp(O.unproject(scene.intrinsics.numpy(), scene.poses.numpy(), scene.depth_u16()), lo, hi)
+    orm, ocm = O.resample_maps(480, 640)
+    np.testing.assert_array_equal(got, O.resample(world, orm, ocm))
+
+
+def test_boundary(scene):
+    d, p, k = _dev(scene)
+    got = VU.boundary(k, p, d).cpu().numpy()
+    ref = O.boundary(O.unproject(scene.intrinsics.numpy(), scene.poses.numpy(), scene.depth_u16()))
+    np.testing.assert_array_equal(got, ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers on materialised coordinates
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def coords384(scene):
+    world = O.unproject(scene.intrinsics.numpy(), scene.poses.numpy(), scene.depth_u16())
+    rm, cm = O.resample_maps(480, 640)
+    return O.resample(world, rm, cm)
+
+
+@pytest.mark.parametrize("p", [27, 14])
+def test_pool_helpers_bit_exact(coords384, p):
+    ct = torch.from_numpy(coords384).to(DEV)
+    np.testing.assert_array_equal(C.average_coordinate_in_patch(ct, p).cpu().numpy(), O.average_coordinate_in_patch(coords384, p))
+    np.testing.assert_array_equal(C.minmax_coordinate_in_patch(ct, p).cpu().numpy(), O.minmax_coordinate_in_patch(coords384, p))
+
+
+@pytest.mark.parametrize("n", [9, 5, 1])
+def test_sample_n_points(coords384, n):
+    ct = torch.from_numpy(coords384).to(DEV)
+    np.testing.assert_array_equal(C.sample_n_points(ct, n).cpu().numpy(), O.sample_n_points(coords384, n))
+
+
+def test_pool_helpers_golden(G):
+    sc = synthetic.make_scene(0, 2, n_total=30, device="cpu")
+    from video_3d_llm_b200 import geometry
+    rm, cm = geometry.resample_maps(480, 640, 384, "center_crop", DEV)
+    ct = VU.unproject(sc.intrinsics, sc.poses, sc.depth, row_map=rm, col_map=cm)
+    np.testing.assert_array_equal(C.average_coordinate_in_patch(ct, 27).cpu().numpy(), G["avg27"])
+    np.testing.assert_array_equal(C.average_coordinate_in_patch(ct, 14).cpu().numpy(), G["avg14"])
+    np.testing.assert_array_equal(C.minmax_coordinate_in_patch(ct, 27).cpu().numpy(), G["minmax27"])
+    np.testing.assert_array_equal(C.sample_n_points(ct, 9).cpu().numpy(), G["sample9"])
+    np.testing.assert_array_equal(C.discrete_coords(torch.from_numpy(G["avg27"]).to(DEV)).cpu().numpy(), G["disc27"])
+
+
+def test_pool_nan_propagation():
+    c = np.random.default_rng(0).standard_normal((1, 384, 384, 3)).astype(np.float32)
+    c[0, 30, 40, 1] = np.nan
+    c[0, 100, 200, 2] = np.inf
+    ct = torch.from_numpy(c).to(DEV)
+    np.testing.assert_array_equal(C.average_coordinate_in_patch(ct, 27).cpu().numpy(), O.average_coordinate_in_patch(c, 27))
+    np.testing.assert_array_equal(C.minmax_coordinate_in_patch(ct, 27).cpu().numpy(), O.minmax_coordinate_in_patch(c, 27))
+
+
+def test_discretize(G):
+    x = np.random.default_rng(1).uniform(-20, 20, (5000, 3)).astype(np.float32)
+    x[:6] = G["disc_stress_in"]
+    xt = torch.from_numpy(x).to(DEV)
+    np.testing.assert_array_equal(C.discrete_coords(xt).cpu().numpy(), O.discrete_coords(x))
+    np.testing.assert_array_equal(C.discrete_coords(xt[:6]).cpu().numpy(), G["disc_stress_out"])
+    np.testing.assert_array_equal(C.discrete_coords(xt, div_mode=cabi.DIV_RECIPROCAL).cpu().numpy(),
+                                  O.discrete_coords(x, div_mode=O.DIV_RECIPROCAL))
+    got = C.discrete_coords(xt, min_xyz_range=None, max_xyz_range=None).cpu().numpy()
+    np.testing.assert_array_equal(got, np.rint(x / np.float32(0.1)))
+    # dtype follows the input like the reference
+    assert C.discrete_coords(xt.half()).dtype == torch.float16
+
+
+# ---------------------------------------------------------------------------------------------
+# sin-3D PE
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("E,n_points", [(3584, 1), (1152, 1), (1155, 1), (3584, 9), (3584, 2), (96, 1)])
+def test_pe_module_discrete_inputs(E, n_points):
+    rng = np.random.default_rng(E + n_points)
+    shape = (2, 50, 3) if n_points == 1 else (2, 50, n_points, 3)
+    x = np.stack([rng.integers(0, 301, shape[:-1]), rng.integers(0, 301, shape[:-1]), rng.integers(0, 101, shape[:-1])], -1).astype(np.float32)
+    mod = PositionEmbeddingSine3D(E, n_points=n_points)
+    ref = O.pe_sine3d(x, E, n_points=n_points)
+    got32 = mod(torch.from_numpy(x).to(DEV))
+    assert got32.dtype == torch.float32 and got32.shape == ref.shape
+    np.testing.assert_allclose(got32.cpu().numpy(), ref, rtol=0, atol=5e-7)
+    gotbf = mod(torch.from_numpy(x).to(DEV).to(torch.bfloat16))  # bf16 inputs: integers above 256 are not representable
+    xb = torch.from_numpy(x).to(torch.bfloat16).float().numpy()
+    assert_bf16_close(bf16_bits(gotbf), O.f32_to_bf16_bits(O.pe_sine3d(xb, E, n_points=n_points)))
+    used = 3 * n_points * (E // (3 * n_points))
+    assert torch.all(got32[..., used:] == 0)
+
+
+def test_pe_module_continuous_and_special_inputs():
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-15, 15, (2, 64, 3)).astype(np.float32)
+    x[0, 0] = [np.nan, 3.0, 1000.0]  # NaN slot, table slot, beyond-table slot
+    x[0, 1] = [-4.0, 0.5, 300.0]
+    mod = PositionEmbeddingSine3D(3584)
+    got = mod(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    ref = O.pe_sine3d(x, 3584)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(ref), rtol=0, atol=2e-6)
+
+
+def test_pe_module_fused_add():
+    rng = np.random.default_rng(6)
+    x = rng.integers(0, 300, (2, 196, 3)).astype(np.float32)
+    tokens = synthetic.make_tokens(3, 2, 196, 3584)
+    mod = PositionEmbeddingSine3D(3584)
+    got = mod(torch.from_numpy(x).to(DEV).to(torch.bfloat16), add_to=tokens.to(DEV))
+    xb = torch.from_numpy(x).to(torch.bfloat16).float().numpy()
+    ref = O.add_pe_bf16(bf16_bits(tokens), O.pe_sine3d(xb, 3584))
+    assert_bf16_close(bf16_bits(got), ref, max_frac=5e-4)
+
+
+def test_pe_golden(G):
+    mod = PositionEmbeddingSine3D(3584)
+    got = mod(torch.from_numpy(G["disc27"].reshape(2, 196, 3)).to(DEV))
+    np.testing.assert_allclose(got[:, ::13].cpu().numpy(), G["pe3584_sel"], rtol=0, atol=5e-7)
+    got = PositionEmbeddingSine3D(1155)(torch.from_numpy(G["disc14"].reshape(2, 729, 3)).to(DEV))
+    np.testing.assert_allclose(got[:, ::37].cpu().numpy(), G["pe1155_sel"], rtol=0, atol=5e-7)
+    got = PositionEmbeddingSine3D(3584, n_points=9)(torch.from_numpy(G["disc_sample9"].reshape(2, 196, 9, 3)).to(DEV))
+    np.testing.assert_allclose(got[:, ::13].cpu().numpy(), G["pe3584_n9_sel"], rtol=0, atol=5e-7)
+    got = PositionEmbeddingSine3D(3584)(torch.from_numpy(G["avg27"].reshape(2, 196, 3)).to(DEV))
+    np.testing.assert_allclose(got[:, ::13].cpu().numpy(), G["pe3584_cont_sel"], rtol=0, atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# the fused kernel
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("patch,E", [(27, 3584), (14, 1152)])
+@pytest.mark.parametrize("add", [False, True])
+def test_fused_frontend_default_recipe(scene, patch, E, add):
+    d, p, k = _dev(scene)
+    fe = FrontEnd(device=DEV, patch_size=patch, embedding_size=E)
+    n_tok = fe.tokens_per_frame
+    tokens = synthetic.make_tokens(11, 3, n_tok, E) if add else None
+    out, pooled, pe_coords = fe(d, p, k, tokens=None if tokens is None else tokens.to(DEV), want_coords=True)
+    ref = O.frontend(scene.depth_u16(), scene.poses.numpy(), scene.intrinsics.numpy(), patch_size=patch, embedding_size=E,
+                     tokens_bf16_bits=None if tokens is None else bf16_bits(tokens))
+    np.testing.assert_array_equal(pooled.cpu().numpy(), ref["pooled"])
+    np.testing.assert_array_equal(pe_coords.cpu().numpy().reshape(3, n_tok, 3), ref["pe_coords"])
+    assert_bf16_close(bf16_bits(out), ref["tokens_out"] if add else ref["pe_bf16"], max_frac=5e-4)
+
+
+def test_fused_in_place_add(scene):
+    d, p, k = _dev(scene)
+    fe = FrontEnd(device=DEV, patch_size=14, embedding_size=1152)
+    tokens = synthetic.make_tokens(12, 3, 729, 1152).to(DEV)
+    expect = fe(d, p, k, tokens=tokens)
+    buf = tokens.clone()
+    got = fe(d, p, k, tokens=buf, out=buf)
+    assert got.data_ptr() == buf.data_ptr()
+    assert torch.equal(got.view(torch.int16), expect.view(torch.int16))
+
+
+@pytest.mark.parametrize("kind,n_points", [("minmax-discrete-sin3d", 2), ("sample9-discrete-sin3d", 9), ("sample5-discrete-sin3d", 5),
+                                           ("sample1-discrete-sin3d", 1), ("avg-sin3d", 1), ("minmax-sin3d", 2)])
+def test_fused_frontend_variants(scene, kind, n_points):
+    d, p, k = _dev(scene)
+    fe = FrontEnd(device=DEV, patch_size=27, embedding_size=3584, world_position_embedding_type=kind)
+    out, pooled, pe_coords = fe(d, p, k, want_coords=True)
+    pool = kind.split("-")[0]
+    ref = O.frontend(scene.depth_u16(), scene.poses.numpy(), scene.intrinsics.numpy(), patch_size=27, embedding_size=3584,
+                     pool=pool, discrete="discrete" in kind)
+    np.testing.assert_array_equal(pooled.cpu().numpy(), ref["pooled"])
+    np.testing.assert_array_equal(pe_coords.cpu().numpy().reshape(ref["pe_coords"].shape), ref["pe_coords"])
+    if "discrete" in kind:
+        assert_bf16_close(bf16_bits(out), ref["pe_bf16"], max_frac=5e-4)
+    else:
+        got = out.float().cpu().numpy()
+        np.testing.assert_allclose(got, O.bf16_bits_to_f32(ref["pe_bf16"]), rtol=0, atol=1.0 / 128)
+        assert float(np.mean(bf16_bits(out) != ref["pe_bf16"])) < 2e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_fused_frontend_other_dtypes(scene, dtype):
+    d, p, k = _dev(scene)
+    fe = FrontEnd(device=DEV, patch_size=27, embedding_size=3584, dtype=dtype)
+    out = fe(d, p, k)
+    ref = O.frontend(scene.depth_u16(), scene.poses.numpy(), scene.intrinsics.numpy(), patch_size=27, embedding_size=3584)
+    if dtype == torch.float32:
+        np.testing.assert_allclose(out.cpu().numpy(), ref["pe_f32"], rtol=0, atol=5e-7)
+    else:
+        np.testing.assert_allclose(out.float().cpu().numpy(), ref["pe_f32"], rtol=0, atol=1e-3)
+
+
+def test_fused_frontend_norm_clamp_and_resize_strategy(scene):
+    d, p, k = _dev(scene)
+    lo, hi = [-1.0, -1.5, 0.2], [1.2, 1.0, 2.0]
+    fe = FrontEnd(device=DEV, patch_size=27, embedding_size=3584, strategy="resize")
+    out, pooled, pe_coords = fe(d, p, k, clamp=(lo, hi), want_coords=True)
+    ref = O.frontend(scene.depth_u16(), scene.poses.numpy(), scene.intrinsics.numpy(), patch_size=27, embedding_size=3584,
+                     strategy="resize", clamp_lo=lo, clamp_hi=hi)
+    np.testing.assert_array_equal(pooled.cpu().numpy(), ref["pooled"])
+    assert_bf16_close(bf16_bits(out), ref["pe_bf16"], max_frac=5e-4)
+
+
+@pytest.mark.parametrize("depth_kind", ["i32", "f32", "u16_unaligned_width"])
+def test_fused_frontend_depth_dtypes_and_non_tma_path(depth_kind):
+    if depth_kind == "u16_unaligned_width":
+        sc = synthetic.make_scene(4, 2, n_total=10, H=481, W=643, device="cpu")  # W*2 % 16 != 0 -> plain-load variant
+    else:
+        sc = synthetic.make_scene(4, 2, n_total=10, device="cpu")
+    du = sc.depth_u16()
+    d = sc.depth
+    if depth_kind == "i32":
+        d = torch.from_numpy(du.astype(np.int32))
+    elif depth_kind == "f32":
+        d = torch.from_numpy(du.astype(np.float32))
+    H, W = du.shape[1:]
+    fe = FrontEnd(device=DEV, H=H, W=W, patch_size=14, embedding_size=1152)
+    out, pooled, _ = fe(d.to(DEV), sc.poses.to(DEV), sc.intrinsics.to(DEV), want_coords=True)
+    ref = O.frontend(du, sc.poses.numpy(), sc.intrinsics.numpy(), patch_size=14, embedding_size=1152)
+    np.testing.assert_array_equal(pooled.cpu().numpy(), ref["pooled"])
+    assert_bf16_close(bf16_bits(out), ref["pe_bf16"], max_frac=5e-4)
+
+
+def test_fused_frontend_golden(G):
+    """Against outputs of the reference itself (tests/golden/frontend.npz)."""
+    sc = synthetic.make_scene(0, 2, n_total=30, device="cpu")
+    tokens = synthetic.make_tokens(0, 2, 196, 3584)
+    fe = FrontEnd(device=DEV, patch_size=27, embedding_size=3584)
+    out, pooled, pe_coords = fe(sc.depth.to(DEV), sc.poses.to(DEV), sc.intrinsics.to(DEV), tokens=tokens.to(DEV), want_coords=True)
+    np.testing.assert_array_equal(pooled.cpu().numpy(), G["avg27"])
+    np.testing.assert_array_equal(pe_coords.cpu().numpy(), G["disc27"])
+    assert_bf16_close(bf16_bits(out[:, ::13]), O.f32_to_bf16_bits(G["added3584_sel"]), max_frac=5e-4)
+    fe14 = FrontEnd(device=DEV, patch_size=14, embedding_size=1152)
+    out14, pooled14, pc14 = fe14(sc.depth.to(DEV), sc.poses.to(DEV), sc.intrinsics.to(DEV), want_coords=True)
+    np.testing.assert_array_equal(pooled14.cpu().numpy(), G["avg14"])
+    np.testing.assert_array_equal(pc14.cpu().numpy(), G["disc14"])
+    assert_bf16_close(bf16_bits(out14[:, ::37]), O.f32_to_bf16_bits(G["pe1152_sel"]), max_frac=5e-4)
+
+
+def test_fused_full_size_properties():
+    """BASELINE config 2 size (16 scenes x 32 frames, 27x27 grid, E=1152): properties that do not need
+    the oracle at full size -- linearity of the add, determinism, agreement with the split path."""
+    scenes = [synthetic.make_scene(100 + s, 32, n_total=300, device=DEV) for s in range(16)]
+    depth = torch.cat([s.depth for s in scenes])
+    poses = torch.cat([s.poses for s in scenes])
+    intr = torch.cat([s.intrinsics for s in scenes])
+    fe = FrontEnd(device=DEV, patch_size=14, embedding_size=1152)
+    pe, pooled, pe_coords = fe(depth, poses, intr, want_coords=True)
+    assert pe.shape == (512, 729, 1152)
+    assert torch.equal(pe.view(torch.int16), fe(depth, poses, intr).view(torch.int16))  # deterministic
+    zeros = torch.zeros_like(pe)
+    assert torch.equal(fe(depth, poses, intr, tokens=zeros).view(torch.int16), pe.view(torch.int16))  # PE + 0 == PE
+    tok = torch.randn(pe.shape, device=DEV, dtype=torch.bfloat16)
+    fused = fe(depth, poses, intr, tokens=tok)
+    assert torch.equal(fused.view(torch.int16), (tok + pe).view(torch.int16))  # fused add == torch's bf16 add
+    # split path: the stand-alone PE kernel on the discretised coordinates gives the same rows
+    pe3 = PositionEmbeddingSine3D(1152)(pe_coords.reshape(512, 729, 3))
+    assert torch.equal(pe3.to(torch.bfloat16).view(torch.int16), pe.view(torch.int16))
+    # first scene against the oracle
+    s0 = scenes[0]
+    ref = O.frontend(s0.depth_u16(), s0.poses.cpu().numpy(), s0.intrinsics.cpu().numpy(), patch_size=14, embedding_size=1152)
+    np.testing.assert_array_equal(pooled[:32].cpu().numpy(), ref["pooled"])
+    assert_bf16_close(bf16_bits(pe[:32]), ref["pe_bf16"], max_frac=5e-4)
+
+
+def test_errors_are_reported_not_swallowed(scene):
+    d, p, k = _dev(scene)
+    with pytest.raises(RuntimeError):
+        FrontEnd(device="cpu")
+    with pytest.raises(RuntimeError):
+        C.average_coordinate_in_patch(torch.zeros(1, 384, 384, 3))  # CPU tensor: no CPU path
+    fe = FrontEnd(device=DEV, patch_size=27, embedding_size=3584)
+    with pytest.raises(ValueError):
+        fe(d[:, :100], p, k)
+    with pytest.raises(ValueError):
+        fe(d, p, k, tokens=torch.zeros(3, 196, 3584, device=DEV))  # wrong dtype
+    with pytest.raises(NotImplementedError):
+        PositionEmbeddingSine3D(12)(torch.zeros(1, 4, 3, device=DEV))  # nf < 8 unsupported, reported as such
+    lib = cabi.load()
+    assert lib.v3d_unproject(None, 0, None, None, 1, 1, 1, 1000.0, None, None, 0, 0, None, None, None) == cabi.V3D_E_ARG
+    assert b"null pointer" in lib.v3d_last_error()
+
+
+# ---------------------------------------------------------------------------------------------
+# MC sampler
+# ---------------------------------------------------------------------------------------------
+def _mc_scene(seed, n_frames, H, W):
+    sc = synthetic.make_scene(seed, n_frames, n_total=n_frames, H=H, W=W, device="cpu")
+    pc = synthetic.mesh_voxels(sc.room, sc.boxes, seed)
+    return sc, pc
+
+
+def test_mc_voxel_ids(scene):
+    world = O.unproject(scene.intrinsics.numpy(), scene.poses.numpy(), scene.depth_u16())[:1]
+    world[0, 0, 0] = [np.nan, np.inf, -3e12]
+    for mode_o, mode_c in ((O.DIV_IEEE, cabi.DIV_IEEE), (O.DIV_RECIPROCAL, cabi.DIV_RECIPROCAL)):
+        got = mc_sampling.voxel_ids(torch.from_numpy(world).to(DEV), 0.1, mode_c).cpu().numpy()
+        np.testing.assert_array_equal(got, O.mc_voxel_ids(world, 0.1, mode_o))
+
+
+@pytest.mark.parametrize("seed,n_frames,H,W", [(21, 40, 120, 160), (22, 9, 480, 640), (23, 70, 60, 80)])
+def test_mc_sampler_bit_exact_vs_oracle(seed, n_frames, H, W):
+    sc, pc = _mc_scene(seed, n_frames, H, W)
+    sampler = mc_sampling.MCSampler(device=DEV)
+    plan = sampler.plan([{"depth": sc.depth.to(DEV), "poses": sc.poses.to(DEV), "intrinsics": sc.intrinsics.to(DEV),
+                          "pc_voxels": torch.from_numpy(pc).to(DEV), "seed": seed}])
+    res = sampler.decode(sampler.run(plan))[0]
+    order, gains, n_all, n_sel, bs = O.mc_sample_scene(sc.depth_u16(), sc.poses.numpy(), sc.intrinsics.numpy(), pc, 0.1, 32, seed)
+    np.testing.assert_array_equal(sampler.bitsets(plan, 0), bs)  # voxel coverage bit-exact
+    assert res["order"] == list(order)  # including MT19937 tie-breaks
+    assert res["gains"] == list(gains)
+    assert (res["n_all"], res["n_sel"]) == (n_all, n_sel)
+
+
+def test_mc_sampler_batch_ragged_and_edge_cases():
+    specs = [(31, 33, 120, 160), (32, 5, 120, 160), (33, 1, 120, 160), (34, 48, 120, 160)]
+    scenes, refs = [], []
+    for i, (seed, n, H, W) in enumerate(specs):
+        sc, pc = _mc_scene(seed, n, H, W)
+        if i == 1:
+            pc = pc[:0]  # empty universe: every gain is 0, all picks are tie-breaks
+        if i == 3:
+            pc = np.concatenate([pc, pc[:50]])  # duplicated voxels behave like a set
+        scenes.append({"depth": sc.depth.to(DEV), "poses": sc.poses.to(DEV), "intrinsics": sc.intrinsics.to(DEV),
+                       "pc_voxels": torch.from_numpy(np.ascontiguousarray(pc)).to(DEV), "seed": 2**40 + seed})
+        upc = pc if i != 3 else pc[: len(pc) - 50]
+        refs.append(O.mc_sample_scene(sc.depth_u16(), sc.poses.numpy(), sc.intrinsics.numpy(), upc, 0.1, 32, 2**40 + seed))
+    res = mc_sampling.MCSampler(device=DEV).sample(scenes)
+    for r, (order, gains, n_all, n_sel, _) in zip(res, refs):
+        assert r["order"] == list(order) and r["gains"] == list(gains) and (r["n_all"], r["n_sel"]) == (n_all, n_sel)
+
+
+def test_mc_sampler_golden(golden_dir):
+    """Against the output of the reference's own max_coverage_sampling.main (tests/golden/dataset.json)."""
+    with open(os.path.join(golden_dir, "dataset.json")) as f:
+        D = json.load(f)
+    for name, meta in D["scenes"].items():
+        sc = synthetic.make_scene(meta["seed"], meta["n_total"], n_total=meta["n_total"], H=meta["H"], W=meta["W"], device="cpu")
+        pc = synthetic.mesh_voxels(sc.room, sc.boxes, meta["seed"])
+        cand = fixtures.mc_candidates(meta["n_total"])
+        poses = torch.from_numpy(fixtures.disk_poses(sc))[cand]
+        gold = next(s for s in D["select_frames"] if s["video_id"].endswith(name))
+        res = mc_sampling.MCSampler(device=DEV).sample([{"depth": sc.depth[cand].to(DEV), "poses": poses.to(DEV),
+                                                         "intrinsics": sc.intrinsics[cand].to(DEV),
+                                                         "pc_voxels": torch.from_numpy(pc).to(DEV), "seed": meta["seed"]}])[0]
+        assert [cand[i] for i in res["order"]] == [int(f.split("/")[-1].split(".")[0]) // 10 for f in gold["frame_files"]]
+        assert res["gains"] == gold["voxel_nums"]
+        assert (res["n_all"], res["n_sel"]) == (gold["num_all_voxels"], gold["num_select_voxels"])

@@ -1,0 +1,90 @@
+"""Mirror of the coordinate helpers of LlavaMetaForCausalLM (llava/model/llava_arch.py:213-272)
+on the CUDA library: same names, arguments and output shapes/dtypes.
+
+Each helper accepts either a materialised coordinate tensor (V,S,S,3) on a CUDA device, as the
+reference passes it, or a `LazyWorldCoords` handle (video_utils.py) over raw depth/pose/intrinsics,
+in which case the pooled coordinates come straight out of the fused kernel and the
+(V,384,384,3) tensor is never built.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import cabi
+
+_POOL = {"avg": cabi.POOL_AVG, "minmax": cabi.POOL_MINMAX, "sample9": cabi.POOL_SAMPLE9,
+         "sample5": cabi.POOL_SAMPLE5, "sample1": cabi.POOL_SAMPLE1}
+
+
+def _pool(world_coords, patch_size: int, mode: str, n_points: int, trim: int = 6):
+    from .video_utils import LazyWorldCoords
+
+    if isinstance(world_coords, LazyWorldCoords):
+        return world_coords.pooled(patch_size, mode, trim)
+    cabi.require_cuda(world_coords, "world_coords")
+    lib = cabi.load()
+    V, H, W, D = world_coords.size()
+    if H != W or D != 3:
+        raise ValueError(f"world_coords must be (V,S,S,3), got {tuple(world_coords.shape)}")
+    grid = (H - trim) // patch_size
+    src = world_coords.detach().to(torch.float32).contiguous()
+    shape = (V, grid, grid, 3) if n_points == 1 else (V, grid, grid, n_points, 3)
+    out = torch.empty(shape, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        cabi.check(lib.v3d_pool_coords(src.data_ptr(), V, H, patch_size, grid, _POOL[mode], out.data_ptr(),
+                                       cabi.stream_ptr(src.device)), "v3d_pool_coords")
+    return out.to(world_coords.dtype)
+
+
+def average_coordinate_in_patch(world_coords, patch_size=27):
+    """llava/model/llava_arch.py:213-223: (V,384,384,3) -> (V,G,G,3), G = 378 // patch_size."""
+    return _pool(world_coords, patch_size, "avg", 1)
+
+
+def minmax_coordinate_in_patch(world_coords, patch_size=27):
+    """llava/model/llava_arch.py:225-239: -> (V,G,G,2,3) with [...,0,:] the min and [...,1,:] the max."""
+    return _pool(world_coords, patch_size, "minmax", 2)
+
+
+def sample_n_points(world_coords, n_points=9):
+    """llava/model/llava_arch.py:241-257: -> (V,14,14,n,3) ((V,14,14,3) for n_points == 1)."""
+    if n_points not in (9, 5, 1):
+        raise NotImplementedError
+    return _pool(world_coords, 27, f"sample{n_points}", n_points)
+
+
+def discrete_coords(world_coords, xyz_min=None, *, voxel_size=0.1, min_xyz_range=(-15, -15, -5), max_xyz_range=(15, 15, 5),
+                    div_mode: int = cabi.DIV_IEEE):
+    """llava/model/llava_arch.py:259-272: round((clamp(c, min, max) - min) / voxel_size); the result
+    stays floating point and detached; `xyz_min` is accepted and ignored like upstream."""
+    cabi.require_cuda(world_coords, "world_coords")
+    lib = cabi.load()
+    if world_coords.shape[-1] != 3:
+        raise ValueError("last dimension must be 3")
+    src = world_coords.detach().to(torch.float32).contiguous()
+    out = torch.empty_like(src)
+    has_range = min_xyz_range is not None and max_xyz_range is not None
+    lo = cabi.host_floats(min_xyz_range) if has_range else None
+    hi = cabi.host_floats(max_xyz_range) if has_range else None
+    with torch.cuda.device(src.device):
+        cabi.check(lib.v3d_discretize(src.data_ptr(), src.numel() // 3, lo, hi, int(has_range), float(voxel_size), div_mode,
+                                      out.data_ptr(), cabi.stream_ptr(src.device)), "v3d_discretize")
+    return out.to(world_coords.dtype)
+
+
+def parse_world_position_embedding_type(kind: str) -> dict:
+    """Substring semantics of llava/model/llava_arch.py:51-63, 395-429."""
+    if "avg" in kind:
+        pool, n_points = "avg", 1
+    elif "sample9" in kind:
+        pool, n_points = "sample9", 9
+    elif "sample5" in kind:
+        pool, n_points = "sample5", 5
+    elif "sample1" in kind:
+        pool, n_points = "sample1", 1
+    elif "minmax" in kind:
+        pool, n_points = "minmax", 2
+    else:
+        pool, n_points = None, 1
+    return {"pool": pool, "n_points": n_points, "discrete": "discrete" in kind, "sin3d": "sin3d" in kind,
+            "mlp": "mlp" in kind, "mrope": "mrope" in kind}

@@ -1,0 +1,923 @@
+// v3d_frontend.cu -- unprojection, patch pooling, discretisation, sin-3D position encoding and
+// the fused depth -> PE (+token add) kernel for sm_100a.  C ABI: include/v3d.h.
+//
+// Arithmetic contract: every fp32 step that decides a bit of the
+// reference's result is an explicitly rounded intrinsic (v3d_common.cuh); pooled sums keep
+// ATen's sequential row-major order; PE values are sinf/cosf of an IEEE quotient.
+#include <math_constants.h>
+#include <stdarg.h>
+
+#include "v3d_common.cuh"
+
+namespace v3d {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return V3D_E_CUDA;
+}
+
+static constexpr int kThreads = 256;
+
+// ============================================================================================
+// 1. stand-alone unprojection (API parity with llava/video_utils.py:38-68, optional gather)
+// ============================================================================================
+template <int DT>
+__global__ void __launch_bounds__(kThreads) k_unproject(const void* __restrict__ depth, const float* __restrict__ poses,
+                                                        const float* __restrict__ intr, int V, int H, int W,
+                                                        float depth_scale, const int32_t* __restrict__ row_map,
+                                                        const int32_t* __restrict__ col_map, int OH, int OW, Clamp clamp,
+                                                        float* __restrict__ out) {
+  // each thread: 4 consecutive output pixels; a warp's 384 floats are transposed through
+  // shared memory so that global stores are contiguous float4s.
+  __shared__ __align__(16) float stage[kThreads / 32][4 * 32 * 3];
+  const size_t total = (size_t)V * OH * OW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t n_groups = (total + 3) / 4;
+  const size_t groups_per_block = kThreads;
+  for (size_t gbase = (size_t)blockIdx.x * groups_per_block; gbase < n_groups; gbase += (size_t)gridDim.x * groups_per_block) {
+    const size_t g = gbase + threadIdx.x;
+    float vals[12];
+    if (g < n_groups) {
+      size_t px = g * 4;
+      int f = (int)(px / ((size_t)OH * OW));
+      int rem = (int)(px - (size_t)f * OH * OW);
+      int r = rem / OW, c = rem - r * OW;
+      Camera cam = load_camera(poses, intr, f);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (px + e < total) {
+          const int sr = row_map ? __ldg(row_map + r) : r;
+          const int sc = col_map ? __ldg(col_map + c) : c;
+          const float d = load_depth<DT>(depth, ((size_t)f * H + sr) * W + sc);
+          unproject_px(cam, d, __fsub_rn((float)sc, cam.cx), __fsub_rn((float)sr, cam.cy), depth_scale, x, y, z);
+          x = apply_clamp(clamp, x, 0);
+          y = apply_clamp(clamp, y, 1);
+          z = apply_clamp(clamp, z, 2);
+          if (++c == OW) {
+            c = 0;
+            if (++r == OH) {
+              r = 0;
+              ++f;
+              if (f < V) cam = load_camera(poses, intr, f);
+            }
+          }
+        }
+        vals[3 * e + 0] = x;
+        vals[3 * e + 1] = y;
+        vals[3 * e + 2] = z;
+      }
+    }
+    float* st = stage[warp];
+    if (g < n_groups) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) st[lane * 12 + k] = vals[k];
+    }
+    __syncwarp();
+    // warp writes floats [3*4*warp_first_group, +384)
+    const size_t warp_first = (gbase + (size_t)warp * 32) * 12;
+    const size_t total_f = total * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int idx = (k * 32 + lane) * 4;
+      const size_t o = warp_first + idx;
+      if (o + 4 <= total_f) {
+        *reinterpret_cast<float4*>(out + o) = *reinterpret_cast<const float4*>(st + idx);
+      } else {
+        for (int e = 0; e < 4; ++e)
+          if (o + e < total_f) out[o + e] = st[idx + e];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ============================================================================================
+// 2. scene AABB ("boundry") straight from depth
+// ============================================================================================
+__device__ __forceinline__ int fkey_max(float f) {  // monotone int key, NaN -> INT_MAX
+  if (f != f) return 0x7fffffff;
+  int b = __float_as_int(f);
+  return b >= 0 ? b : (b ^ 0x7fffffff);
+}
+__device__ __forceinline__ int fkey_min(float f) {  // NaN -> INT_MIN
+  if (f != f) return (int)0x80000000;
+  int b = __float_as_int(f);
+  return b >= 0 ? b : (b ^ 0x7fffffff);
+}
+__device__ __forceinline__ float fkey_decode(int k) {
+  if (k == 0x7fffffff || k == (int)0x80000000) return CUDART_NAN_F;
+  return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff));
+}
+
+__global__ void k_boundary_init(int* keys) {
+  if (threadIdx.x < 6) keys[threadIdx.x] = (threadIdx.x & 1) ? fkey_max(-CUDART_INF_F) : fkey_min(CUDART_INF_F);
+}
+__global__ void k_boundary_final(int* keys) {
+  if (threadIdx.x < 6) reinterpret_cast<float*>(keys)[threadIdx.x] = fkey_decode(keys[threadIdx.x]);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kThreads) k_boundary(const void* __restrict__ depth, const float* __restrict__ poses,
+                                                       const float* __restrict__ intr, int V, int H, int W,
+                                                       float depth_scale, Clamp clamp, int* __restrict__ keys) {
+  // one CTA works on rows of one frame at a time: blockIdx -> (frame, row-slab)
+  const int rows_per_cta = 8;
+  const int slabs = (H + rows_per_cta - 1) / rows_per_cta;
+  int mn[3] = {0x7ffffffe, 0x7ffffffe, 0x7ffffffe}, mx[3] = {(int)0x80000001, (int)0x80000001, (int)0x80000001};
+  for (int item = blockIdx.x; item < V * slabs; item += gridDim.x) {
+    const int f = item / slabs, r0 = (item - f * slabs) * rows_per_cta;
+    const Camera cam = load_camera(poses, intr, f);
+    const int r1 = min(r0 + rows_per_cta, H);
+    for (int i = threadIdx.x; i < (r1 - r0) * W; i += kThreads) {
+      const int r = r0 + i / W, c = i - (i / W) * W;
+      float p[3];
+      unproject_px(cam, load_depth<DT>(depth, ((size_t)f * H + r) * W + c), __fsub_rn((float)c, cam.cx),
+                   __fsub_rn((float)r, cam.cy), depth_scale, p[0], p[1], p[2]);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float v = apply_clamp(clamp, p[a], a);
+        mn[a] = min(mn[a], fkey_min(v));
+        mx[a] = max(mx[a], fkey_max(v));
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    for (int o = 16; o; o >>= 1) {
+      mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(keys + 2 * a, mn[a]);
+      atomicMax(keys + 2 * a + 1, mx[a]);
+    }
+  }
+}
+
+// ============================================================================================
+// 3. sin-3D PE building blocks
+// ============================================================================================
+// llava/model/position_encoding.py:27-42: feature j of a coordinate x
+__device__ __forceinline__ float pe_value(float x, int j, const float* __restrict__ dim_t) {
+  const float pos = __fdiv_rn(x, __ldg(dim_t + j));
+  return (j & 1) ? cosf(pos) : sinf(pos);
+}
+
+// Table geometry shared by host and device: slot s covers output channels [s*nf, (s+1)*nf);
+// its table rows start at channel lo_s = floor8(s*nf) and are Wt = ceil8(nf+7) wide.
+__host__ __device__ __forceinline__ int pe_table_width(int nf) { return (nf + 7 + 7) & ~7; }
+
+struct PeGeom {
+  int E, nf, n_slots, cpt;  // cpt = chunks (of 8 channels) per token = ceil(E/8)
+  int rows, Wt;             // table rows (without the NaN row), row width in elements
+};
+
+// per-chunk descriptor: which slots a chunk of 8 channels touches and where in their rows
+struct __align__(8) ChunkDesc {
+  uint8_t s0, s1;   // slot ids, 0xFF = none
+  uint16_t k0;      // element offset of the chunk inside slot s0's table row
+  uint16_t k1;      // ... inside slot s1's row
+  uint16_t pad;
+};
+
+__device__ __forceinline__ ChunkDesc make_chunk_desc(int c8, const PeGeom& g) {
+  ChunkDesc d;
+  const int c = c8 * 8;
+  const int s0 = c / g.nf, s1 = (c + 7) / g.nf;
+  d.s0 = (s0 < g.n_slots) ? (uint8_t)s0 : 0xFF;
+  d.k0 = (uint16_t)(c - ((s0 * g.nf) & ~7));
+  d.s1 = (s1 != s0 && s1 < g.n_slots) ? (uint8_t)s1 : 0xFF;
+  d.k1 = (uint16_t)(c - ((s1 * g.nf) & ~7));
+  d.pad = 0;
+  return d;
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads) k_pe_table(const float* __restrict__ dim_t, PeGeom g, OutT* __restrict__ table) {
+  const size_t total = (size_t)g.n_slots * (g.rows + 1) * g.Wt;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
+    const int k = (int)(i % g.Wt);
+    const int r = (int)((i / g.Wt) % (g.rows + 1));
+    const int s = (int)(i / ((size_t)g.Wt * (g.rows + 1)));
+    const int j = ((s * g.nf) & ~7) + k - s * g.nf;
+    float v = 0.0f;
+    if (j >= 0 && j < g.nf) v = (r == g.rows) ? CUDART_NAN_F : pe_value((float)r, j, dim_t);
+    table[i] = Elem<OutT>::from(v);
+  }
+}
+
+// one chunk = 8 consecutive channels
+template <typename OutT>
+struct alignas(sizeof(OutT) * 8) Chunk {
+  OutT v[8];
+};
+
+template <typename OutT>
+__device__ __forceinline__ Chunk<OutT> chunk_zero() {
+  Chunk<OutT> c;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) c.v[e] = Elem<OutT>::from(0.0f);
+  return c;
+}
+template <typename OutT>
+__device__ __forceinline__ Chunk<OutT> chunk_ldg(const OutT* p) {
+  Chunk<OutT> c;
+  if constexpr (sizeof(OutT) == 2) {
+    *reinterpret_cast<uint4*>(&c) = __ldg(reinterpret_cast<const uint4*>(p));
+  } else {
+    reinterpret_cast<uint4*>(&c)[0] = __ldg(reinterpret_cast<const uint4*>(p));
+    reinterpret_cast<uint4*>(&c)[1] = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  }
+  return c;
+}
+template <typename OutT>
+__device__ __forceinline__ Chunk<OutT> chunk_ld_stream(const OutT* p) {
+  Chunk<OutT> c;
+  if constexpr (sizeof(OutT) == 2) {
+    *reinterpret_cast<uint4*>(&c) = ld_stream_v4(p);
+  } else {
+    reinterpret_cast<uint4*>(&c)[0] = ld_stream_v4(p);
+    reinterpret_cast<uint4*>(&c)[1] = ld_stream_v4(reinterpret_cast<const uint4*>(p) + 1);
+  }
+  return c;
+}
+template <typename OutT>
+__device__ __forceinline__ void chunk_st_stream(OutT* p, const Chunk<OutT>& c) {
+  if constexpr (sizeof(OutT) == 2) {
+    st_stream_v4(p, *reinterpret_cast<const uint4*>(&c));
+  } else {
+    st_stream_v4(p, reinterpret_cast<const uint4*>(&c)[0]);
+    st_stream_v4(reinterpret_cast<uint4*>(p) + 1, reinterpret_cast<const uint4*>(&c)[1]);
+  }
+}
+template <typename OutT>
+__device__ __forceinline__ void chunk_or(Chunk<OutT>& a, const Chunk<OutT>& b) {
+  constexpr int n = sizeof(Chunk<OutT>) / 4;
+#pragma unroll
+  for (int i = 0; i < n; ++i) reinterpret_cast<uint32_t*>(&a)[i] |= reinterpret_cast<const uint32_t*>(&b)[i];
+}
+
+// PE rows of `n_tok` tokens, 8 channels per step.  s_pts: [n_tok][n_slots] coordinates the PE
+// is evaluated on; s_row: same shape, table row (>= 0) or -1 = evaluate directly.
+// out/tokens point at the first token's row; tail chunks of a row whose width is not a
+// multiple of 8 are written element-wise.
+template <typename OutT, int UNROLL>
+__device__ __forceinline__ void stream_pe(const PeGeom& g, const float* __restrict__ dim_t, const OutT* __restrict__ table,
+                                          const float* s_pts, const int* s_row, const ChunkDesc* s_desc, int n_tok,
+                                          const OutT* tokens, OutT* out) {
+  const int total = n_tok * g.cpt;
+  const bool vec_ok = (g.E & 7) == 0;
+  for (int q0 = threadIdx.x; q0 < total; q0 += kThreads * UNROLL) {
+    Chunk<OutT> tv[UNROLL];
+    int tok[UNROLL], c8[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int q = q0 + u * kThreads;
+      tok[u] = q / g.cpt;
+      c8[u] = q - tok[u] * g.cpt;
+      if (tokens != nullptr && vec_ok && q < total) tv[u] = chunk_ld_stream(tokens + (size_t)tok[u] * g.E + c8[u] * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int q = q0 + u * kThreads;
+      if (q >= total) break;
+      const ChunkDesc d = s_desc[c8[u]];
+      Chunk<OutT> pe = chunk_zero<OutT>();
+      const int r0 = (d.s0 != 0xFF) ? s_row[tok[u] * g.n_slots + d.s0] : 0;
+      const int r1 = (d.s1 != 0xFF) ? s_row[tok[u] * g.n_slots + d.s1] : 0;
+      if (r0 >= 0 && r1 >= 0) {
+        if (d.s0 != 0xFF) pe = chunk_ldg(table + ((size_t)d.s0 * (g.rows + 1) + r0) * g.Wt + d.k0);
+        if (d.s1 != 0xFF) chunk_or(pe, chunk_ldg(table + ((size_t)d.s1 * (g.rows + 1) + r1) * g.Wt + d.k1));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int ch = c8[u] * 8 + e;
+          const int s = ch / g.nf;
+          if (s < g.n_slots) pe.v[e] = Elem<OutT>::from(pe_value(s_pts[tok[u] * g.n_slots + s], ch - s * g.nf, dim_t));
+        }
+      }
+      OutT* o = out + (size_t)tok[u] * g.E + c8[u] * 8;
+      if (vec_ok) {
+        if (tokens != nullptr) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            pe.v[e] = Elem<OutT>::from(__fadd_rn(Elem<OutT>::to(tv[u].v[e]), Elem<OutT>::to(pe.v[e])));
+        }
+        chunk_st_stream(o, pe);
+      } else {
+        for (int e = 0; e < 8 && c8[u] * 8 + e < g.E; ++e) {
+          float v = Elem<OutT>::to(pe.v[e]);
+          if (tokens != nullptr) v = __fadd_rn(Elem<OutT>::to(tokens[(size_t)tok[u] * g.E + c8[u] * 8 + e]), v);
+          o[e] = Elem<OutT>::from(tokens != nullptr ? v : Elem<OutT>::to(pe.v[e]));
+        }
+      }
+    }
+  }
+}
+
+// table row for a coordinate: integer-valued in [0,rows) -> that row, NaN -> the NaN row,
+// anything else -> -1 (direct evaluation)
+__device__ __forceinline__ int pe_row_of(float x, int rows, bool have_table) {
+  if (!have_table) return -1;
+  if (x != x) return rows;
+  if (x >= 0.0f && x < (float)rows && x == rintf(x)) return (int)x;
+  return -1;
+}
+
+// stand-alone PE: llava/model/position_encoding.py:17-49 (+ llava_arch.py:515 add)
+static constexpr int kPeTokPerCta = 16;
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads) k_pe_sine3d(const float* __restrict__ coords, size_t n_tokens, PeGeom g,
+                                                        const float* __restrict__ dim_t, const OutT* __restrict__ table,
+                                                        const OutT* tokens, OutT* out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ChunkDesc* s_desc = reinterpret_cast<ChunkDesc*>(smem_raw);
+  float* s_pts = reinterpret_cast<float*>(s_desc + g.cpt);
+  int* s_row = reinterpret_cast<int*>(s_pts + kPeTokPerCta * g.n_slots);
+  for (int i = threadIdx.x; i < g.cpt; i += kThreads) s_desc[i] = make_chunk_desc(i, g);
+  for (size_t t0 = (size_t)blockIdx.x * kPeTokPerCta; t0 < n_tokens; t0 += (size_t)gridDim.x * kPeTokPerCta) {
+    const int n_tok = (int)min((size_t)kPeTokPerCta, n_tokens - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_tok * g.n_slots; i += kThreads) {
+      const float x = __ldg(coords + t0 * g.n_slots + i);
+      s_pts[i] = x;
+      s_row[i] = pe_row_of(x, g.rows, table != nullptr);
+    }
+    __syncthreads();
+    stream_pe<OutT, 4>(g, dim_t, table, s_pts, s_row, s_desc, n_tok, tokens ? tokens + t0 * g.E : nullptr, out + t0 * g.E);
+  }
+}
+
+// ============================================================================================
+// 4. the fused kernel: one CTA per (frame, patch row)
+// ============================================================================================
+struct FusedParams {
+  const void* depth;
+  const float* poses;
+  const float* intr;
+  const float* coords_in;  // FROM_DEPTH == false: (V,S,S,3) materialised coordinates
+  int n_frames, H, W, S;
+  float depth_scale;
+  const int32_t* row_map;
+  const int32_t* col_map;
+  int patch, grid, Sp, Sp_pad;  // Sp = patch*grid columns/rows used
+  int pool_mode, n_points;
+  Clamp clamp;
+  Discretize disc;
+  int pe_mode;
+  PeGeom g;
+  const float* dim_t;
+  const void* table;
+  const void* tokens_in;
+  void* pe_out;
+  float* pooled_out;
+  float* pe_coords_out;
+  // TMA staging: bytes [col_lo_byte, col_lo_byte + span) of each needed depth row
+  int col_lo_byte, span;
+};
+
+__host__ __device__ inline size_t fused_smem_bytes(const FusedParams& p, bool stage_depth) {
+  size_t b = 16;                                              // mbarrier
+  if (stage_depth) b += (size_t)p.patch * p.span;             // depth rows
+  b += (size_t)2 * 3 * p.Sp_pad * sizeof(float);              // double-buffered xyz row
+  b += (size_t)p.grid * 3 * p.n_points * (sizeof(float) + sizeof(int));  // PE coordinates + table rows
+  b = (b + 7) & ~(size_t)7;
+  if (p.pe_mode != V3D_PE_NONE) b += (size_t)p.g.cpt * sizeof(ChunkDesc);
+  return b;
+}
+
+template <int DT, bool FROM_DEPTH, bool USE_TMA, typename OutT>
+__global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kEsz = (DT == V3D_DEPTH_U16) ? 2 : 4;
+  const int t = threadIdx.x;
+  const int f = blockIdx.x / p.grid, gi = blockIdx.x - f * p.grid;
+  const int G = p.grid, P = p.patch, n_slots = 3 * p.n_points;
+
+  // ---- shared memory carve-up
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  unsigned char* s_depth = smem_raw + 16;
+  float* s_row = reinterpret_cast<float*>(s_depth + ((FROM_DEPTH && USE_TMA) ? (size_t)P * p.span : 0));
+  float* s_pts = s_row + 2 * 3 * p.Sp_pad;
+  int* s_tab = reinterpret_cast<int*>(s_pts + G * n_slots);
+  ChunkDesc* s_desc = reinterpret_cast<ChunkDesc*>((reinterpret_cast<uintptr_t>(s_tab + G * n_slots) + 7) & ~(uintptr_t)7);
+
+  // ---- stage the P depth rows of this patch row with the TMA unit
+  if constexpr (FROM_DEPTH && USE_TMA) {
+    if (t == 0) {
+      mbar_init(bar, 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (t < 32) {
+      if (t == 0) mbar_arrive_expect_tx(bar, (uint32_t)(P * p.span));
+      __syncwarp();
+      for (int dy = t; dy < P; dy += 32) {
+        const int sr = __ldg(p.row_map + gi * P + dy);
+        const unsigned char* src =
+            reinterpret_cast<const unsigned char*>(p.depth) + ((size_t)f * p.H + sr) * p.W * kEsz + p.col_lo_byte;
+        tma_bulk_g2s(s_depth + (size_t)dy * p.span, src, (uint32_t)p.span, bar);
+      }
+    }
+  }
+  if (p.pe_mode != V3D_PE_NONE) {
+    for (int i = t; i < p.g.cpt; i += kThreads) s_desc[i] = make_chunk_desc(i, p.g);
+  }
+
+  Camera cam;
+  if constexpr (FROM_DEPTH) cam = load_camera(p.poses, p.intr, f);
+
+  // per-thread column constants: thread t owns dst columns t and (second round, taken from the
+  // top of the block so that the chain warps at the bottom get less unprojection work)
+  int col[2], scol[2];
+  float um[2];
+  col[0] = (t < p.Sp) ? t : -1;
+  col[1] = (kThreads + (kThreads - 1 - t) < p.Sp) ? kThreads + (kThreads - 1 - t) : -1;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    scol[k] = 0;
+    um[k] = 0.f;
+    if (col[k] >= 0) {
+      scol[k] = FROM_DEPTH ? __ldg(p.col_map + col[k]) : col[k];
+      if constexpr (FROM_DEPTH) um[k] = __fsub_rn((float)scol[k], cam.cx);
+    }
+  }
+
+  if constexpr (FROM_DEPTH && USE_TMA) mbar_wait(bar, 0);
+
+  const bool is_sample = p.pool_mode >= V3D_POOL_SAMPLE9;
+  if (!is_sample) {
+    // ---- chains: thread q < 3G owns (axis a = q / G, patch j = q % G)
+    const int q = t;
+    const bool chain = q < 3 * G;
+    const int a = chain ? q / G : 0, j = chain ? q - a * G : 0;
+    float acc = 0.0f, mx = -CUDART_INF_F, mneg = -CUDART_INF_F;
+    for (int dy = 0; dy < P; ++dy) {
+      float* buf = s_row + (dy & 1) * 3 * p.Sp_pad;
+      const int sr = FROM_DEPTH ? __ldg(p.row_map + gi * P + dy) : gi * P + dy;
+      float vm = 0.f;
+      if constexpr (FROM_DEPTH) vm = __fsub_rn((float)sr, cam.cy);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (col[k] < 0) continue;
+        float x, y, z;
+        if constexpr (FROM_DEPTH) {
+          float d;
+          if constexpr (USE_TMA) {
+            const unsigned char* sp = s_depth + (size_t)dy * p.span + (scol[k] * kEsz - p.col_lo_byte);
+            if constexpr (DT == V3D_DEPTH_U16) d = (float)*reinterpret_cast<const uint16_t*>(sp);
+            else if constexpr (DT == V3D_DEPTH_I32) d = (float)*reinterpret_cast<const int32_t*>(sp);
+            else d = *reinterpret_cast<const float*>(sp);
+          } else {
+            d = load_depth<DT>(p.depth, ((size_t)f * p.H + sr) * p.W + scol[k]);
+          }
+          unproject_px(cam, d, um[k], vm, p.depth_scale, x, y, z);
+          x = apply_clamp(p.clamp, x, 0);
+          y = apply_clamp(p.clamp, y, 1);
+          z = apply_clamp(p.clamp, z, 2);
+        } else {
+          const float* src = p.coords_in + (((size_t)f * p.S + sr) * p.S + scol[k]) * 3;
+          x = __ldg(src);
+          y = __ldg(src + 1);
+          z = __ldg(src + 2);
+        }
+        buf[col[k]] = x;
+        buf[p.Sp_pad + col[k]] = y;
+        buf[2 * p.Sp_pad + col[k]] = z;
+      }
+      __syncthreads();
+      if (chain) {
+        const float* src = buf + a * p.Sp_pad + j * P;
+        if (p.pool_mode == V3D_POOL_AVG) {
+#pragma unroll 9
+          for (int dx = 0; dx < P; ++dx) acc = __fadd_rn(acc, src[dx]);
+        } else {
+          for (int dx = 0; dx < P; ++dx) {
+            const float v = src[dx];
+            if (v > mx || v != v) mx = v;
+            const float nv = -v;
+            if (nv > mneg || nv != nv) mneg = nv;
+          }
+        }
+      }
+    }
+    if (chain) {
+      const size_t tok = ((size_t)f * G + gi) * G + j;
+      if (p.pool_mode == V3D_POOL_AVG) {
+        const float v = __fdiv_rn(acc, (float)(P * P));
+        const float pv = p.disc.on ? discretize1(p.disc, v, a) : v;
+        if (p.pooled_out) p.pooled_out[tok * 3 + a] = v;
+        if (p.pe_coords_out) p.pe_coords_out[tok * 3 + a] = pv;
+        s_pts[j * n_slots + a] = pv;
+        s_tab[j * n_slots + a] = pe_row_of(pv, p.g.rows, p.table != nullptr);
+      } else {  // minmax: point 0 = min, point 1 = max (llava_arch.py:237)
+        const float v2[2] = {-mneg, mx};
+#pragma unroll
+        for (int pt = 0; pt < 2; ++pt) {
+          const float pv = p.disc.on ? discretize1(p.disc, v2[pt], a) : v2[pt];
+          if (p.pooled_out) p.pooled_out[(tok * 2 + pt) * 3 + a] = v2[pt];
+          if (p.pe_coords_out) p.pe_coords_out[(tok * 2 + pt) * 3 + a] = pv;
+          s_pts[j * n_slots + pt * 3 + a] = pv;
+          s_tab[j * n_slots + pt * 3 + a] = pe_row_of(pv, p.g.rows, p.table != nullptr);
+        }
+      }
+    }
+  } else {
+    // ---- sample modes (llava_arch.py:241-257): offsets {4,13,22}^2 of the 27-pixel window
+    const int np = p.n_points;
+    for (int i = t; i < G * np; i += kThreads) {
+      const int j = i / np, k = i - j * np;
+      const int q9 = (np == 9) ? k : (np == 5 ? 2 * k : 4);
+      const int r = gi * P + 4 + 9 * (q9 / 3), c = j * P + 4 + 9 * (q9 % 3);
+      float v[3];
+      if constexpr (FROM_DEPTH) {
+        const int sr = __ldg(p.row_map + r), sc = __ldg(p.col_map + c);
+        const float d = load_depth<DT>(p.depth, ((size_t)f * p.H + sr) * p.W + sc);
+        unproject_px(cam, d, __fsub_rn((float)sc, cam.cx), __fsub_rn((float)sr, cam.cy), p.depth_scale, v[0], v[1], v[2]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) v[a] = apply_clamp(p.clamp, v[a], a);
+      } else {
+        const float* src = p.coords_in + (((size_t)f * p.S + r) * p.S + c) * 3;
+        v[0] = __ldg(src);
+        v[1] = __ldg(src + 1);
+        v[2] = __ldg(src + 2);
+      }
+      const size_t tok = ((size_t)f * G + gi) * G + j;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float pv = p.disc.on ? discretize1(p.disc, v[a], a) : v[a];
+        if (p.pooled_out) p.pooled_out[(tok * np + k) * 3 + a] = v[a];
+        if (p.pe_coords_out) p.pe_coords_out[(tok * np + k) * 3 + a] = pv;
+        s_pts[j * n_slots + k * 3 + a] = pv;
+        s_tab[j * n_slots + k * 3 + a] = pe_row_of(pv, p.g.rows, p.table != nullptr);
+      }
+    }
+  }
+  if (p.pe_mode == V3D_PE_NONE) return;
+  __syncthreads();
+
+  // ---- stream the PE rows of this patch row (G tokens x E channels), fused token add
+  const size_t row0 = ((size_t)f * G + gi) * G;
+  const OutT* tokens = reinterpret_cast<const OutT*>(p.tokens_in);
+  stream_pe<OutT, 4>(p.g, p.dim_t, reinterpret_cast<const OutT*>(p.table), s_pts, s_tab, s_desc, G,
+                     tokens ? tokens + row0 * p.g.E : nullptr, reinterpret_cast<OutT*>(p.pe_out) + row0 * p.g.E);
+}
+
+// ============================================================================================
+// 5. element-wise discretisation
+// ============================================================================================
+__global__ void __launch_bounds__(kThreads) k_discretize(const float* __restrict__ c, size_t n, Discretize d, int has_range,
+                                                         float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+    const int a = (int)(i % 3);
+    float x = c[i];
+    if (has_range) {
+      out[i] = discretize1(d, x, a);
+    } else {
+      x = (d.div_mode == V3D_DIV_RECIPROCAL) ? __fmul_rn(x, d.rcp_voxel) : __fdiv_rn(x, d.voxel);
+      out[i] = rintf(x);
+    }
+  }
+}
+
+// ============================================================================================
+// host side
+// ============================================================================================
+static Clamp make_clamp(const float* lo_hi) {
+  Clamp c;
+  memset(&c, 0, sizeof(c));
+  if (lo_hi) {
+    c.on = 1;
+    for (int a = 0; a < 3; ++a) {
+      c.lo[a] = lo_hi[a];
+      c.hi[a] = lo_hi[3 + a];
+    }
+  }
+  return c;
+}
+static Discretize make_disc(int on, const float* lo, const float* hi, float voxel, int div_mode) {
+  Discretize d;
+  memset(&d, 0, sizeof(d));
+  d.on = on;
+  for (int a = 0; a < 3; ++a) {
+    d.lo[a] = lo ? lo[a] : 0.f;
+    d.hi[a] = hi ? hi[a] : 0.f;
+  }
+  d.voxel = voxel;
+  d.rcp_voxel = 1.0f / voxel;
+  d.div_mode = div_mode;
+  return d;
+}
+
+static int make_pe_geom(int E, int n_points, int rows, PeGeom* g) {
+  V3D_REQUIRE(E > 0 && n_points > 0, V3D_E_ARG, "bad E=%d / n_points=%d", E, n_points);
+  const int nf = E / (3 * n_points);
+  V3D_REQUIRE(nf >= 8, V3D_E_UNSUPPORTED, "embedding %d too small for %d points (nf=%d < 8)", E, n_points, nf);
+  V3D_REQUIRE(3 * n_points <= 254, V3D_E_UNSUPPORTED, "too many points per token (%d)", n_points);
+  g->E = E;
+  g->nf = nf;
+  g->n_slots = 3 * n_points;
+  g->cpt = (E + 7) / 8;
+  g->rows = rows;
+  g->Wt = pe_table_width(nf);
+  V3D_REQUIRE(nf + 14 < 65536 && E < 65536 * 8, V3D_E_UNSUPPORTED, "embedding too large");
+  return V3D_OK;
+}
+
+template <typename F>
+static int dispatch_out(int dtype, F&& f) {
+  switch (dtype) {
+    case V3D_BF16: return f(__nv_bfloat16());
+    case V3D_F16: return f(__half());
+    case V3D_F32: return f(float());
+    default: set_error("unknown dtype %d", dtype); return V3D_E_ARG;
+  }
+}
+
+static int grid_for(size_t work_items, int per_block, int max_waves = 8) {
+  size_t blocks = (work_items + per_block - 1) / per_block;
+  size_t cap = (size_t)num_sms() * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace v3d
+
+using namespace v3d;
+
+extern "C" {
+
+int v3d_version(void) { return V3D_VERSION; }
+const char* v3d_last_error(void) { return g_err; }
+
+int v3d_pool_points(int pool_mode) {
+  switch (pool_mode) {
+    case V3D_POOL_AVG: return 1;
+    case V3D_POOL_MINMAX: return 2;
+    case V3D_POOL_SAMPLE9: return 9;
+    case V3D_POOL_SAMPLE5: return 5;
+    case V3D_POOL_SAMPLE1: return 1;
+    default: return -1;
+  }
+}
+
+int v3d_unproject(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
+                  float depth_scale, const int32_t* row_map, const int32_t* col_map, int out_h, int out_w,
+                  const float* clamp_lo_hi_host, float* world_out, v3d_stream_t stream) {
+  V3D_REQUIRE(depth && poses && intr && world_out, V3D_E_ARG, "v3d_unproject: null pointer");
+  V3D_REQUIRE(V >= 0 && H > 0 && W > 0, V3D_E_ARG, "v3d_unproject: bad shape V=%d H=%d W=%d", V, H, W);
+  V3D_REQUIRE((row_map == nullptr) == (col_map == nullptr), V3D_E_ARG, "v3d_unproject: give both maps or none");
+  V3D_REQUIRE((reinterpret_cast<uintptr_t>(world_out) & 15) == 0, V3D_E_ALIGN, "v3d_unproject: output not 16-byte aligned");
+  const int OH = row_map ? out_h : H, OW = col_map ? out_w : W;
+  V3D_REQUIRE(OH > 0 && OW > 0, V3D_E_ARG, "v3d_unproject: bad output size %dx%d", OH, OW);
+  if (V == 0) return V3D_OK;
+  const Clamp cl = make_clamp(clamp_lo_hi_host);
+  const size_t groups = ((size_t)V * OH * OW + 3) / 4;
+  const int grid = grid_for(groups, kThreads, 16);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (depth_dtype) {
+    case V3D_DEPTH_U16:
+      k_unproject<V3D_DEPTH_U16><<<grid, kThreads, 0, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, OH, OW, cl, world_out);
+      break;
+    case V3D_DEPTH_I32:
+      k_unproject<V3D_DEPTH_I32><<<grid, kThreads, 0, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, OH, OW, cl, world_out);
+      break;
+    case V3D_DEPTH_F32:
+      k_unproject<V3D_DEPTH_F32><<<grid, kThreads, 0, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, OH, OW, cl, world_out);
+      break;
+    default: set_error("v3d_unproject: unknown depth dtype %d", depth_dtype); return V3D_E_ARG;
+  }
+  return check_launch("k_unproject");
+}
+
+int v3d_boundary(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
+                 float depth_scale, const float* clamp_lo_hi_host, float* out6, v3d_stream_t stream) {
+  V3D_REQUIRE(depth && poses && intr && out6, V3D_E_ARG, "v3d_boundary: null pointer");
+  V3D_REQUIRE(V > 0 && H > 0 && W > 0, V3D_E_ARG, "v3d_boundary: bad shape");
+  const Clamp cl = make_clamp(clamp_lo_hi_host);
+  cudaStream_t s = (cudaStream_t)stream;
+  int* keys = reinterpret_cast<int*>(out6);
+  k_boundary_init<<<1, 32, 0, s>>>(keys);
+  const int grid = grid_for((size_t)V * ((H + 7) / 8), 1, 8);
+  switch (depth_dtype) {
+    case V3D_DEPTH_U16: k_boundary<V3D_DEPTH_U16><<<grid, kThreads, 0, s>>>(depth, poses, intr, V, H, W, depth_scale, cl, keys); break;
+    case V3D_DEPTH_I32: k_boundary<V3D_DEPTH_I32><<<grid, kThreads, 0, s>>>(depth, poses, intr, V, H, W, depth_scale, cl, keys); break;
+    case V3D_DEPTH_F32: k_boundary<V3D_DEPTH_F32><<<grid, kThreads, 0, s>>>(depth, poses, intr, V, H, W, depth_scale, cl, keys); break;
+    default: set_error("v3d_boundary: unknown depth dtype %d", depth_dtype); return V3D_E_ARG;
+  }
+  k_boundary_final<<<1, 32, 0, s>>>(keys);
+  return check_launch("k_boundary");
+}
+
+int v3d_discretize(const float* coords, size_t n_points, const float* min_xyz_host, const float* max_xyz_host,
+                   int has_range, float voxel_size, int div_mode, float* out, v3d_stream_t stream) {
+  V3D_REQUIRE(coords && out, V3D_E_ARG, "v3d_discretize: null pointer");
+  V3D_REQUIRE(!has_range || (min_xyz_host && max_xyz_host), V3D_E_ARG, "v3d_discretize: range requested but not given");
+  V3D_REQUIRE(voxel_size > 0.f, V3D_E_ARG, "v3d_discretize: voxel_size must be positive");
+  if (n_points == 0) return V3D_OK;
+  const Discretize d = make_disc(1, min_xyz_host, max_xyz_host, voxel_size, div_mode);
+  const size_t n = n_points * 3;
+  k_discretize<<<grid_for(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(coords, n, d, has_range, out);
+  return check_launch("k_discretize");
+}
+
+size_t v3d_pe_table_bytes(int E, int n_points, int rows, int dtype) {
+  PeGeom g;
+  if (make_pe_geom(E, n_points, rows, &g) != V3D_OK || rows <= 0) return 0;
+  return (size_t)g.n_slots * (rows + 1) * g.Wt * dtype_size(dtype);
+}
+
+int v3d_pe_table_build(const float* dim_t, int E, int n_points, int rows, int dtype, void* table, v3d_stream_t stream) {
+  V3D_REQUIRE(dim_t && table, V3D_E_ARG, "v3d_pe_table_build: null pointer");
+  V3D_REQUIRE(rows > 0, V3D_E_ARG, "v3d_pe_table_build: rows must be positive");
+  V3D_REQUIRE((reinterpret_cast<uintptr_t>(table) & 15) == 0, V3D_E_ALIGN, "v3d_pe_table_build: table not 16-byte aligned");
+  PeGeom g;
+  int rc = make_pe_geom(E, n_points, rows, &g);
+  if (rc != V3D_OK) return rc;
+  const size_t total = (size_t)g.n_slots * (rows + 1) * g.Wt;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_out(dtype, [&](auto tag) {
+    using T = decltype(tag);
+    k_pe_table<T><<<grid_for(total, kThreads), kThreads, 0, s>>>(dim_t, g, reinterpret_cast<T*>(table));
+    return check_launch("k_pe_table");
+  });
+}
+
+int v3d_pe_sine3d(const float* coords, size_t n_tokens, int n_points, int E, const float* dim_t, const void* table,
+                  int rows, int dtype, const void* tokens_in, void* out, v3d_stream_t stream) {
+  V3D_REQUIRE(coords && dim_t && out, V3D_E_ARG, "v3d_pe_sine3d: null pointer");
+  PeGeom g;
+  int rc = make_pe_geom(E, n_points, table ? rows : 0, &g);
+  if (rc != V3D_OK) return rc;
+  V3D_REQUIRE(!table || rows > 0, V3D_E_ARG, "v3d_pe_sine3d: table given with rows=%d", rows);
+  const bool vec = (E & 7) == 0;
+  V3D_REQUIRE(!vec || ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(tokens_in) | reinterpret_cast<uintptr_t>(table)) & 15) == 0,
+              V3D_E_ALIGN, "v3d_pe_sine3d: out/tokens/table must be 16-byte aligned");
+  if (n_tokens == 0) return V3D_OK;
+  const size_t smem = (size_t)g.cpt * sizeof(ChunkDesc) + (size_t)kPeTokPerCta * g.n_slots * 8;
+  const int grid = grid_for((n_tokens + kPeTokPerCta - 1) / kPeTokPerCta, 1, 16);
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_out(dtype, [&](auto tag) {
+    using T = decltype(tag);
+    if (smem > 48 * 1024) V3D_CUDA(cudaFuncSetAttribute(k_pe_sine3d<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pe_sine3d<T><<<grid, kThreads, smem, s>>>(coords, n_tokens, g, dim_t, reinterpret_cast<const T*>(table),
+                                                reinterpret_cast<const T*>(tokens_in), reinterpret_cast<T*>(out));
+    return check_launch("k_pe_sine3d");
+  });
+}
+
+}  // extern "C"
+
+// ---- fused launcher ---------------------------------------------------------------------------
+template <int DT, bool FROM_DEPTH, bool USE_TMA, typename OutT>
+static int launch_fused(const FusedParams& p, cudaStream_t s) {
+  const size_t smem = fused_smem_bytes(p, FROM_DEPTH && USE_TMA);
+  V3D_REQUIRE(smem <= 227 * 1024, V3D_E_UNSUPPORTED, "fused kernel needs %zu bytes of shared memory", smem);
+  auto kern = k_fused<DT, FROM_DEPTH, USE_TMA, OutT>;
+  if (smem > 48 * 1024) V3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<p.n_frames * p.grid, kThreads, smem, s>>>(p);
+  return check_launch("k_fused");
+}
+
+template <bool FROM_DEPTH, typename OutT>
+static int launch_fused_dt(int depth_dtype, bool use_tma, const FusedParams& p, cudaStream_t s) {
+  if constexpr (!FROM_DEPTH) {
+    return launch_fused<V3D_DEPTH_F32, false, false, OutT>(p, s);
+  } else {
+    switch (depth_dtype) {
+      case V3D_DEPTH_U16:
+        return use_tma ? launch_fused<V3D_DEPTH_U16, true, true, OutT>(p, s) : launch_fused<V3D_DEPTH_U16, true, false, OutT>(p, s);
+      case V3D_DEPTH_I32:
+        return use_tma ? launch_fused<V3D_DEPTH_I32, true, true, OutT>(p, s) : launch_fused<V3D_DEPTH_I32, true, false, OutT>(p, s);
+      case V3D_DEPTH_F32:
+        return use_tma ? launch_fused<V3D_DEPTH_F32, true, true, OutT>(p, s) : launch_fused<V3D_DEPTH_F32, true, false, OutT>(p, s);
+      default: set_error("unknown depth dtype %d", depth_dtype); return V3D_E_ARG;
+    }
+  }
+}
+
+static int check_pool(int pool_mode, int patch, int grid, int* n_points) {
+  *n_points = v3d_pool_points(pool_mode);
+  V3D_REQUIRE(*n_points > 0, V3D_E_ARG, "unknown pool mode %d", pool_mode);
+  V3D_REQUIRE(patch > 0 && grid > 0, V3D_E_ARG, "bad patch=%d grid=%d", patch, grid);
+  V3D_REQUIRE(patch * grid <= 2 * kThreads, V3D_E_UNSUPPORTED, "patch*grid=%d exceeds %d columns", patch * grid, 2 * kThreads);
+  V3D_REQUIRE(3 * grid <= kThreads, V3D_E_UNSUPPORTED, "grid=%d too large", grid);
+  if (pool_mode >= V3D_POOL_SAMPLE9)
+    V3D_REQUIRE(patch == 27 && grid == 14, V3D_E_UNSUPPORTED, "sample pooling is defined for patch 27 / grid 14 only (llava_arch.py:245)");
+  return V3D_OK;
+}
+
+extern "C" {
+
+int v3d_pool_coords(const float* coords, int V, int S, int patch, int grid, int pool_mode, float* out, v3d_stream_t stream) {
+  V3D_REQUIRE(coords && out, V3D_E_ARG, "v3d_pool_coords: null pointer");
+  V3D_REQUIRE(V >= 0 && S > 0, V3D_E_ARG, "v3d_pool_coords: bad shape");
+  int n_points;
+  int rc = check_pool(pool_mode, patch, grid, &n_points);
+  if (rc != V3D_OK) return rc;
+  V3D_REQUIRE(patch * grid <= S, V3D_E_ARG, "v3d_pool_coords: patch*grid=%d exceeds S=%d", patch * grid, S);
+  if (V == 0) return V3D_OK;
+  FusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.coords_in = coords;
+  p.n_frames = V;
+  p.S = S;
+  p.patch = patch;
+  p.grid = grid;
+  p.Sp = patch * grid;
+  p.Sp_pad = p.Sp + 1;
+  p.pool_mode = pool_mode;
+  p.n_points = n_points;
+  p.pe_mode = V3D_PE_NONE;
+  p.pooled_out = out;
+  return launch_fused_dt<false, __nv_bfloat16>(0, false, p, (cudaStream_t)stream);
+}
+
+int v3d_frontend_pe(const v3d_frontend_desc* d, v3d_stream_t stream) {
+  V3D_REQUIRE(d, V3D_E_ARG, "v3d_frontend_pe: null descriptor");
+  V3D_REQUIRE(d->depth && d->poses && d->intr && d->row_map && d->col_map, V3D_E_ARG, "v3d_frontend_pe: null input pointer");
+  V3D_REQUIRE(d->n_frames >= 0 && d->H > 0 && d->W > 0, V3D_E_ARG, "v3d_frontend_pe: bad shape");
+  int n_points;
+  int rc = check_pool(d->pool_mode, d->patch, d->grid, &n_points);
+  if (rc != V3D_OK) return rc;
+  V3D_REQUIRE(d->pe_mode == V3D_PE_NONE || d->pe_mode == V3D_PE_SINE3D, V3D_E_ARG, "unknown pe_mode %d", d->pe_mode);
+  V3D_REQUIRE(d->pe_mode != V3D_PE_NONE || d->pooled_out || d->pe_coords_out, V3D_E_ARG, "v3d_frontend_pe: nothing to compute");
+  FusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.depth = d->depth;
+  p.poses = d->poses;
+  p.intr = d->intr;
+  p.n_frames = d->n_frames;
+  p.H = d->H;
+  p.W = d->W;
+  p.depth_scale = d->depth_scale;
+  p.row_map = d->row_map;
+  p.col_map = d->col_map;
+  p.patch = d->patch;
+  p.grid = d->grid;
+  p.Sp = d->patch * d->grid;
+  p.Sp_pad = p.Sp + 1;
+  p.pool_mode = d->pool_mode;
+  p.n_points = n_points;
+  if (d->has_clamp) {
+    float lh[6] = {d->clamp_lo[0], d->clamp_lo[1], d->clamp_lo[2], d->clamp_hi[0], d->clamp_hi[1], d->clamp_hi[2]};
+    p.clamp = make_clamp(lh);
+  }
+  if (d->discrete) {
+    V3D_REQUIRE(d->voxel_size > 0.f, V3D_E_ARG, "v3d_frontend_pe: voxel_size must be positive");
+    p.disc = make_disc(1, d->min_xyz, d->max_xyz, d->voxel_size, d->div_mode);
+  }
+  p.pe_mode = d->pe_mode;
+  p.pooled_out = d->pooled_out;
+  p.pe_coords_out = d->pe_coords_out;
+  if (d->pe_mode == V3D_PE_SINE3D) {
+    V3D_REQUIRE(d->pe_out && d->dim_t, V3D_E_ARG, "v3d_frontend_pe: pe_out / dim_t missing");
+    rc = make_pe_geom(d->E, n_points, d->table ? d->table_rows : 0, &p.g);
+    if (rc != V3D_OK) return rc;
+    V3D_REQUIRE(!d->table || d->table_rows > 0, V3D_E_ARG, "v3d_frontend_pe: table given with rows=%d", d->table_rows);
+    if (d->discrete && d->table) {
+      for (int a = 0; a < 3; ++a) {
+        const float top = rintf((d->max_xyz[a] - d->min_xyz[a]) / d->voxel_size);
+        V3D_REQUIRE(top < (float)d->table_rows, V3D_E_ARG, "v3d_frontend_pe: table has %d rows, axis %d needs %d", d->table_rows, a, (int)top + 1);
+      }
+    }
+    if ((d->E & 7) == 0)
+      V3D_REQUIRE(((reinterpret_cast<uintptr_t>(d->pe_out) | reinterpret_cast<uintptr_t>(d->tokens_in) | reinterpret_cast<uintptr_t>(d->table)) & 15) == 0,
+                  V3D_E_ALIGN, "v3d_frontend_pe: pe_out/tokens_in/table must be 16-byte aligned");
+    p.dim_t = d->dim_t;
+    p.table = d->table;
+    p.tokens_in = d->tokens_in;
+    p.pe_out = d->pe_out;
+  }
+  if (d->n_frames == 0) return V3D_OK;
+
+  // TMA staging geometry: bytes [lo, hi) of a depth row that cover every column the maps use.
+  const size_t esz = depth_size(d->depth_dtype);
+  V3D_REQUIRE(d->src_col_min >= 0 && d->src_col_max >= d->src_col_min && d->src_col_max < d->W, V3D_E_ARG,
+              "v3d_frontend_pe: src_col_min/max [%d,%d] outside [0,%d)", d->src_col_min, d->src_col_max, d->W);
+  const bool use_tma = ((size_t)d->W * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->depth) & 15) == 0;
+  if (use_tma) {
+    const int lo = (int)((d->src_col_min * esz) & ~(size_t)15);
+    const int hi = (int)(((d->src_col_max + 1) * esz + 15) & ~(size_t)15);
+    p.col_lo_byte = lo;
+    p.span = hi - lo;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_out(d->pe_mode == V3D_PE_NONE ? V3D_BF16 : d->dtype, [&](auto tag) {
+    using T = decltype(tag);
+    return launch_fused_dt<true, T>(d->depth_dtype, use_tma, p, s);
+  });
+}
+
+}  // extern "C"

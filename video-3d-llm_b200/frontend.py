@@ -1,0 +1,123 @@
+"""The fused front end: raw depth + pose + intrinsics -> 3D position encoding (+ vision tokens).
+
+One call = one launch of the fused kernel (v3d_frontend_pe, include/v3d.h): it replaces the chain
+  VideoProcessor.calculate_world_coords / preprocess   (llava/video_utils.py:196-238, 291-308)
+  average_coordinate_in_patch / discrete_coords        (llava/model/llava_arch.py:213-272, 396-420)
+  world_position_embedding(...) and the add            (llava/model/position_encoding.py:17-49, llava_arch.py:515)
+without ever materialising world coordinates in HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from dataclasses import dataclass
+
+import torch
+
+from . import cabi, geometry
+from .coords import _POOL, parse_world_position_embedding_type
+from .position_encoding import get_tables
+
+
+@dataclass
+class FrontEndConfig:
+    H: int = 480
+    W: int = 640
+    crop_size: int = 384
+    strategy: str = "center_crop"                 # llava/video_utils.py:293-308
+    patch_size: int = 27                          # 27 -> 14x14 grid (reference default); 14 -> 27x27 grid
+    trim: int = 6                                 # the [:-6, :-6] of llava_arch.py:217
+    world_position_embedding_type: str = "avg-discrete-sin3d"   # scripts/3d/train/train_multi.sh:82
+    embedding_size: int = 3584
+    temperature: float = 10000
+    voxel_size: float = 0.1
+    min_xyz_range: tuple = (-15, -15, -5)
+    max_xyz_range: tuple = (15, 15, 5)
+    depth_scale: float = 1000.0
+    dtype: torch.dtype = torch.bfloat16
+    div_mode: int = cabi.DIV_IEEE
+
+    @property
+    def grid(self) -> int:
+        return (self.crop_size - self.trim) // self.patch_size
+
+
+class FrontEnd:
+    """Callable bound to one configuration and device; caches maps, dim_t and the PE table."""
+
+    def __init__(self, config: FrontEndConfig | None = None, device=None, **overrides):
+        cfg = dataclasses.replace(config or FrontEndConfig(), **overrides)
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise RuntimeError("FrontEnd needs a CUDA device: this path has no CPU implementation")
+        self.lib = cabi.load()
+        self.flags = parse_world_position_embedding_type(cfg.world_position_embedding_type)
+        if self.flags["pool"] is None:
+            raise ValueError(f"{cfg.world_position_embedding_type!r} names no pooling (avg / sample9 / sample5 / sample1 / minmax)")
+        self.n_points = self.flags["n_points"]
+        self.row_map, self.col_map = geometry.resample_maps(cfg.H, cfg.W, cfg.crop_size, cfg.strategy, self.device)
+        _, cols = geometry.resample_maps_host(cfg.H, cfg.W, cfg.crop_size, cfg.strategy)
+        used = cols[: cfg.grid * cfg.patch_size]
+        self.src_col_min, self.src_col_max = min(used), max(used)
+        self.tables = None
+        if self.flags["sin3d"]:
+            rows = 1
+            if self.flags["discrete"]:
+                rows = 1 + max(int(round((hi - lo) / cfg.voxel_size)) for lo, hi in zip(cfg.min_xyz_range, cfg.max_xyz_range))
+            self.tables = get_tables(cfg.embedding_size, self.n_points, cfg.temperature, cfg.dtype, self.device, max(rows, 2))
+
+    @property
+    def tokens_per_frame(self) -> int:
+        return self.cfg.grid * self.cfg.grid
+
+    def __call__(self, depth, poses, intrinsics, tokens=None, out=None, clamp=None, want_coords=False):
+        """depth (V,H,W) uint16/int16-bits/int32/float32, poses & intrinsics (V,4,4) float32, all on the
+        device.  tokens: optional (V, G*G, E) in cfg.dtype to add the PE to (may be `out`).
+        Returns the PE (or tokens + PE) as (V, G*G, E); with want_coords also (pooled, pe_coords)."""
+        cfg = self.cfg
+        for name, t in (("depth", depth), ("poses", poses), ("intrinsics", intrinsics)):
+            cabi.require_cuda(t, name)
+        V, H, W = depth.shape
+        if (H, W) != (cfg.H, cfg.W):
+            raise ValueError(f"depth is {H}x{W}, front end was configured for {cfg.H}x{cfg.W}")
+        depth = depth.contiguous()
+        poses = poses.to(torch.float32).contiguous()
+        intrinsics = intrinsics.to(torch.float32).contiguous()
+        G, E = cfg.grid, cfg.embedding_size
+        d = cabi.FrontendDesc()
+        d.depth, d.depth_dtype, d.poses, d.intr = depth.data_ptr(), cabi.depth_code(depth), poses.data_ptr(), intrinsics.data_ptr()
+        d.n_frames, d.H, d.W, d.depth_scale = V, H, W, cfg.depth_scale
+        d.row_map, d.col_map = self.row_map.data_ptr(), self.col_map.data_ptr()
+        d.src_col_min, d.src_col_max = self.src_col_min, self.src_col_max
+        d.patch, d.grid, d.pool_mode = cfg.patch_size, G, _POOL[self.flags["pool"]]
+        if clamp is not None:
+            d.has_clamp, d.clamp_lo, d.clamp_hi = 1, cabi.float3(clamp[0]), cabi.float3(clamp[1])
+        d.discrete = int(self.flags["discrete"])
+        d.min_xyz, d.max_xyz = cabi.float3(cfg.min_xyz_range), cabi.float3(cfg.max_xyz_range)
+        d.voxel_size, d.div_mode = cfg.voxel_size, cfg.div_mode
+        pooled = pe_coords = None
+        if want_coords or not self.flags["sin3d"]:
+            shape = (V, G, G, 3) if self.n_points == 1 else (V, G, G, self.n_points, 3)
+            pooled = torch.empty(shape, dtype=torch.float32, device=self.device)
+            pe_coords = torch.empty(shape, dtype=torch.float32, device=self.device)
+            d.pooled_out, d.pe_coords_out = pooled.data_ptr(), pe_coords.data_ptr()
+        if self.flags["sin3d"]:
+            if out is None:
+                out = torch.empty((V, G * G, E), dtype=cfg.dtype, device=self.device)
+            elif out.shape != (V, G * G, E) or out.dtype != cfg.dtype or not out.is_contiguous():
+                raise ValueError("out must be a contiguous (V, G*G, E) tensor of the configured dtype")
+            if tokens is not None:
+                if tokens.shape != out.shape or tokens.dtype != cfg.dtype:
+                    raise ValueError(f"tokens must be {tuple(out.shape)} {cfg.dtype}, got {tuple(tokens.shape)} {tokens.dtype}")
+                tokens = tokens.contiguous()
+            d.pe_mode, d.E, d.dtype = cabi.PE_SINE3D, E, cabi.dtype_code(cfg.dtype)
+            d.dim_t, d.table, d.table_rows = self.tables.dim_t.data_ptr(), self.tables.table.data_ptr(), self.tables.rows
+            d.tokens_in, d.pe_out = cabi.ptr(tokens), out.data_ptr()
+        else:
+            d.pe_mode = cabi.PE_NONE
+        with torch.cuda.device(self.device):
+            cabi.check(self.lib.v3d_frontend_pe(C.byref(d), cabi.stream_ptr(self.device)), "v3d_frontend_pe")
+        if want_coords:
+            return out, pooled, pe_coords
+        return out if self.flags["sin3d"] else pe_coords

@@ -1,0 +1,474 @@
+"""Mirror of llava/video_utils.py on the CUDA library: `unproject`, `VideoProcessor`,
+`merge_video_dict` keep the reference's names, arguments, option-string semantics and outputs.
+
+Two ways to consume the geometry:
+  * eager  (lazy=False): `unproject` / `calculate_world_coords` / `preprocess` return real tensors
+    like the reference, computed by the CUDA kernels on the current device.
+  * lazy   (lazy=True, the default of VideoProcessor): `world_coords` is a `LazyWorldCoords`
+    handle over the raw uint16 depth, poses and intrinsics.  DataLoader workers never touch CUDA
+    (it cannot be initialised in forked workers) and ship 3x less data; the fused kernel runs where
+    the model runs, when `average_coordinate_in_patch` & co. (coords.py) receive the handle.
+    Anything else done to the handle materialises the (V,384,384,3) tensor on demand, so code
+    written against the reference keeps working.
+"""
+from __future__ import annotations
+
+import json
+import os
+import pickle
+
+import numpy as np
+import torch
+from PIL import Image
+
+from . import cabi, geometry
+
+DEPTH_SCALE = 1000.0
+
+
+def _device_for(*tensors):
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the video-3d-llm_b200 front end has no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _as_depth(depths: torch.Tensor) -> torch.Tensor:
+    """Keep uint16/int16/int32/float32 depth as is; anything else goes through float32 like the
+    reference's `.float()` (llava/video_utils.py:230)."""
+    if depths.dtype in (torch.int16, torch.int32, torch.float32) or depths.dtype == getattr(torch, "uint16", None):
+        return depths.contiguous()
+    return depths.to(torch.float32).contiguous()
+
+
+def unproject(intrinsics, poses, depths, *, row_map=None, col_map=None, clamp=None):
+    """llava/video_utils.py:38-68.  intrinsics (V,4,4), poses (V,4,4), depths (V,H,W) ->
+    world coordinates (V,H,W,3) float32 on the CUDA device (inputs on the CPU are moved there).
+    row_map/col_map (int32 device tensors) gather a resampled/cropped window instead."""
+    lib = cabi.load()
+    dev = _device_for(depths, poses, intrinsics)
+    depths = _as_depth(depths).to(dev, non_blocking=True)
+    poses = poses.to(dev, torch.float32).contiguous()
+    intrinsics = intrinsics.to(dev, torch.float32).contiguous()
+    V, H, W = depths.shape
+    if poses.shape != (V, 4, 4) or intrinsics.shape != (V, 4, 4):
+        raise ValueError("intrinsics and poses must be (V,4,4)")
+    oh, ow = (H, W) if row_map is None else (int(row_map.numel()), int(col_map.numel()))
+    out = torch.empty((V, oh, ow, 3), dtype=torch.float32, device=dev)
+    lo_hi = None if clamp is None else cabi.host_floats(list(clamp[0]) + list(clamp[1]))
+    with torch.cuda.device(dev):
+        cabi.check(lib.v3d_unproject(depths.data_ptr(), cabi.depth_code(depths), poses.data_ptr(), intrinsics.data_ptr(), V, H, W,
+                                     DEPTH_SCALE, cabi.ptr(row_map), cabi.ptr(col_map), oh, ow, lo_hi, out.data_ptr(),
+                                     cabi.stream_ptr(dev)), "v3d_unproject")
+    return out
+
+
+def boundary(intrinsics, poses, depths, clamp=None) -> torch.Tensor:
+    """[xmin,xmax,ymin,ymax,zmin,zmax] of the unprojected scene (llava/video_utils.py:273-277)."""
+    lib = cabi.load()
+    dev = _device_for(depths, poses, intrinsics)
+    depths = _as_depth(depths).to(dev)
+    poses = poses.to(dev, torch.float32).contiguous()
+    intrinsics = intrinsics.to(dev, torch.float32).contiguous()
+    V, H, W = depths.shape
+    out = torch.empty(6, dtype=torch.float32, device=dev)
+    lo_hi = None if clamp is None else cabi.host_floats(list(clamp[0]) + list(clamp[1]))
+    with torch.cuda.device(dev):
+        cabi.check(lib.v3d_boundary(depths.data_ptr(), cabi.depth_code(depths), poses.data_ptr(), intrinsics.data_ptr(), V, H, W,
+                                    DEPTH_SCALE, lo_hi, out.data_ptr(), cabi.stream_ptr(dev)), "v3d_boundary")
+    return out
+
+
+class _LazyMin:
+    """Result of `lazy.view(B,-1,3).min(dim=1)`: llava_arch.py:387 computes it and never uses the value
+    (discrete_coords ignores its xyz_min argument), so it is only evaluated if somebody looks."""
+
+    def __init__(self, owner):
+        self._owner = owner
+        self._val = None
+
+    def _get(self):
+        if self._val is None:
+            full = self._owner.materialize()
+            self._val = full.reshape(self._owner.batch_size, -1, 3).min(dim=1)
+        return self._val
+
+    def __getitem__(self, i):
+        return _LazyMinItem(self, i)
+
+    def __iter__(self):
+        return iter(self._get())
+
+
+class _LazyMinItem:
+    def __init__(self, parent, i):
+        self._parent, self._i = parent, i
+
+    def _get(self):
+        return self._parent._get()[self._i]
+
+    def __getitem__(self, j):
+        return _LazyMinItem(self, j)
+
+    def __getattr__(self, name):
+        return getattr(self._get(), name)
+
+
+class _LazyFlat:
+    def __init__(self, owner):
+        self._owner = owner
+
+    def min(self, dim=None, **kw):
+        if dim == 1:
+            return _LazyMin(self._owner)
+        return self._owner.materialize().reshape(self._owner.batch_size, -1, 3).min(dim=dim, **kw)
+
+    def __getattr__(self, name):
+        return getattr(self._owner.materialize().reshape(self._owner.batch_size, -1, 3), name)
+
+
+class LazyWorldCoords:
+    """Stand-in for the `world_coords` tensor of the reference's video_dict, shape (V,S,S,3) per
+    scene or (B,V,S,S,3) after merge_video_dict, backed by raw depth/pose/intrinsics."""
+
+    def __init__(self, depth, poses, intrinsics, crop_size=384, strategy="center_crop", clamp=None, dtype=torch.float32,
+                 batched=False):
+        self.depth, self.poses, self.intrinsics = depth, poses, intrinsics
+        self.crop_size, self.strategy, self.clamp = crop_size, strategy, clamp
+        self.dtype = dtype
+        self.batched = batched  # depth is (B,V,H,W) instead of (V,H,W)
+        self._full = None
+
+    # ---- tensor-like surface used by the reference ------------------------------------------
+    @property
+    def batch_size(self):
+        return self.depth.shape[0] if self.batched else 1
+
+    @property
+    def shape(self):
+        lead = tuple(self.depth.shape[:-2])
+        return torch.Size(lead + (self.crop_size, self.crop_size, 3))
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    @property
+    def device(self):
+        return self.depth.device
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def _like(self, depth=None, poses=None, intrinsics=None, dtype=None, batched=None):
+        return LazyWorldCoords(self.depth if depth is None else depth, self.poses if poses is None else poses,
+                               self.intrinsics if intrinsics is None else intrinsics, self.crop_size, self.strategy, self.clamp,
+                               self.dtype if dtype is None else dtype, self.batched if batched is None else batched)
+
+    def to(self, *args, **kwargs):
+        device, dtype = kwargs.get("device"), kwargs.get("dtype")
+        for a in args:
+            if isinstance(a, torch.dtype):
+                dtype = a
+            elif isinstance(a, (str, torch.device, int)):
+                device = a
+            elif isinstance(a, torch.Tensor):
+                device, dtype = a.device, a.dtype
+        out = self
+        if device is not None:
+            nb = bool(kwargs.get("non_blocking", False))
+            out = out._like(self.depth.to(device, non_blocking=nb), self.poses.to(device, non_blocking=nb),
+                            self.intrinsics.to(device, non_blocking=nb))
+        if dtype is not None:
+            out = out._like(dtype=dtype)
+        return out
+
+    def cuda(self, device=None, non_blocking=False):
+        return self.to(device=torch.device("cuda", torch.cuda.current_device() if device is None else device), non_blocking=non_blocking)
+
+    def half(self):
+        return self._like(dtype=torch.float16)
+
+    def bfloat16(self):
+        return self._like(dtype=torch.bfloat16)
+
+    def float(self):
+        return self._like(dtype=torch.float32)
+
+    def detach(self):
+        return self
+
+    def pin_memory(self):
+        return self._like(self.depth.pin_memory(), self.poses.pin_memory(), self.intrinsics.pin_memory())
+
+    def __iter__(self):
+        if not self.batched:
+            raise TypeError("iterate a batched LazyWorldCoords (B,V,S,S,3)")
+        for b in range(self.depth.shape[0]):
+            yield self._like(self.depth[b], self.poses[b], self.intrinsics[b], batched=False)
+
+    def __getitem__(self, idx):
+        if self.batched and isinstance(idx, int):
+            return self._like(self.depth[idx], self.poses[idx], self.intrinsics[idx], batched=False)
+        return self.materialize()[idx]
+
+    def view(self, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)):
+            shape = tuple(shape[0])
+        if len(shape) == 3 and shape[1] == -1 and shape[2] == 3 and shape[0] == self.batch_size:
+            return _LazyFlat(self)
+        return self.materialize().view(*shape)
+
+    def __getattr__(self, name):
+        # anything not modelled above falls back to the real tensor
+        if name.startswith("_") or name in ("depth", "poses", "intrinsics"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+    # ---- evaluation ------------------------------------------------------------------------------
+    def _maps(self, dev):
+        H, W = self.depth.shape[-2:]
+        return geometry.resample_maps(H, W, self.crop_size, self.strategy, dev)
+
+    def materialize(self) -> torch.Tensor:
+        """The tensor the reference would hold: (…,S,S,3) in self.dtype (llava/video_utils.py:296-321)."""
+        if self._full is None:
+            dev = _device_for(self.depth)
+            rm, cm = self._maps(dev)
+            d = self.depth.reshape((-1,) + tuple(self.depth.shape[-2:]))
+            full = unproject(self.intrinsics.reshape(-1, 4, 4), self.poses.reshape(-1, 4, 4), d, row_map=rm, col_map=cm, clamp=self.clamp)
+            self._full = full.reshape(tuple(self.shape)).to(self.dtype)
+        return self._full
+
+    def pooled(self, patch_size: int, mode: str, trim: int = 6) -> torch.Tensor:
+        """Pooled coordinates (V,G,G[,n],3) straight from depth with the fused kernel (PE off)."""
+        from .frontend import FrontEnd
+
+        if self.batched:
+            raise TypeError("pool one scene at a time (the reference iterates over the batch, llava_arch.py:396)")
+        dev = _device_for(self.depth)
+        H, W = self.depth.shape[-2:]
+        kind = mode  # 'avg' | 'minmax' | 'sample9' | ...
+        fe = _pool_frontends.get((H, W, self.crop_size, self.strategy, patch_size, trim, kind, str(dev)))
+        if fe is None:
+            fe = FrontEnd(device=dev, H=H, W=W, crop_size=self.crop_size, strategy=self.strategy, patch_size=patch_size, trim=trim,
+                          world_position_embedding_type=kind)
+            _pool_frontends[(H, W, self.crop_size, self.strategy, patch_size, trim, kind, str(dev))] = fe
+        _, pooled, _ = fe(self.depth.to(dev), self.poses.to(dev), self.intrinsics.to(dev), clamp=self.clamp, want_coords=True)
+        return pooled.to(self.dtype)
+
+
+_pool_frontends: dict = {}
+
+
+class VideoProcessor:
+    """llava/video_utils.py:71-358 with the same constructor and methods.  `lazy` (extra, keyword
+    only) selects what `world_coords` is: a LazyWorldCoords handle (default) or a real tensor."""
+
+    def __init__(self, video_folder="data", annotation_dir="data/embodiedscan/", voxel_size=None, min_xyz_range=None,
+                 max_xyz_range=None, frame_sampling_strategy="uniform", val_box_type="pred", *, lazy=True, metadata_dir=None):
+        self.video_folder = video_folder
+        self.voxel_size = voxel_size
+        self.min_xyz_range = torch.tensor(min_xyz_range) if min_xyz_range is not None else None
+        self.max_xyz_range = torch.tensor(max_xyz_range) if max_xyz_range is not None else None
+        self.frame_sampling_strategy = frame_sampling_strategy
+        self.lazy = lazy
+        self.scene = {}
+        print("============frame sampling strategy: {}=============".format(self.frame_sampling_strategy))
+        # the reference hard-codes data/metadata relative to the working directory (:102,109,116)
+        meta = metadata_dir if metadata_dir is not None else os.path.join("data", "metadata")
+
+        for split in ["train", "val", "test"]:
+            with open(os.path.join(annotation_dir, f"embodiedscan_infos_{split}.pkl"), "rb") as f:
+                for item in pickle.load(f)["data_list"]:
+                    if item["sample_idx"].startswith("scannet"):
+                        self.scene[item["sample_idx"]] = item
+
+        self.scan2obj = {}
+        for split in ["train", "val"]:
+            box_type = "gt" if split == "train" else val_box_type
+            with open(os.path.join(meta, f"scannet_{split}_{box_type}_box.json")) as f:
+                self.scan2obj.update(json.load(f))
+
+        if "mc" in self.frame_sampling_strategy:
+            with open(os.path.join(meta, "scannet_select_frames.json")) as f:
+                self.mc_sampling_files = {dd["video_id"]: dd for dd in json.load(f)}
+            with open(os.path.join(meta, "pcd_discrete_0.1.pkl"), "rb") as f:
+                pc_data = pickle.load(f)
+            self.pc_min, self.pc_max = {}, {}
+            for scene_id, pts in pc_data.items():
+                arr = np.asarray(pts, dtype=np.int64).reshape(-1, 3)
+                # the reference starts its running min/max at +-1000 (:121-122)
+                mn = np.minimum(arr.min(0), 1000) if len(arr) else np.array([1000] * 3)
+                mx = np.maximum(arr.max(0), -1000) if len(arr) else np.array([-1000] * 3)
+                self.pc_min[scene_id] = torch.Tensor(mn.tolist()) / 10
+                self.pc_max[scene_id] = torch.Tensor(mx.tolist()) / 10
+
+    # ---- frame selection (host, integer work) ------------------------------------------------
+    def sample_frame_files_mc(self, video_id: str, frames_upbound: int = 32, do_shift=False):
+        """:131-159 -- prefix of the offline MC order, cut at the coverage ratio, sorted by frame id."""
+        mc = self.mc_sampling_files[video_id]
+        frame_files = mc["frame_files"][:frames_upbound]
+        voxel_nums = mc["voxel_nums"][:frames_upbound]
+        ratio = 1.0
+        if "ratio95" in self.frame_sampling_strategy:
+            ratio = 0.95
+        elif "ratio90" in self.frame_sampling_strategy:
+            ratio = 0.9
+        if ratio != 1.0:
+            need = mc["num_all_voxels"] * ratio
+            kept, covered = [], 0
+            for frame_file, n in zip(frame_files, voxel_nums):
+                kept.append(frame_file)
+                covered += n
+                if covered >= need:
+                    break
+            frame_files = kept
+        frame_files.sort(key=lambda file: int(file.split("/")[-1].split(".")[0]))
+        return frame_files
+
+    def sample_frame_files(self, video_id: str, force_sample: bool = False, frames_upbound: int = 0):
+        """:162-194 -- uniform np.linspace over the scene's frames (10 unless force_sample)."""
+        frame_files = [os.path.join(self.video_folder, img["img_path"]) for img in self.scene[video_id]["images"]]
+        n = frames_upbound if force_sample else 10
+        picks = np.linspace(0, len(frame_files) - 1, n, dtype=int)
+        return [frame_files[i] for i in picks]
+
+    # ---- geometry --------------------------------------------------------------------------------
+    def load_frames(self, video_id: str, frame_files):
+        """Raw inputs of :196-230: uint16 depth stack, float32(axis_align @ pose), float32 intrinsics."""
+        meta_info = self.scene[video_id]
+        axis_align = np.array(meta_info["axis_align_matrix"], dtype=np.float64)
+        intr = np.array(meta_info["depth_cam2img"], dtype=np.float64)
+        depths, poses = [], []
+        for frame_path in frame_files:
+            with Image.open(frame_path.replace(".jpg", ".png")) as im:
+                d = np.array(im)
+            if d.dtype != np.uint16:
+                d = d.astype(np.int32)
+            depths.append(d)
+            poses.append(axis_align @ np.loadtxt(frame_path.replace("jpg", "txt")))
+        depth = np.stack(depths)
+        depth_t = torch.from_numpy(depth.view(np.int16)) if depth.dtype == np.uint16 else torch.from_numpy(depth)
+        poses_t = torch.from_numpy(np.stack(poses)).float()
+        intr_t = torch.from_numpy(intr).unsqueeze(0).repeat(len(frame_files), 1, 1).float()
+        return depth_t, poses_t, intr_t
+
+    def _clamp_for(self, video_id: str, do_normalize: bool):
+        if not do_normalize:
+            return None
+        scene_id = video_id.split("/")[-1]
+        return (self.pc_min[scene_id].tolist(), self.pc_max[scene_id].tolist())
+
+    def calculate_world_coords(self, video_id: str, frame_files, do_normalize=False):
+        """:196-238 -> {"world_coords": (V,H,W,3) float32} on the CUDA device (always eager: the MC
+        preprocessing script consumes full-resolution coordinates, max_coverage_sampling.py:34-37)."""
+        depth, poses, intr = self.load_frames(video_id, frame_files)
+        return {"world_coords": unproject(intr, poses, depth, clamp=self._clamp_for(video_id, do_normalize))}
+
+    def preprocess(self, video_id: str, image_processor, force_sample: bool = False, frames_upbound: int = 0,
+                   strategy: str = "center_crop"):
+        """:242-326 -> {"images", "world_coords", "video_size", "boundry", "objects"}."""
+        if "mc" in self.frame_sampling_strategy:
+            frame_files = self.sample_frame_files_mc(video_id, frames_upbound=frames_upbound,
+                                                     do_shift=("shift" in self.frame_sampling_strategy))
+        else:
+            frame_files = self.sample_frame_files(video_id, force_sample=force_sample, frames_upbound=frames_upbound)
+        depth, poses, intr = self.load_frames(video_id, frame_files)
+        clamp = self._clamp_for(video_id, "norm" in self.frame_sampling_strategy)
+        V, H, W = depth.shape
+
+        images = []
+        for frame_file in frame_files:
+            with Image.open(frame_file) as img:
+                images.append(img.convert("RGB"))
+        crop_size = image_processor.crop_size["width"]
+        if strategy == "resize":
+            images = [frame.resize((crop_size, crop_size)) for frame in images]
+        elif strategy == "center_crop":
+            new_height, new_width = crop_size, int(W * (crop_size / H))
+            left, top = (new_width - crop_size) // 2, (new_height - crop_size) // 2
+            images = [frame.resize((new_width, new_height)).crop((left, top, left + crop_size, top + crop_size)) for frame in images]
+
+        handle = LazyWorldCoords(depth, poses, intr, crop_size=crop_size, strategy=strategy, clamp=clamp)
+        if self.lazy:
+            world_coords = handle
+            boundry = _LazyBoundary(depth, poses, intr, clamp)
+        else:
+            world_coords = handle.materialize()
+            boundry = boundary(intr, poses, depth, clamp)
+        return {
+            "images": images,
+            "world_coords": world_coords,
+            "video_size": len(images),
+            "boundry": boundry,
+            "objects": torch.tensor(self.scan2obj[video_id]),
+        }
+
+    def process_3d_video(self, video_id: str, image_processor, force_sample: bool = False, frames_upbound: int = 0,
+                         strategy: str = "center_crop"):
+        """:329-345 -- preprocess + SigLIP image preprocessing of the RGB frames."""
+        video_dict = self.preprocess(video_id, image_processor, force_sample, frames_upbound, strategy)
+        video_dict["images"] = image_processor.preprocess(video_dict["images"], return_tensors="pt")["pixel_values"]
+        return video_dict
+
+    def discrete_point(self, xyz):
+        """:348-358 -- host twin of discrete_coords on a list of points; returns nested int lists.
+        A handful of points per call (box centres, the origin): plain torch on the host, as upstream."""
+        xyz = torch.tensor(xyz)
+        if self.min_xyz_range is not None:
+            xyz = torch.maximum(xyz, self.min_xyz_range.to(xyz.device))
+        if self.max_xyz_range is not None:
+            xyz = torch.minimum(xyz, self.max_xyz_range.to(xyz.device))
+        if self.min_xyz_range is not None:
+            xyz = xyz - self.min_xyz_range.to(xyz.device)
+        xyz = xyz / self.voxel_size
+        return xyz.round().int().tolist()
+
+
+class _LazyBoundary:
+    """`boundry` is dropped by merge_video_dict and unused downstream; compute on demand."""
+
+    def __init__(self, depth, poses, intr, clamp):
+        self._args, self._val = (depth, poses, intr, clamp), None
+
+    def tensor(self) -> torch.Tensor:
+        if self._val is None:
+            d, p, k, c = self._args
+            self._val = boundary(k, p, d, c).cpu()
+        return self._val
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.tensor(), name)
+
+    def __getitem__(self, i):
+        return self.tensor()[i]
+
+
+def merge_video_dict(video_dict_list):
+    """llava/video_utils.py:361-373: stack world_coords/images/objects over the batch, collect the
+    non-None box_input entries, drop every other key.  Lazy handles are merged into one batched handle."""
+    new_video_dict = {"box_input": []}
+    for k in video_dict_list[0]:
+        if k in ["world_coords", "images", "objects"]:
+            vals = [vd[k] for vd in video_dict_list]
+            if k == "world_coords" and isinstance(vals[0], LazyWorldCoords):
+                h0 = vals[0]
+                new_video_dict[k] = LazyWorldCoords(torch.stack([v.depth for v in vals]), torch.stack([v.poses for v in vals]),
+                                                    torch.stack([v.intrinsics for v in vals]), h0.crop_size, h0.strategy, h0.clamp,
+                                                    h0.dtype, batched=True)
+            else:
+                new_video_dict[k] = torch.stack(vals)
+        elif k in ["box_input"]:
+            for vd in video_dict_list:
+                if vd[k] is not None:
+                    new_video_dict["box_input"].append(vd[k])
+    new_video_dict["box_input"] = torch.Tensor(new_video_dict["box_input"])
+    return new_video_dict
