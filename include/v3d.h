@@ -46,6 +46,11 @@ typedef void* v3d_stream_t;
 
 int v3d_version(void);
 const char* v3d_last_error(void);
+/* Diagnostic: the kernels divide by per-frame constants (depth scale, fx, fy, voxel size) with a
+ * hoisted-reciprocal sequence that must equal IEEE division bit for bit.  This runs that sequence
+ * against div.rn.f32 for all 2^32 dividends of `divisor` and writes the number of mismatches
+ * (device uint64) -- expected 0. */
+int v3d_selftest_division(float divisor, uint64_t* mismatches, v3d_stream_t stream);
 /* number of points per token for a pool mode: avg 1, minmax 2, sample9/5/1 -> 9/5/1 */
 int v3d_pool_points(int pool_mode);
 

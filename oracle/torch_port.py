@@ -1,0 +1,99 @@
+"""TEST / BASELINE INFRASTRUCTURE ONLY -- torch-CPU port of the reference's front end.
+
+The reference (pure Python) runs this path as a sequence of ATen CPU operators inside DataLoader
+workers plus a handful of tiny kernels in the model forward.  /root/reference cannot travel to the
+GPU box, so `bench.py`'s cpu_baseline and `--impl reference` legs time this port instead: the same
+operator sequence (ATen bmm / elementwise / cv2.resize / avg_pool2d / sin / cos), the same
+intermediate tensors, all host threads torch will use.  It is also a second checker: pinned
+bit-for-bit against the reference in tests/test_oracle_golden.py::test_torch_port_*.
+
+Nothing under video-3d-llm_b200/ imports this module.
+"""
+from __future__ import annotations
+
+import cv2
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def unproject(intrinsics: torch.Tensor, poses: torch.Tensor, depths: torch.Tensor) -> torch.Tensor:
+    """llava/video_utils.py:38-68: pixel grid -> camera rays scaled by depth/1000 -> homogeneous
+    points -> bmm with the pose -> divide by w.  Materialises the same intermediates as upstream."""
+    n, h, w = depths.shape
+    rows, cols = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    u = cols.reshape(1, h * w).repeat(n, 1)
+    v = rows.reshape(1, h * w).repeat(n, 1)
+    k = {name: intrinsics[:, i, j].reshape(n, 1).repeat(1, h * w) for name, (i, j) in
+         {"fx": (0, 0), "fy": (1, 1), "cx": (0, 2), "cy": (1, 2)}.items()}
+    z = depths.reshape(n, h * w) / 1000
+    x = (u - k["cx"]) * z / k["fx"]
+    y = (v - k["cy"]) * z / k["fy"]
+    cam = torch.stack((x, y, z, torch.ones_like(x)), dim=-1)
+    world = torch.bmm(poses, cam.transpose(1, 2)).transpose(1, 2)
+    world = world[..., :3] / world[..., 3:4]
+    return world.reshape(n, h, w, 3)
+
+
+def boundary(world: torch.Tensor) -> torch.Tensor:
+    """llava/video_utils.py:273-277: six separate reductions with .item()."""
+    flat = world.reshape(-1, 3)
+    vals = []
+    for a in range(3):
+        vals += [flat[:, a].min().item(), flat[:, a].max().item()]
+    return torch.tensor(vals)
+
+
+def resize_center_crop(world: torch.Tensor, crop: int = 384) -> torch.Tensor:
+    """llava/video_utils.py:296-321: per-frame cv2 nearest resize to (W*crop/H, crop), centre crop,
+    np.stack, from_numpy."""
+    n, h, w, _ = world.shape
+    new_w = int(w * (crop / h))
+    left = (new_w - crop) // 2
+    frames = [cv2.resize(f.numpy(), (new_w, crop), interpolation=cv2.INTER_NEAREST)[:, left:left + crop, :] for f in world]
+    return torch.from_numpy(np.stack(frames))
+
+
+def average_coordinate_in_patch(coords: torch.Tensor, patch: int = 27) -> torch.Tensor:
+    """llava/model/llava_arch.py:213-223."""
+    c = coords[:, :-6, :-6, :].permute(0, 3, 1, 2)
+    return F.avg_pool2d(c, kernel_size=patch, stride=patch).permute(0, 2, 3, 1)
+
+
+def discrete_coords(coords: torch.Tensor, lo=(-15, -15, -5), hi=(15, 15, 5), voxel: float = 0.1) -> torch.Tensor:
+    """llava/model/llava_arch.py:259-272."""
+    lo_t, hi_t = torch.tensor(lo), torch.tensor(hi)
+    c = torch.minimum(torch.maximum(coords, lo_t), hi_t)
+    return ((c - lo_t) / voxel).round()
+
+
+def pe_sine3d(x: torch.Tensor, embedding_size: int, temperature: float = 10000) -> torch.Tensor:
+    """llava/model/position_encoding.py:17-49 for n_points == 1 and even num_feats."""
+    nf = embedding_size // 3
+    dim_t = torch.arange(nf, dtype=torch.float32)
+    dim_t = temperature ** (2 * (dim_t // 2) / nf)
+    parts = []
+    for a in range(3):
+        pos = x[:, :, a, None] / dim_t
+        parts.append(torch.stack((pos[:, :, 0::2].sin(), pos[:, :, 1::2].cos()), dim=3).flatten(2))
+    pos = torch.cat(parts, dim=2)
+    out = torch.zeros((x.shape[0], x.shape[1], embedding_size), dtype=x.dtype)
+    out[:, :, :pos.shape[2]] = pos
+    return out
+
+
+def frontend(depths: torch.Tensor, poses: torch.Tensor, intrinsics: torch.Tensor, patch: int, embedding_size: int,
+             tokens: torch.Tensor | None = None, with_boundary: bool = False):
+    """The chain a1 -> a3(iii) -> a4 -> a5 -> a6 -> a7 of SURVEY.md section 8 as the reference runs it
+    (fp32 coordinates, PE cast to the token dtype before the add).  with_boundary adds the unused
+    scene-AABB reductions of video_utils.py:273-277 ("as shipped")."""
+    world = unproject(intrinsics.float(), poses.float(), depths.float())
+    if with_boundary:
+        boundary(world)
+    coords = resize_center_crop(world)
+    pooled = average_coordinate_in_patch(coords, patch)
+    disc = discrete_coords(pooled)
+    pe = pe_sine3d(disc.flatten(1, 2), embedding_size)
+    if tokens is not None:
+        return tokens + pe.to(tokens.dtype), pooled, disc
+    return pe.to(torch.bfloat16), pooled, disc

@@ -450,3 +450,18 @@ def test_mc_sampler_golden(golden_dir):
         assert [cand[i] for i in res["order"]] == [int(f.split("/")[-1].split(".")[0]) // 10 for f in gold["frame_files"]]
         assert res["gains"] == gold["voxel_nums"]
         assert (res["n_all"], res["n_sel"]) == (gold["num_all_voxels"], gold["num_select_voxels"])
+
+
+# ---------------------------------------------------------------------------------------------
+# the hoisted-reciprocal division is IEEE division, for every dividend
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("divisor", [1000.0, 577.87, 577.87 * 0.25, 0.1, 0.05, 518.8579, 1170.1877, -3.0, 1e-30, 3e38, 2.0 ** -45])
+def test_exact_division_exhaustive(divisor):
+    """div_exact(a, b) == a / b (div.rn.f32) for all 2^32 bit patterns of a: the depth scale, ScanNet-like
+    focal lengths, voxel sizes, a negative divisor, and divisors outside the fast range (which must take
+    the IEEE fallback)."""
+    lib = cabi.load()
+    bad = torch.zeros(1, dtype=torch.int64, device=DEV)
+    cabi.check(lib.v3d_selftest_division(float(np.float32(divisor)), bad.data_ptr(), cabi.stream_ptr(DEV)))
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0

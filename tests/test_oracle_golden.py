@@ -231,3 +231,24 @@ def test_mc_prefix_cut(D, strat):
         for ub in (32, 8, 3):
             mine = O.mc_prefix_cut(s["frame_files"], s["voxel_nums"], s["num_all_voxels"], strat, ub)
             assert mine == D["video_processor"][strat][name][f"files_ub{ub}"]
+
+
+# ---------------------------------------------------------------------------------------------
+# the torch-CPU port timed by bench.py as the CPU baseline is pinned too
+# ---------------------------------------------------------------------------------------------
+def test_torch_port_bit_exact(G, scene0):
+    from oracle import torch_port as TP
+
+    depth = torch.from_numpy(scene0.depth_u16().astype(np.int32))
+    tokens = synthetic.make_tokens(0, 2, 196, 3584)
+    out, pooled, disc = TP.frontend(depth, scene0.poses, scene0.intrinsics, 27, 3584, tokens=tokens)
+    world = TP.unproject(scene0.intrinsics, scene0.poses, depth.float())
+    assert sha(world.numpy()) == str(G["world_sha"])
+    np.testing.assert_array_equal(TP.boundary(world).numpy(), G["boundry"])
+    assert sha(TP.resize_center_crop(world).numpy()) == str(G["coords_sha"])
+    np.testing.assert_array_equal(pooled.numpy(), G["avg27"])
+    np.testing.assert_array_equal(disc.numpy(), G["disc27"])
+    assert sha(out.view(torch.int16).numpy()) == str(G["added3584_bf16_sha"])
+    pe, pooled14, disc14 = TP.frontend(depth, scene0.poses, scene0.intrinsics, 14, 1152)
+    np.testing.assert_array_equal(pooled14.numpy(), G["avg14"])
+    assert sha(pe.view(torch.int16).numpy()) == str(G["pe1152_bf16_sha"])

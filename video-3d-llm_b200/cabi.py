@@ -25,7 +25,7 @@ MC_RECORD_INTS = 2 * MC_MAX_PICK + 4
 
 # every symbol include/v3d.h declares (tests check that the library exports them all)
 SYMBOLS = (
-    "v3d_version", "v3d_last_error", "v3d_pool_points", "v3d_unproject", "v3d_boundary", "v3d_pool_coords",
+    "v3d_version", "v3d_last_error", "v3d_selftest_division", "v3d_pool_points", "v3d_unproject", "v3d_boundary", "v3d_pool_coords",
     "v3d_discretize", "v3d_pe_table_bytes", "v3d_pe_table_build", "v3d_pe_sine3d", "v3d_frontend_pe",
     "v3d_mc_hash_slots", "v3d_mc_sample", "v3d_mc_voxelize", "v3d_mc_greedy", "v3d_mc_voxel_ids", "v3d_pe_mlp",
 )
@@ -81,6 +81,7 @@ def load():
     lib.v3d_version.restype = i
     lib.v3d_last_error.restype = C.c_char_p
     lib.v3d_pool_points.argtypes, lib.v3d_pool_points.restype = [i], i
+    lib.v3d_selftest_division.argtypes = [f, vp, vp]
     lib.v3d_unproject.argtypes = [vp, i, vp, vp, i, i, i, f, vp, vp, i, i, vp, vp, vp]
     lib.v3d_boundary.argtypes = [vp, i, vp, vp, i, i, i, f, vp, vp, vp]
     lib.v3d_pool_coords.argtypes = [vp, i, i, i, i, i, vp, vp]
@@ -97,7 +98,7 @@ def load():
     lib.v3d_pe_mlp.argtypes = [vp, i, i, vp, vp, vp, vp, f, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("v3d_version", "v3d_last_error", "v3d_pool_points", "v3d_pe_table_bytes", "v3d_mc_hash_slots"):
+        if name not in ("v3d_version", "v3d_last_error", "v3d_selftest_division", "v3d_pool_points", "v3d_pe_table_bytes", "v3d_mc_hash_slots"):
             fn.restype = i
     _lib = lib
     return lib

@@ -7,6 +7,8 @@
 #include <math_constants.h>
 #include <stdarg.h>
 
+#include <type_traits>
+
 #include "v3d_common.cuh"
 
 namespace v3d {
@@ -42,6 +44,7 @@ __global__ void __launch_bounds__(kThreads) k_unproject(const void* __restrict__
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t n_groups = (total + 3) / 4;
   const size_t groups_per_block = kThreads;
+  const Divisor ds = make_divisor(depth_scale);
   for (size_t gbase = (size_t)blockIdx.x * groups_per_block; gbase < n_groups; gbase += (size_t)gridDim.x * groups_per_block) {
     const size_t g = gbase + threadIdx.x;
     float vals[12];
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(kThreads) k_unproject(const void* __restrict__
           const int sr = row_map ? __ldg(row_map + r) : r;
           const int sc = col_map ? __ldg(col_map + c) : c;
           const float d = load_depth<DT>(depth, ((size_t)f * H + sr) * W + sc);
-          unproject_px(cam, d, __fsub_rn((float)sc, cam.cx), __fsub_rn((float)sr, cam.cy), depth_scale, x, y, z);
+          unproject_px(cam, d, __fsub_rn((float)sc, cam.cx), __fsub_rn((float)sr, cam.cy), ds, x, y, z);
           x = apply_clamp(clamp, x, 0);
           y = apply_clamp(clamp, y, 1);
           z = apply_clamp(clamp, z, 2);
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(kThreads) k_boundary(const void* __restrict__ 
   // one CTA works on rows of one frame at a time: blockIdx -> (frame, row-slab)
   const int rows_per_cta = 8;
   const int slabs = (H + rows_per_cta - 1) / rows_per_cta;
+  const Divisor ds = make_divisor(depth_scale);
   int mn[3] = {0x7ffffffe, 0x7ffffffe, 0x7ffffffe}, mx[3] = {(int)0x80000001, (int)0x80000001, (int)0x80000001};
   for (int item = blockIdx.x; item < V * slabs; item += gridDim.x) {
     const int f = item / slabs, r0 = (item - f * slabs) * rows_per_cta;
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(kThreads) k_boundary(const void* __restrict__ 
       const int r = r0 + i / W, c = i - (i / W) * W;
       float p[3];
       unproject_px(cam, load_depth<DT>(depth, ((size_t)f * H + r) * W + c), __fsub_rn((float)c, cam.cx),
-                   __fsub_rn((float)r, cam.cy), depth_scale, p[0], p[1], p[2]);
+                   __fsub_rn((float)r, cam.cy), ds, p[0], p[1], p[2]);
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         const float v = apply_clamp(clamp, p[a], a);
@@ -266,71 +270,127 @@ __device__ __forceinline__ void chunk_or(Chunk<OutT>& a, const Chunk<OutT>& b) {
   for (int i = 0; i < n; ++i) reinterpret_cast<uint32_t*>(&a)[i] |= reinterpret_cast<const uint32_t*>(&b)[i];
 }
 
-// PE rows of `n_tok` tokens, 8 channels per step.  s_pts: [n_tok][n_slots] coordinates the PE
-// is evaluated on; s_row: same shape, table row (>= 0) or -1 = evaluate directly.
-// out/tokens point at the first token's row; tail chunks of a row whose width is not a
-// multiple of 8 are written element-wise.
-template <typename OutT, int UNROLL>
-__device__ __forceinline__ void stream_pe(const PeGeom& g, const float* __restrict__ dim_t, const OutT* __restrict__ table,
-                                          const float* s_pts, const int* s_row, const ChunkDesc* s_desc, int n_tok,
-                                          const OutT* tokens, OutT* out) {
-  const int total = n_tok * g.cpt;
-  const bool vec_ok = (g.E & 7) == 0;
-  for (int q0 = threadIdx.x; q0 < total; q0 += kThreads * UNROLL) {
-    Chunk<OutT> tv[UNROLL];
-    int tok[UNROLL], c8[UNROLL];
+template <typename OutT>
+__device__ __forceinline__ Chunk<OutT> chunk_add(const Chunk<OutT>& a, const Chunk<OutT>& b) {
+  // a + b with ONE rounding to OutT per element.  For 16-bit types the packed add rounds the exact
+  // sum once, which equals torch's "add in fp32, round to bf16/fp16" for every pair of inputs: the
+  // fp32 sum of two 8/11-bit significands is exact unless their exponents differ by more than 16/13,
+  // and then the smaller term is below a quarter ulp of the result either way.
+  Chunk<OutT> c;
+  if constexpr (std::is_same<OutT, __nv_bfloat16>::value) {
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int q = q0 + u * kThreads;
-      tok[u] = q / g.cpt;
-      c8[u] = q - tok[u] * g.cpt;
-      if (tokens != nullptr && vec_ok && q < total) tv[u] = chunk_ld_stream(tokens + (size_t)tok[u] * g.E + c8[u] * 8);
+    for (int i = 0; i < 4; ++i)
+      reinterpret_cast<__nv_bfloat162*>(&c)[i] = __hadd2(reinterpret_cast<const __nv_bfloat162*>(&a)[i], reinterpret_cast<const __nv_bfloat162*>(&b)[i]);
+  } else if constexpr (std::is_same<OutT, __half>::value) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      reinterpret_cast<__half2*>(&c)[i] = __hadd2(reinterpret_cast<const __half2*>(&a)[i], reinterpret_cast<const __half2*>(&b)[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c.v[i] = __fadd_rn(a.v[i], b.v[i]);
+  }
+  return c;
+}
+
+// PE chunks that cannot be served from the table (non-integer / out-of-range coordinates): kept out
+// of line so that the sinf/cosf slow paths do not bloat the streaming loop.  One warp, one token.
+template <typename OutT>
+__device__ __noinline__ void stream_pe_direct(const PeGeom g, const float* __restrict__ dim_t, const OutT* __restrict__ table,
+                                              const float* pts, const int* off, const ChunkDesc* s_desc, const OutT* trow,
+                                              OutT* orow) {
+  const int lane = threadIdx.x & 31;
+  for (int c8 = lane; c8 < g.cpt; c8 += 32) {
+    const ChunkDesc d = s_desc[c8];
+    const int o0 = (d.s0 != 0xFF) ? off[d.s0] : 0;
+    const int o1 = (d.s1 != 0xFF) ? off[d.s1] : 0;
+    if (o0 >= 0 && o1 >= 0) continue;  // already written by the table path
+    Chunk<OutT> pe = chunk_zero<OutT>();
+#pragma unroll 1
+    for (int e = 0; e < 8; ++e) {
+      const int ch = c8 * 8 + e;
+      const int s = ch / g.nf;
+      if (s >= g.n_slots) continue;
+      const int j = ch - s * g.nf;
+      const int o = off[s];
+      pe.v[e] = (o >= 0) ? table[o + (s * g.nf - ((s * g.nf) & ~7)) + j] : Elem<OutT>::from(pe_value(pts[s], j, dim_t));
     }
+    if (trow) pe = chunk_add(chunk_ld_stream(trow + c8 * 8), pe);
+    chunk_st_stream(orow + c8 * 8, pe);
+  }
+}
+
+// PE rows of `n_tok` tokens: one warp per token, lanes stride the 16-byte chunks of its row, U
+// chunks in flight per lane (all loads of a batch are issued before the first add/store; the
+// compiler cannot do that itself because tokens may alias out).
+//   s_pts [n_tok][n_slots]  coordinates the PE is evaluated on
+//   s_off [n_tok][n_slots]  element offset of the slot's table row, or -1 = evaluate directly
+template <typename OutT, int U>
+__device__ __forceinline__ void stream_pe(const PeGeom& g, const float* __restrict__ dim_t, const OutT* __restrict__ table,
+                                          const float* s_pts, const int* s_off, const ChunkDesc* s_desc, int n_tok,
+                                          const OutT* tokens, OutT* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kThreads / 32;
+  if ((g.E & 7) == 0) {
+    for (int tok = warp; tok < n_tok; tok += kWarps) {
+      const int* off = s_off + tok * g.n_slots;
+      const OutT* trow = tokens ? tokens + (size_t)tok * g.E : nullptr;
+      OutT* orow = out + (size_t)tok * g.E;
+      bool need_direct = false;
+      for (int c0 = lane; c0 < g.cpt; c0 += 32 * U) {
+        Chunk<OutT> tv[U], pe[U];
+        bool ok[U];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int q = q0 + u * kThreads;
-      if (q >= total) break;
-      const ChunkDesc d = s_desc[c8[u]];
-      Chunk<OutT> pe = chunk_zero<OutT>();
-      const int r0 = (d.s0 != 0xFF) ? s_row[tok[u] * g.n_slots + d.s0] : 0;
-      const int r1 = (d.s1 != 0xFF) ? s_row[tok[u] * g.n_slots + d.s1] : 0;
-      if (r0 >= 0 && r1 >= 0) {
-        if (d.s0 != 0xFF) pe = chunk_ldg(table + ((size_t)d.s0 * (g.rows + 1) + r0) * g.Wt + d.k0);
-        if (d.s1 != 0xFF) chunk_or(pe, chunk_ldg(table + ((size_t)d.s1 * (g.rows + 1) + r1) * g.Wt + d.k1));
-      } else {
+        for (int u = 0; u < U; ++u) {
+          const int c8 = c0 + 32 * u;
+          ok[u] = false;
+          if (c8 < g.cpt) {
+            const ChunkDesc d = s_desc[c8];
+            const int o0 = (d.s0 != 0xFF) ? off[d.s0] : 0;
+            const int o1 = (d.s1 != 0xFF) ? off[d.s1] : 0;
+            if (o0 >= 0 && o1 >= 0) {
+              ok[u] = true;
+              if (trow) tv[u] = chunk_ld_stream(trow + c8 * 8);
+              pe[u] = (d.s0 != 0xFF) ? chunk_ldg(table + o0 + d.k0) : chunk_zero<OutT>();
+              if (d.s1 != 0xFF) chunk_or(pe[u], chunk_ldg(table + o1 + d.k1));
+            } else {
+              need_direct = true;
+            }
+          }
+        }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int ch = c8[u] * 8 + e;
-          const int s = ch / g.nf;
-          if (s < g.n_slots) pe.v[e] = Elem<OutT>::from(pe_value(s_pts[tok[u] * g.n_slots + s], ch - s * g.nf, dim_t));
+        for (int u = 0; u < U; ++u) {
+          if (ok[u]) chunk_st_stream(orow + (c0 + 32 * u) * 8, trow ? chunk_add(tv[u], pe[u]) : pe[u]);
         }
       }
-      OutT* o = out + (size_t)tok[u] * g.E + c8[u] * 8;
-      if (vec_ok) {
-        if (tokens != nullptr) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            pe.v[e] = Elem<OutT>::from(__fadd_rn(Elem<OutT>::to(tv[u].v[e]), Elem<OutT>::to(pe.v[e])));
-        }
-        chunk_st_stream(o, pe);
-      } else {
-        for (int e = 0; e < 8 && c8[u] * 8 + e < g.E; ++e) {
-          float v = Elem<OutT>::to(pe.v[e]);
-          if (tokens != nullptr) v = __fadd_rn(Elem<OutT>::to(tokens[(size_t)tok[u] * g.E + c8[u] * 8 + e]), v);
-          o[e] = Elem<OutT>::from(tokens != nullptr ? v : Elem<OutT>::to(pe.v[e]));
-        }
+      if (__any_sync(0xffffffffu, need_direct)) stream_pe_direct<OutT>(g, dim_t, table, s_pts + tok * g.n_slots, off, s_desc, trow, orow);
+    }
+  } else {
+    // rows that are not a whole number of 16-byte chunks: element-wise (rare configuration)
+    for (int i = threadIdx.x; i < n_tok * g.E; i += kThreads) {
+      const int tok = i / g.E, ch = i - tok * g.E;
+      const int s = ch / g.nf;
+      float v = 0.0f;
+      if (s < g.n_slots) {
+        const int o = s_off[tok * g.n_slots + s];
+        const int j = ch - s * g.nf;
+        v = (o >= 0) ? Elem<OutT>::to(table[o + (s * g.nf - ((s * g.nf) & ~7)) + j]) : Elem<OutT>::to(Elem<OutT>::from(pe_value(s_pts[tok * g.n_slots + s], j, dim_t)));
       }
+      const size_t oidx = (size_t)tok * g.E + ch;
+      if (tokens) v = __fadd_rn(Elem<OutT>::to(tokens[oidx]), v);
+      out[oidx] = Elem<OutT>::from(v);
     }
   }
 }
 
-// table row for a coordinate: integer-valued in [0,rows) -> that row, NaN -> the NaN row,
-// anything else -> -1 (direct evaluation)
-__device__ __forceinline__ int pe_row_of(float x, int rows, bool have_table) {
+// element offset of the table row serving coordinate x in slot s: integer-valued in [0,rows) -> that
+// row, NaN -> the NaN row, anything else -> -1 (direct evaluation)
+__device__ __forceinline__ int pe_row_offset(float x, int s, const PeGeom& g, bool have_table) {
   if (!have_table) return -1;
-  if (x != x) return rows;
-  if (x >= 0.0f && x < (float)rows && x == rintf(x)) return (int)x;
-  return -1;
+  int row;
+  if (x != x) row = g.rows;
+  else if (x >= 0.0f && x < (float)g.rows && x == rintf(x)) row = (int)x;
+  else return -1;
+  return (s * (g.rows + 1) + row) * g.Wt;
 }
 
 // stand-alone PE: llava/model/position_encoding.py:17-49 (+ llava_arch.py:515 add)
@@ -343,7 +403,7 @@ __global__ void __launch_bounds__(kThreads) k_pe_sine3d(const float* __restrict_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ChunkDesc* s_desc = reinterpret_cast<ChunkDesc*>(smem_raw);
   float* s_pts = reinterpret_cast<float*>(s_desc + g.cpt);
-  int* s_row = reinterpret_cast<int*>(s_pts + kPeTokPerCta * g.n_slots);
+  int* s_off = reinterpret_cast<int*>(s_pts + kPeTokPerCta * g.n_slots);
   for (int i = threadIdx.x; i < g.cpt; i += kThreads) s_desc[i] = make_chunk_desc(i, g);
   for (size_t t0 = (size_t)blockIdx.x * kPeTokPerCta; t0 < n_tokens; t0 += (size_t)gridDim.x * kPeTokPerCta) {
     const int n_tok = (int)min((size_t)kPeTokPerCta, n_tokens - t0);
@@ -351,10 +411,10 @@ __global__ void __launch_bounds__(kThreads) k_pe_sine3d(const float* __restrict_
     for (int i = threadIdx.x; i < n_tok * g.n_slots; i += kThreads) {
       const float x = __ldg(coords + t0 * g.n_slots + i);
       s_pts[i] = x;
-      s_row[i] = pe_row_of(x, g.rows, table != nullptr);
+      s_off[i] = pe_row_offset(x, i % g.n_slots, g, table != nullptr);
     }
     __syncthreads();
-    stream_pe<OutT, 4>(g, dim_t, table, s_pts, s_row, s_desc, n_tok, tokens ? tokens + t0 * g.E : nullptr, out + t0 * g.E);
+    stream_pe<OutT, 3>(g, dim_t, table, s_pts, s_off, s_desc, n_tok, tokens ? tokens + t0 * g.E : nullptr, out + t0 * g.E);
   }
 }
 
@@ -390,7 +450,8 @@ __host__ __device__ inline size_t fused_smem_bytes(const FusedParams& p, bool st
   size_t b = 16;                                              // mbarrier
   if (stage_depth) b += (size_t)p.patch * p.span;             // depth rows
   b += (size_t)2 * 3 * p.Sp_pad * sizeof(float);              // double-buffered xyz row
-  b += (size_t)p.grid * 3 * p.n_points * (sizeof(float) + sizeof(int));  // PE coordinates + table rows
+  b += (size_t)p.patch * 2 * sizeof(int);                     // source row index + (row - cy) per patch row
+  b += (size_t)p.grid * 3 * p.n_points * (sizeof(float) + sizeof(int));  // PE coordinates + table row offsets
   b = (b + 7) & ~(size_t)7;
   if (p.pe_mode != V3D_PE_NONE) b += (size_t)p.g.cpt * sizeof(ChunkDesc);
   return b;
@@ -408,9 +469,11 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   unsigned char* s_depth = smem_raw + 16;
   float* s_row = reinterpret_cast<float*>(s_depth + ((FROM_DEPTH && USE_TMA) ? (size_t)P * p.span : 0));
-  float* s_pts = s_row + 2 * 3 * p.Sp_pad;
-  int* s_tab = reinterpret_cast<int*>(s_pts + G * n_slots);
-  ChunkDesc* s_desc = reinterpret_cast<ChunkDesc*>((reinterpret_cast<uintptr_t>(s_tab + G * n_slots) + 7) & ~(uintptr_t)7);
+  int* s_srow = reinterpret_cast<int*>(s_row + 2 * 3 * p.Sp_pad);
+  float* s_vm = reinterpret_cast<float*>(s_srow + P);
+  float* s_pts = s_vm + P;
+  int* s_off = reinterpret_cast<int*>(s_pts + G * n_slots);
+  ChunkDesc* s_desc = reinterpret_cast<ChunkDesc*>((reinterpret_cast<uintptr_t>(s_off + G * n_slots) + 7) & ~(uintptr_t)7);
 
   // ---- stage the P depth rows of this patch row with the TMA unit
   if constexpr (FROM_DEPTH && USE_TMA) {
@@ -435,38 +498,51 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
   }
 
   Camera cam;
-  if constexpr (FROM_DEPTH) cam = load_camera(p.poses, p.intr, f);
+  Divisor ds;
+  if constexpr (FROM_DEPTH) {
+    cam = load_camera(p.poses, p.intr, f);
+    ds = make_divisor(p.depth_scale);
+  }
+  for (int dy = t; dy < P; dy += kThreads) {
+    const int sr = FROM_DEPTH ? __ldg(p.row_map + gi * P + dy) : gi * P + dy;
+    s_srow[dy] = sr;
+    s_vm[dy] = FROM_DEPTH ? __fsub_rn((float)sr, cam.cy) : 0.0f;
+  }
 
-  // per-thread column constants: thread t owns dst columns t and (second round, taken from the
-  // top of the block so that the chain warps at the bottom get less unprojection work)
-  int col[2], scol[2];
+  // per-thread column constants: thread t owns dst column t and (second round, taken from the top of
+  // the block so that the chain warps at the bottom get less unprojection work) 511 - t
+  int col[2];
   float um[2];
+  size_t src_off[2];  // FROM_DEPTH: byte offset inside a staged row / element offset inside a global row
   col[0] = (t < p.Sp) ? t : -1;
   col[1] = (kThreads + (kThreads - 1 - t) < p.Sp) ? kThreads + (kThreads - 1 - t) : -1;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
-    scol[k] = 0;
     um[k] = 0.f;
+    src_off[k] = 0;
     if (col[k] >= 0) {
-      scol[k] = FROM_DEPTH ? __ldg(p.col_map + col[k]) : col[k];
-      if constexpr (FROM_DEPTH) um[k] = __fsub_rn((float)scol[k], cam.cx);
+      const int sc = FROM_DEPTH ? __ldg(p.col_map + col[k]) : col[k];
+      if constexpr (FROM_DEPTH) {
+        um[k] = __fsub_rn((float)sc, cam.cx);
+        src_off[k] = USE_TMA ? (size_t)(sc * kEsz - p.col_lo_byte) : (size_t)sc;
+      } else {
+        src_off[k] = (size_t)sc * 3;
+      }
     }
   }
-
+  __syncthreads();  // s_srow / s_vm / s_desc visible
   if constexpr (FROM_DEPTH && USE_TMA) mbar_wait(bar, 0);
 
   const bool is_sample = p.pool_mode >= V3D_POOL_SAMPLE9;
   if (!is_sample) {
     // ---- chains: thread q < 3G owns (axis a = q / G, patch j = q % G)
-    const int q = t;
-    const bool chain = q < 3 * G;
-    const int a = chain ? q / G : 0, j = chain ? q - a * G : 0;
+    const bool chain = t < 3 * G;
+    const int a = chain ? t / G : 0, j = chain ? t - a * G : 0;
     float acc = 0.0f, mx = -CUDART_INF_F, mneg = -CUDART_INF_F;
+    const float* chain_src = s_row + a * p.Sp_pad + j * P;
     for (int dy = 0; dy < P; ++dy) {
       float* buf = s_row + (dy & 1) * 3 * p.Sp_pad;
-      const int sr = FROM_DEPTH ? __ldg(p.row_map + gi * P + dy) : gi * P + dy;
-      float vm = 0.f;
-      if constexpr (FROM_DEPTH) vm = __fsub_rn((float)sr, cam.cy);
+      const float vm = s_vm[dy];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         if (col[k] < 0) continue;
@@ -474,19 +550,21 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
         if constexpr (FROM_DEPTH) {
           float d;
           if constexpr (USE_TMA) {
-            const unsigned char* sp = s_depth + (size_t)dy * p.span + (scol[k] * kEsz - p.col_lo_byte);
+            const unsigned char* sp = s_depth + (size_t)dy * p.span + src_off[k];
             if constexpr (DT == V3D_DEPTH_U16) d = (float)*reinterpret_cast<const uint16_t*>(sp);
             else if constexpr (DT == V3D_DEPTH_I32) d = (float)*reinterpret_cast<const int32_t*>(sp);
             else d = *reinterpret_cast<const float*>(sp);
           } else {
-            d = load_depth<DT>(p.depth, ((size_t)f * p.H + sr) * p.W + scol[k]);
+            d = load_depth<DT>(p.depth, ((size_t)f * p.H + s_srow[dy]) * p.W + src_off[k]);
           }
-          unproject_px(cam, d, um[k], vm, p.depth_scale, x, y, z);
-          x = apply_clamp(p.clamp, x, 0);
-          y = apply_clamp(p.clamp, y, 1);
-          z = apply_clamp(p.clamp, z, 2);
+          unproject_px(cam, d, um[k], vm, ds, x, y, z);
+          if (p.clamp.on) {
+            x = apply_clamp(p.clamp, x, 0);
+            y = apply_clamp(p.clamp, y, 1);
+            z = apply_clamp(p.clamp, z, 2);
+          }
         } else {
-          const float* src = p.coords_in + (((size_t)f * p.S + sr) * p.S + scol[k]) * 3;
+          const float* src = p.coords_in + ((size_t)f * p.S + s_srow[dy]) * p.S * 3 + src_off[k];
           x = __ldg(src);
           y = __ldg(src + 1);
           z = __ldg(src + 2);
@@ -497,7 +575,7 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
       }
       __syncthreads();
       if (chain) {
-        const float* src = buf + a * p.Sp_pad + j * P;
+        const float* src = chain_src + (dy & 1) * 3 * p.Sp_pad;
         if (p.pool_mode == V3D_POOL_AVG) {
 #pragma unroll 9
           for (int dx = 0; dx < P; ++dx) acc = __fadd_rn(acc, src[dx]);
@@ -513,13 +591,14 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
     }
     if (chain) {
       const size_t tok = ((size_t)f * G + gi) * G + j;
+      const bool have_table = p.table != nullptr;
       if (p.pool_mode == V3D_POOL_AVG) {
         const float v = __fdiv_rn(acc, (float)(P * P));
         const float pv = p.disc.on ? discretize1(p.disc, v, a) : v;
         if (p.pooled_out) p.pooled_out[tok * 3 + a] = v;
         if (p.pe_coords_out) p.pe_coords_out[tok * 3 + a] = pv;
         s_pts[j * n_slots + a] = pv;
-        s_tab[j * n_slots + a] = pe_row_of(pv, p.g.rows, p.table != nullptr);
+        s_off[j * n_slots + a] = pe_row_offset(pv, a, p.g, have_table);
       } else {  // minmax: point 0 = min, point 1 = max (llava_arch.py:237)
         const float v2[2] = {-mneg, mx};
 #pragma unroll
@@ -528,7 +607,7 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
           if (p.pooled_out) p.pooled_out[(tok * 2 + pt) * 3 + a] = v2[pt];
           if (p.pe_coords_out) p.pe_coords_out[(tok * 2 + pt) * 3 + a] = pv;
           s_pts[j * n_slots + pt * 3 + a] = pv;
-          s_tab[j * n_slots + pt * 3 + a] = pe_row_of(pv, p.g.rows, p.table != nullptr);
+          s_off[j * n_slots + pt * 3 + a] = pe_row_offset(pv, pt * 3 + a, p.g, have_table);
         }
       }
     }
@@ -543,7 +622,7 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
       if constexpr (FROM_DEPTH) {
         const int sr = __ldg(p.row_map + r), sc = __ldg(p.col_map + c);
         const float d = load_depth<DT>(p.depth, ((size_t)f * p.H + sr) * p.W + sc);
-        unproject_px(cam, d, __fsub_rn((float)sc, cam.cx), __fsub_rn((float)sr, cam.cy), p.depth_scale, v[0], v[1], v[2]);
+        unproject_px(cam, d, __fsub_rn((float)sc, cam.cx), __fsub_rn((float)sr, cam.cy), ds, v[0], v[1], v[2]);
 #pragma unroll
         for (int a = 0; a < 3; ++a) v[a] = apply_clamp(p.clamp, v[a], a);
       } else {
@@ -559,7 +638,7 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
         if (p.pooled_out) p.pooled_out[(tok * np + k) * 3 + a] = v[a];
         if (p.pe_coords_out) p.pe_coords_out[(tok * np + k) * 3 + a] = pv;
         s_pts[j * n_slots + k * 3 + a] = pv;
-        s_tab[j * n_slots + k * 3 + a] = pe_row_of(pv, p.g.rows, p.table != nullptr);
+        s_off[j * n_slots + k * 3 + a] = pe_row_offset(pv, k * 3 + a, p.g, p.table != nullptr);
       }
     }
   }
@@ -569,7 +648,7 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
   // ---- stream the PE rows of this patch row (G tokens x E channels), fused token add
   const size_t row0 = ((size_t)f * G + gi) * G;
   const OutT* tokens = reinterpret_cast<const OutT*>(p.tokens_in);
-  stream_pe<OutT, 4>(p.g, p.dim_t, reinterpret_cast<const OutT*>(p.table), s_pts, s_tab, s_desc, G,
+  stream_pe<OutT, 3>(p.g, p.dim_t, reinterpret_cast<const OutT*>(p.table), s_pts, s_off, s_desc, G,
                      tokens ? tokens + row0 * p.g.E : nullptr, reinterpret_cast<OutT*>(p.pe_out) + row0 * p.g.E);
 }
 
@@ -588,6 +667,23 @@ __global__ void __launch_bounds__(kThreads) k_discretize(const float* __restrict
       out[i] = rintf(x);
     }
   }
+}
+
+// ============================================================================================
+// 6. self-test: div_exact(a, b) against div.rn.f32 for EVERY fp32 dividend a
+// ============================================================================================
+__global__ void __launch_bounds__(kThreads) k_selftest_div(float b, unsigned long long* mismatches) {
+  const Divisor d = make_divisor(b);
+  unsigned long long bad = 0;
+  const unsigned long long total = 1ull << 32;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * kThreads) {
+    const float a = __uint_as_float((unsigned)i);
+    const unsigned got = __float_as_uint(div_exact(a, d)), ref = __float_as_uint(__fdiv_rn(a, b));
+    const bool both_nan = ((got & 0x7fffffffu) > 0x7f800000u) && ((ref & 0x7fffffffu) > 0x7f800000u);
+    if (got != ref && !both_nan) ++bad;
+  }
+  for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
 }
 
 // ============================================================================================
@@ -659,6 +755,14 @@ using namespace v3d;
 extern "C" {
 
 int v3d_version(void) { return V3D_VERSION; }
+
+int v3d_selftest_division(float divisor, uint64_t* mismatches, v3d_stream_t stream) {
+  V3D_REQUIRE(mismatches, V3D_E_ARG, "v3d_selftest_division: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  V3D_CUDA(cudaMemsetAsync(mismatches, 0, sizeof(uint64_t), s));
+  k_selftest_div<<<num_sms() * 16, kThreads, 0, s>>>(divisor, reinterpret_cast<unsigned long long*>(mismatches));
+  return check_launch("k_selftest_div");
+}
 const char* v3d_last_error(void) { return g_err; }
 
 int v3d_pool_points(int pool_mode) {

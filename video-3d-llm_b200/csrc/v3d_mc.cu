@@ -70,8 +70,8 @@ __device__ __forceinline__ int hash_find(const int4* __restrict__ tab, uint32_t 
 
 // ---- stage 1: voxelise -------------------------------------------------------------------------
 // torch: (w / voxel).round().int(); float->int of non-finite / out-of-range values is INT_MIN on x86
-__device__ __forceinline__ int voxel_id(float w, float voxel, float rcp, int div_mode) {
-  float x = (div_mode == V3D_DIV_RECIPROCAL) ? __fmul_rn(w, rcp) : __fdiv_rn(w, voxel);
+__device__ __forceinline__ int voxel_id(float w, const Divisor& voxel, float rcp, int div_mode) {
+  float x = (div_mode == V3D_DIV_RECIPROCAL) ? __fmul_rn(w, rcp) : div_exact(w, voxel);
   x = rintf(x);
   return (x >= -2147483648.0f && x < 2147483648.0f) ? (int)x : (int)0x80000000;
 }
@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(kMcThreads) k_mc_voxelize(const v3d_mc_scene* 
   const uint32_t mask = (uint32_t)sc.hash_slots - 1u;
   const int4* tab = reinterpret_cast<const int4*>(sc.hash_table);
   const float rcp = 1.0f / voxel;
+  const Divisor ds = make_divisor(depth_scale);
+  const Divisor dv = make_divisor(voxel);
   const int groups_per_row = (W + kPxPerThread - 1) / kPxPerThread;
   for (int item = blockIdx.x; item < sc.n_frames * slabs_per_frame; item += gridDim.x) {
     const int f = item / slabs_per_frame, r0 = (item - f * slabs_per_frame) * rows_per_slab;
@@ -120,8 +122,8 @@ __global__ void __launch_bounds__(kMcThreads) k_mc_voxelize(const v3d_mc_scene* 
       for (int e = 0; e < kPxPerThread; ++e) {
         if (c0 + e >= W) break;
         float x, y, z;
-        unproject_px(cam, d[e], __fsub_rn((float)(c0 + e), cam.cx), vm, depth_scale, x, y, z);
-        const int vi = voxel_id(x, voxel, rcp, div_mode), vj = voxel_id(y, voxel, rcp, div_mode), vk = voxel_id(z, voxel, rcp, div_mode);
+        unproject_px(cam, d[e], __fsub_rn((float)(c0 + e), cam.cx), vm, ds, x, y, z);
+        const int vi = voxel_id(x, dv, rcp, div_mode), vj = voxel_id(y, dv, rcp, div_mode), vk = voxel_id(z, dv, rcp, div_mode);
         if (vi == li && vj == lj && vk == lk) continue;
         li = vi;
         lj = vj;
@@ -139,8 +141,9 @@ __global__ void __launch_bounds__(kMcThreads) k_mc_voxelize(const v3d_mc_scene* 
 __global__ void __launch_bounds__(kMcThreads) k_mc_voxel_ids(const float* __restrict__ world, size_t n, float voxel, int div_mode,
                                                              int32_t* __restrict__ ids) {
   const float rcp = 1.0f / voxel;
+  const Divisor dv = make_divisor(voxel);
   for (size_t i = (size_t)blockIdx.x * kMcThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kMcThreads)
-    ids[i] = voxel_id(world[i], voxel, rcp, div_mode);
+    ids[i] = voxel_id(world[i], dv, rcp, div_mode);
 }
 
 // ---- stage 2: greedy set cover -------------------------------------------------------------------
