@@ -185,36 +185,38 @@ struct PeGeom {
   int rows, Wt;             // table rows (without the NaN row), row width in elements
 };
 
-// per-chunk descriptor: which slots a chunk of 8 channels touches and where in their rows
+// per-chunk descriptor: which slots a chunk of 8 channels touches and where in their table rows.
+// Each half is (slot << 16) | element offset inside the slot's row; slot == n_slots is the virtual
+// "zero" slot whose row (the last row of the table) is all zeros, so that the streaming loop needs no
+// branches: a chunk is always row(s0)[k0..] | row(s1)[k1..].
 struct __align__(8) ChunkDesc {
-  uint8_t s0, s1;   // slot ids, 0xFF = none
-  uint16_t k0;      // element offset of the chunk inside slot s0's table row
-  uint16_t k1;      // ... inside slot s1's row
-  uint16_t pad;
+  uint32_t a, b;
 };
 
 __device__ __forceinline__ ChunkDesc make_chunk_desc(int c8, const PeGeom& g) {
   ChunkDesc d;
   const int c = c8 * 8;
   const int s0 = c / g.nf, s1 = (c + 7) / g.nf;
-  d.s0 = (s0 < g.n_slots) ? (uint8_t)s0 : 0xFF;
-  d.k0 = (uint16_t)(c - ((s0 * g.nf) & ~7));
-  d.s1 = (s1 != s0 && s1 < g.n_slots) ? (uint8_t)s1 : 0xFF;
-  d.k1 = (uint16_t)(c - ((s1 * g.nf) & ~7));
-  d.pad = 0;
+  const uint32_t none = (uint32_t)g.n_slots << 16;
+  d.a = (s0 < g.n_slots) ? (((uint32_t)s0 << 16) | (uint32_t)(c - ((s0 * g.nf) & ~7))) : none;
+  d.b = (s1 != s0 && s1 < g.n_slots) ? (((uint32_t)s1 << 16) | (uint32_t)(c - ((s1 * g.nf) & ~7))) : none;
   return d;
+}
+
+__host__ __device__ __forceinline__ size_t pe_table_elems(const PeGeom& g) {
+  return ((size_t)g.n_slots * (g.rows + 1) + 1) * g.Wt;  // + the zero row
 }
 
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads) k_pe_table(const float* __restrict__ dim_t, PeGeom g, OutT* __restrict__ table) {
-  const size_t total = (size_t)g.n_slots * (g.rows + 1) * g.Wt;
+  const size_t total = pe_table_elems(g);
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
     const int k = (int)(i % g.Wt);
     const int r = (int)((i / g.Wt) % (g.rows + 1));
     const int s = (int)(i / ((size_t)g.Wt * (g.rows + 1)));
     const int j = ((s * g.nf) & ~7) + k - s * g.nf;
     float v = 0.0f;
-    if (j >= 0 && j < g.nf) v = (r == g.rows) ? CUDART_NAN_F : pe_value((float)r, j, dim_t);
+    if (s < g.n_slots && j >= 0 && j < g.nf) v = (r == g.rows) ? CUDART_NAN_F : pe_value((float)r, j, dim_t);
     table[i] = Elem<OutT>::from(v);
   }
 }
@@ -292,18 +294,25 @@ __device__ __forceinline__ Chunk<OutT> chunk_add(const Chunk<OutT>& a, const Chu
   return c;
 }
 
-// PE chunks that cannot be served from the table (non-integer / out-of-range coordinates): kept out
-// of line so that the sinf/cosf slow paths do not bloat the streaming loop.  One warp, one token.
+__device__ __forceinline__ uint2 lds_u2(const void* p) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(smem_u32(p)));
+  return r;
+}
+__device__ __forceinline__ int lds_s32(const void* p) {
+  int r;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(smem_u32(p)));
+  return r;
+}
+
+// A whole token row evaluated without the table wherever a slot needs it (non-integer / out-of-range
+// coordinates): kept out of line so that the sinf/cosf slow paths do not bloat the streaming loop.
+// One warp, one token.  off: n_slots+1 table row offsets (-1 = evaluate directly).
 template <typename OutT>
 __device__ __noinline__ void stream_pe_direct(const PeGeom g, const float* __restrict__ dim_t, const OutT* __restrict__ table,
-                                              const float* pts, const int* off, const ChunkDesc* s_desc, const OutT* trow,
-                                              OutT* orow) {
+                                              const float* pts, const int* off, const OutT* trow, OutT* orow) {
   const int lane = threadIdx.x & 31;
   for (int c8 = lane; c8 < g.cpt; c8 += 32) {
-    const ChunkDesc d = s_desc[c8];
-    const int o0 = (d.s0 != 0xFF) ? off[d.s0] : 0;
-    const int o1 = (d.s1 != 0xFF) ? off[d.s1] : 0;
-    if (o0 >= 0 && o1 >= 0) continue;  // already written by the table path
     Chunk<OutT> pe = chunk_zero<OutT>();
 #pragma unroll 1
     for (int e = 0; e < 8; ++e) {
@@ -319,50 +328,59 @@ __device__ __noinline__ void stream_pe_direct(const PeGeom g, const float* __res
   }
 }
 
-// PE rows of `n_tok` tokens: one warp per token, lanes stride the 16-byte chunks of its row, U
-// chunks in flight per lane (all loads of a batch are issued before the first add/store; the
-// compiler cannot do that itself because tokens may alias out).
-//   s_pts [n_tok][n_slots]  coordinates the PE is evaluated on
-//   s_off [n_tok][n_slots]  element offset of the slot's table row, or -1 = evaluate directly
+// PE rows of `n_tok` tokens.  Lanes own 16-byte chunk columns (U per pass, descriptors in registers),
+// warps stride the tokens; per token all U loads of tokens and table rows are issued before the
+// first add/store (the compiler cannot reorder them itself because tokens may alias out).
+//   s_pts  [n_tok][n_slots]    coordinates the PE is evaluated on
+//   s_off  [n_tok][n_slots+1]  element offset of each slot's table row (-1 = evaluate directly);
+//                              entry n_slots is the zero row
+//   s_flag [n_tok]             1 = some slot of the token needs direct evaluation
 template <typename OutT, int U>
 __device__ __forceinline__ void stream_pe(const PeGeom& g, const float* __restrict__ dim_t, const OutT* __restrict__ table,
-                                          const float* s_pts, const int* s_off, const ChunkDesc* s_desc, int n_tok,
-                                          const OutT* tokens, OutT* out) {
+                                          const float* s_pts, const int* s_off, const int* s_flag, const ChunkDesc* s_desc,
+                                          int n_tok, const OutT* tokens, OutT* out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kWarps = kThreads / 32;
+  const int n_off = g.n_slots + 1;
   if ((g.E & 7) == 0) {
-    for (int tok = warp; tok < n_tok; tok += kWarps) {
-      const int* off = s_off + tok * g.n_slots;
-      const OutT* trow = tokens ? tokens + (size_t)tok * g.E : nullptr;
-      OutT* orow = out + (size_t)tok * g.E;
-      bool need_direct = false;
-      for (int c0 = lane; c0 < g.cpt; c0 += 32 * U) {
+    const bool straddle = (g.nf & 7) != 0;
+    for (int c0 = lane; c0 < g.cpt; c0 += 32 * U) {
+      uint32_t sa[U], ka[U], sb[U], kb[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c8 = c0 + 32 * u;
+        const uint2 d = (c8 < g.cpt) ? lds_u2(s_desc + c8) : make_uint2(0u, 0u);
+        sa[u] = (d.x >> 16) * 4u;  // byte offset into the token's offset list
+        ka[u] = d.x & 0xffffu;
+        sb[u] = (d.y >> 16) * 4u;
+        kb[u] = d.y & 0xffffu;
+      }
+      for (int tok = warp; tok < n_tok; tok += kWarps) {
+        if (lds_s32(s_flag + tok)) continue;
+        const unsigned char* off = reinterpret_cast<const unsigned char*>(s_off + tok * n_off);
+        const OutT* trow = tokens ? tokens + (size_t)tok * g.E : nullptr;
+        OutT* orow = out + (size_t)tok * g.E;
         Chunk<OutT> tv[U], pe[U];
-        bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int c8 = c0 + 32 * u;
-          ok[u] = false;
           if (c8 < g.cpt) {
-            const ChunkDesc d = s_desc[c8];
-            const int o0 = (d.s0 != 0xFF) ? off[d.s0] : 0;
-            const int o1 = (d.s1 != 0xFF) ? off[d.s1] : 0;
-            if (o0 >= 0 && o1 >= 0) {
-              ok[u] = true;
-              if (trow) tv[u] = chunk_ld_stream(trow + c8 * 8);
-              pe[u] = (d.s0 != 0xFF) ? chunk_ldg(table + o0 + d.k0) : chunk_zero<OutT>();
-              if (d.s1 != 0xFF) chunk_or(pe[u], chunk_ldg(table + o1 + d.k1));
-            } else {
-              need_direct = true;
-            }
+            if (trow) tv[u] = chunk_ld_stream(trow + c8 * 8);
+            pe[u] = chunk_ldg(table + (uint32_t)lds_s32(off + sa[u]) + ka[u]);
+            if (straddle) chunk_or(pe[u], chunk_ldg(table + (uint32_t)lds_s32(off + sb[u]) + kb[u]));
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (ok[u]) chunk_st_stream(orow + (c0 + 32 * u) * 8, trow ? chunk_add(tv[u], pe[u]) : pe[u]);
+          const int c8 = c0 + 32 * u;
+          if (c8 < g.cpt) chunk_st_stream(orow + c8 * 8, trow ? chunk_add(tv[u], pe[u]) : pe[u]);
         }
       }
-      if (__any_sync(0xffffffffu, need_direct)) stream_pe_direct<OutT>(g, dim_t, table, s_pts + tok * g.n_slots, off, s_desc, trow, orow);
+    }
+    for (int tok = warp; tok < n_tok; tok += kWarps) {
+      if (s_flag[tok])
+        stream_pe_direct<OutT>(g, dim_t, table, s_pts + tok * g.n_slots, s_off + tok * n_off,
+                               tokens ? tokens + (size_t)tok * g.E : nullptr, out + (size_t)tok * g.E);
     }
   } else {
     // rows that are not a whole number of 16-byte chunks: element-wise (rare configuration)
@@ -371,7 +389,7 @@ __device__ __forceinline__ void stream_pe(const PeGeom& g, const float* __restri
       const int s = ch / g.nf;
       float v = 0.0f;
       if (s < g.n_slots) {
-        const int o = s_off[tok * g.n_slots + s];
+        const int o = s_off[tok * n_off + s];
         const int j = ch - s * g.nf;
         v = (o >= 0) ? Elem<OutT>::to(table[o + (s * g.nf - ((s * g.nf) & ~7)) + j]) : Elem<OutT>::to(Elem<OutT>::from(pe_value(s_pts[tok * g.n_slots + s], j, dim_t)));
       }
@@ -392,6 +410,7 @@ __device__ __forceinline__ int pe_row_offset(float x, int s, const PeGeom& g, bo
   else return -1;
   return (s * (g.rows + 1) + row) * g.Wt;
 }
+__device__ __forceinline__ int pe_zero_row_offset(const PeGeom& g) { return g.n_slots * (g.rows + 1) * g.Wt; }
 
 // stand-alone PE: llava/model/position_encoding.py:17-49 (+ llava_arch.py:515 add)
 static constexpr int kPeTokPerCta = 16;
@@ -404,17 +423,26 @@ __global__ void __launch_bounds__(kThreads) k_pe_sine3d(const float* __restrict_
   ChunkDesc* s_desc = reinterpret_cast<ChunkDesc*>(smem_raw);
   float* s_pts = reinterpret_cast<float*>(s_desc + g.cpt);
   int* s_off = reinterpret_cast<int*>(s_pts + kPeTokPerCta * g.n_slots);
+  int* s_flag = s_off + kPeTokPerCta * (g.n_slots + 1);
+  const int n_off = g.n_slots + 1;
   for (int i = threadIdx.x; i < g.cpt; i += kThreads) s_desc[i] = make_chunk_desc(i, g);
   for (size_t t0 = (size_t)blockIdx.x * kPeTokPerCta; t0 < n_tokens; t0 += (size_t)gridDim.x * kPeTokPerCta) {
     const int n_tok = (int)min((size_t)kPeTokPerCta, n_tokens - t0);
     __syncthreads();
-    for (int i = threadIdx.x; i < n_tok * g.n_slots; i += kThreads) {
-      const float x = __ldg(coords + t0 * g.n_slots + i);
-      s_pts[i] = x;
-      s_off[i] = pe_row_offset(x, i % g.n_slots, g, table != nullptr);
+    for (int i = threadIdx.x; i < n_tok; i += kThreads) {
+      int flag = 0;
+      for (int sl = 0; sl < g.n_slots; ++sl) {
+        const float x = __ldg(coords + (t0 + i) * g.n_slots + sl);
+        const int o = pe_row_offset(x, sl, g, table != nullptr);
+        s_pts[i * g.n_slots + sl] = x;
+        s_off[i * n_off + sl] = o;
+        flag |= (o < 0);
+      }
+      s_off[i * n_off + g.n_slots] = pe_zero_row_offset(g);
+      s_flag[i] = flag;
     }
     __syncthreads();
-    stream_pe<OutT, 3>(g, dim_t, table, s_pts, s_off, s_desc, n_tok, tokens ? tokens + t0 * g.E : nullptr, out + t0 * g.E);
+    stream_pe<OutT, 3>(g, dim_t, table, s_pts, s_off, s_flag, s_desc, n_tok, tokens ? tokens + t0 * g.E : nullptr, out + t0 * g.E);
   }
 }
 
@@ -447,14 +475,39 @@ struct FusedParams {
 };
 
 __host__ __device__ inline size_t fused_smem_bytes(const FusedParams& p, bool stage_depth) {
+  const size_t n_slots = (size_t)3 * p.n_points;
   size_t b = 16;                                              // mbarrier
   if (stage_depth) b += (size_t)p.patch * p.span;             // depth rows
   b += (size_t)2 * 3 * p.Sp_pad * sizeof(float);              // double-buffered xyz row
   b += (size_t)p.patch * 2 * sizeof(int);                     // source row index + (row - cy) per patch row
-  b += (size_t)p.grid * 3 * p.n_points * (sizeof(float) + sizeof(int));  // PE coordinates + table row offsets
+  b += (size_t)p.grid * (n_slots * sizeof(float) + (n_slots + 1) * sizeof(int) + sizeof(int));  // PE coords, row offsets, flags
   b = (b + 7) & ~(size_t)7;
   if (p.pe_mode != V3D_PE_NONE) b += (size_t)p.g.cpt * sizeof(ChunkDesc);
   return b;
+}
+
+// sequential sum of PW consecutive floats (ATen's avg_pool2d order); PW = 0: runtime width
+template <int PW>
+__device__ __forceinline__ float chain_add(float acc, const float* src, int P) {
+  if constexpr (PW > 0) {
+    if constexpr ((PW & 1) == 0) {
+      // even width: rows of a patch start 8-byte aligned (Sp_pad is even) -> 64-bit shared loads
+      if ((smem_u32(src) & 7) == 0) {
+#pragma unroll
+        for (int dx = 0; dx < PW; dx += 2) {
+          const float2 v = *reinterpret_cast<const float2*>(src + dx);
+          acc = __fadd_rn(__fadd_rn(acc, v.x), v.y);
+        }
+        return acc;
+      }
+    }
+#pragma unroll
+    for (int dx = 0; dx < PW; ++dx) acc = __fadd_rn(acc, src[dx]);
+  } else {
+#pragma unroll 4
+    for (int dx = 0; dx < P; ++dx) acc = __fadd_rn(acc, src[dx]);
+  }
+  return acc;
 }
 
 template <int DT, bool FROM_DEPTH, bool USE_TMA, typename OutT>
@@ -463,17 +516,19 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
   constexpr int kEsz = (DT == V3D_DEPTH_U16) ? 2 : 4;
   const int t = threadIdx.x;
   const int f = blockIdx.x / p.grid, gi = blockIdx.x - f * p.grid;
-  const int G = p.grid, P = p.patch, n_slots = 3 * p.n_points;
+  const int G = p.grid, P = p.patch, n_slots = 3 * p.n_points, n_off = n_slots + 1;
+  const int Sp_pad = p.Sp_pad;
 
   // ---- shared memory carve-up
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   unsigned char* s_depth = smem_raw + 16;
   float* s_row = reinterpret_cast<float*>(s_depth + ((FROM_DEPTH && USE_TMA) ? (size_t)P * p.span : 0));
-  int* s_srow = reinterpret_cast<int*>(s_row + 2 * 3 * p.Sp_pad);
+  int* s_srow = reinterpret_cast<int*>(s_row + 2 * 3 * Sp_pad);
   float* s_vm = reinterpret_cast<float*>(s_srow + P);
   float* s_pts = s_vm + P;
   int* s_off = reinterpret_cast<int*>(s_pts + G * n_slots);
-  ChunkDesc* s_desc = reinterpret_cast<ChunkDesc*>((reinterpret_cast<uintptr_t>(s_off + G * n_slots) + 7) & ~(uintptr_t)7);
+  int* s_flag = s_off + G * n_off;
+  ChunkDesc* s_desc = reinterpret_cast<ChunkDesc*>((reinterpret_cast<uintptr_t>(s_flag + G) + 7) & ~(uintptr_t)7);
 
   // ---- stage the P depth rows of this patch row with the TMA unit
   if constexpr (FROM_DEPTH && USE_TMA) {
@@ -513,23 +568,31 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
   // the block so that the chain warps at the bottom get less unprojection work) 511 - t
   int col[2];
   float um[2];
+  bool um_ok[2];
   size_t src_off[2];  // FROM_DEPTH: byte offset inside a staged row / element offset inside a global row
   col[0] = (t < p.Sp) ? t : -1;
   col[1] = (kThreads + (kThreads - 1 - t) < p.Sp) ? kThreads + (kThreads - 1 - t) : -1;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     um[k] = 0.f;
+    um_ok[k] = false;
     src_off[k] = 0;
     if (col[k] >= 0) {
       const int sc = FROM_DEPTH ? __ldg(p.col_map + col[k]) : col[k];
       if constexpr (FROM_DEPTH) {
         um[k] = __fsub_rn((float)sc, cam.cx);
+        um_ok[k] = fabsf(um[k]) >= 0x1p-20f && fabsf(um[k]) <= 0x1p20f;
         src_off[k] = USE_TMA ? (size_t)(sc * kEsz - p.col_lo_byte) : (size_t)sc;
       } else {
         src_off[k] = (size_t)sc * 3;
       }
     }
   }
+  // uint16 depth, rigid pose, all divisors and (u-cx),(v-cy) well inside the normal range: every
+  // dividend of the three divisions is either exactly zero (d == 0) or inside div_exact's fast range and
+  // every camera-space value is finite, so the per-pixel range tests and the w-division disappear.
+  bool frame_fast = false;
+  if constexpr (FROM_DEPTH && DT == V3D_DEPTH_U16) frame_fast = cam.rigid && ds.ok && cam.fx.ok && cam.fy.ok && ds.b > 0.f;
   __syncthreads();  // s_srow / s_vm / s_desc visible
   if constexpr (FROM_DEPTH && USE_TMA) mbar_wait(bar, 0);
 
@@ -539,25 +602,46 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
     const bool chain = t < 3 * G;
     const int a = chain ? t / G : 0, j = chain ? t - a * G : 0;
     float acc = 0.0f, mx = -CUDART_INF_F, mneg = -CUDART_INF_F;
-    const float* chain_src = s_row + a * p.Sp_pad + j * P;
+    const float* chain_src = s_row + a * Sp_pad + j * P;
     for (int dy = 0; dy < P; ++dy) {
-      float* buf = s_row + (dy & 1) * 3 * p.Sp_pad;
+      float* buf = s_row + (dy & 1) * 3 * Sp_pad;
       const float vm = s_vm[dy];
+      const bool row_fast = frame_fast && fabsf(vm) >= 0x1p-20f && fabsf(vm) <= 0x1p20f;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         if (col[k] < 0) continue;
         float x, y, z;
         if constexpr (FROM_DEPTH) {
-          float d;
-          if constexpr (USE_TMA) {
-            const unsigned char* sp = s_depth + (size_t)dy * p.span + src_off[k];
-            if constexpr (DT == V3D_DEPTH_U16) d = (float)*reinterpret_cast<const uint16_t*>(sp);
-            else if constexpr (DT == V3D_DEPTH_I32) d = (float)*reinterpret_cast<const int32_t*>(sp);
-            else d = *reinterpret_cast<const float*>(sp);
+          if (DT == V3D_DEPTH_U16 && USE_TMA && row_fast && um_ok[k]) {
+            const uint32_t raw = *reinterpret_cast<const uint16_t*>(s_depth + (size_t)dy * p.span + src_off[k]);
+            const float d = (float)raw;
+            const bool nz = raw != 0;
+            float q0 = __fmul_rn(d, ds.r);
+            float q1 = __fmaf_rn(ds.r, __fmaf_rn(-ds.b, q0, d), q0);
+            const float cz = nz ? q1 : q0;
+            const float ax = __fmul_rn(um[k], cz);
+            q0 = __fmul_rn(ax, cam.fx.r);
+            q1 = __fmaf_rn(cam.fx.r, __fmaf_rn(-cam.fx.b, q0, ax), q0);
+            const float cx_ = nz ? q1 : q0;
+            const float ay = __fmul_rn(vm, cz);
+            q0 = __fmul_rn(ay, cam.fy.r);
+            q1 = __fmaf_rn(cam.fy.r, __fmaf_rn(-cam.fy.b, q0, ay), q0);
+            const float cy_ = nz ? q1 : q0;
+            x = __fadd_rn(__fmaf_rn(cam.P[2], cz, __fmaf_rn(cam.P[1], cy_, __fmul_rn(cam.P[0], cx_))), cam.P[3]);
+            y = __fadd_rn(__fmaf_rn(cam.P[6], cz, __fmaf_rn(cam.P[5], cy_, __fmul_rn(cam.P[4], cx_))), cam.P[7]);
+            z = __fadd_rn(__fmaf_rn(cam.P[10], cz, __fmaf_rn(cam.P[9], cy_, __fmul_rn(cam.P[8], cx_))), cam.P[11]);
           } else {
-            d = load_depth<DT>(p.depth, ((size_t)f * p.H + s_srow[dy]) * p.W + src_off[k]);
+            float d;
+            if constexpr (USE_TMA) {
+              const unsigned char* sp = s_depth + (size_t)dy * p.span + src_off[k];
+              if constexpr (DT == V3D_DEPTH_U16) d = (float)*reinterpret_cast<const uint16_t*>(sp);
+              else if constexpr (DT == V3D_DEPTH_I32) d = (float)*reinterpret_cast<const int32_t*>(sp);
+              else d = *reinterpret_cast<const float*>(sp);
+            } else {
+              d = load_depth<DT>(p.depth, ((size_t)f * p.H + s_srow[dy]) * p.W + src_off[k]);
+            }
+            unproject_px(cam, d, um[k], vm, ds, x, y, z);
           }
-          unproject_px(cam, d, um[k], vm, ds, x, y, z);
           if (p.clamp.on) {
             x = apply_clamp(p.clamp, x, 0);
             y = apply_clamp(p.clamp, y, 1);
@@ -570,15 +654,16 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
           z = __ldg(src + 2);
         }
         buf[col[k]] = x;
-        buf[p.Sp_pad + col[k]] = y;
-        buf[2 * p.Sp_pad + col[k]] = z;
+        buf[Sp_pad + col[k]] = y;
+        buf[2 * Sp_pad + col[k]] = z;
       }
       __syncthreads();
       if (chain) {
-        const float* src = chain_src + (dy & 1) * 3 * p.Sp_pad;
+        const float* src = chain_src + (dy & 1) * 3 * Sp_pad;
         if (p.pool_mode == V3D_POOL_AVG) {
-#pragma unroll 9
-          for (int dx = 0; dx < P; ++dx) acc = __fadd_rn(acc, src[dx]);
+          if (P == 14) acc = chain_add<14>(acc, src, P);
+          else if (P == 27) acc = chain_add<27>(acc, src, P);
+          else acc = chain_add<0>(acc, src, P);
         } else {
           for (int dx = 0; dx < P; ++dx) {
             const float v = src[dx];
@@ -598,7 +683,7 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
         if (p.pooled_out) p.pooled_out[tok * 3 + a] = v;
         if (p.pe_coords_out) p.pe_coords_out[tok * 3 + a] = pv;
         s_pts[j * n_slots + a] = pv;
-        s_off[j * n_slots + a] = pe_row_offset(pv, a, p.g, have_table);
+        s_off[j * n_off + a] = pe_row_offset(pv, a, p.g, have_table);
       } else {  // minmax: point 0 = min, point 1 = max (llava_arch.py:237)
         const float v2[2] = {-mneg, mx};
 #pragma unroll
@@ -607,7 +692,7 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
           if (p.pooled_out) p.pooled_out[(tok * 2 + pt) * 3 + a] = v2[pt];
           if (p.pe_coords_out) p.pe_coords_out[(tok * 2 + pt) * 3 + a] = pv;
           s_pts[j * n_slots + pt * 3 + a] = pv;
-          s_off[j * n_slots + pt * 3 + a] = pe_row_offset(pv, pt * 3 + a, p.g, have_table);
+          s_off[j * n_off + pt * 3 + a] = pe_row_offset(pv, pt * 3 + a, p.g, have_table);
         }
       }
     }
@@ -638,17 +723,25 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
         if (p.pooled_out) p.pooled_out[(tok * np + k) * 3 + a] = v[a];
         if (p.pe_coords_out) p.pe_coords_out[(tok * np + k) * 3 + a] = pv;
         s_pts[j * n_slots + k * 3 + a] = pv;
-        s_off[j * n_slots + k * 3 + a] = pe_row_offset(pv, k * 3 + a, p.g, p.table != nullptr);
+        s_off[j * n_off + k * 3 + a] = pe_row_offset(pv, k * 3 + a, p.g, p.table != nullptr);
       }
     }
   }
   if (p.pe_mode == V3D_PE_NONE) return;
   __syncthreads();
+  // per-token bookkeeping for the streaming loop: zero-row offset, "needs direct evaluation" flag
+  for (int j = t; j < G; j += kThreads) {
+    int flag = 0;
+    for (int sl = 0; sl < n_slots; ++sl) flag |= (s_off[j * n_off + sl] < 0);
+    s_off[j * n_off + n_slots] = pe_zero_row_offset(p.g);
+    s_flag[j] = flag;
+  }
+  __syncthreads();
 
   // ---- stream the PE rows of this patch row (G tokens x E channels), fused token add
   const size_t row0 = ((size_t)f * G + gi) * G;
   const OutT* tokens = reinterpret_cast<const OutT*>(p.tokens_in);
-  stream_pe<OutT, 3>(p.g, p.dim_t, reinterpret_cast<const OutT*>(p.table), s_pts, s_off, s_desc, G,
+  stream_pe<OutT, 3>(p.g, p.dim_t, reinterpret_cast<const OutT*>(p.table), s_pts, s_off, s_flag, s_desc, G,
                      tokens ? tokens + row0 * p.g.E : nullptr, reinterpret_cast<OutT*>(p.pe_out) + row0 * p.g.E);
 }
 
@@ -839,7 +932,7 @@ int v3d_discretize(const float* coords, size_t n_points, const float* min_xyz_ho
 size_t v3d_pe_table_bytes(int E, int n_points, int rows, int dtype) {
   PeGeom g;
   if (make_pe_geom(E, n_points, rows, &g) != V3D_OK || rows <= 0) return 0;
-  return (size_t)g.n_slots * (rows + 1) * g.Wt * dtype_size(dtype);
+  return pe_table_elems(g) * dtype_size(dtype);
 }
 
 int v3d_pe_table_build(const float* dim_t, int E, int n_points, int rows, int dtype, void* table, v3d_stream_t stream) {
@@ -849,7 +942,7 @@ int v3d_pe_table_build(const float* dim_t, int E, int n_points, int rows, int dt
   PeGeom g;
   int rc = make_pe_geom(E, n_points, rows, &g);
   if (rc != V3D_OK) return rc;
-  const size_t total = (size_t)g.n_slots * (rows + 1) * g.Wt;
+  const size_t total = pe_table_elems(g);
   cudaStream_t s = (cudaStream_t)stream;
   return dispatch_out(dtype, [&](auto tag) {
     using T = decltype(tag);
@@ -869,7 +962,7 @@ int v3d_pe_sine3d(const float* coords, size_t n_tokens, int n_points, int E, con
   V3D_REQUIRE(!vec || ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(tokens_in) | reinterpret_cast<uintptr_t>(table)) & 15) == 0,
               V3D_E_ALIGN, "v3d_pe_sine3d: out/tokens/table must be 16-byte aligned");
   if (n_tokens == 0) return V3D_OK;
-  const size_t smem = (size_t)g.cpt * sizeof(ChunkDesc) + (size_t)kPeTokPerCta * g.n_slots * 8;
+  const size_t smem = (size_t)g.cpt * sizeof(ChunkDesc) + (size_t)kPeTokPerCta * ((size_t)g.n_slots * 8 + 8);
   const int grid = grid_for((n_tokens + kPeTokPerCta - 1) / kPeTokPerCta, 1, 16);
   cudaStream_t s = (cudaStream_t)stream;
   return dispatch_out(dtype, [&](auto tag) {
@@ -940,7 +1033,7 @@ int v3d_pool_coords(const float* coords, int V, int S, int patch, int grid, int 
   p.patch = patch;
   p.grid = grid;
   p.Sp = patch * grid;
-  p.Sp_pad = p.Sp + 1;
+  p.Sp_pad = (p.Sp + 2) & ~1;
   p.pool_mode = pool_mode;
   p.n_points = n_points;
   p.pe_mode = V3D_PE_NONE;
@@ -971,7 +1064,7 @@ int v3d_frontend_pe(const v3d_frontend_desc* d, v3d_stream_t stream) {
   p.patch = d->patch;
   p.grid = d->grid;
   p.Sp = d->patch * d->grid;
-  p.Sp_pad = p.Sp + 1;
+  p.Sp_pad = (p.Sp + 2) & ~1;
   p.pool_mode = d->pool_mode;
   p.n_points = n_points;
   if (d->has_clamp) {
