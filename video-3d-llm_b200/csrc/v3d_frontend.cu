@@ -328,9 +328,70 @@ __device__ __noinline__ void stream_pe_direct(const PeGeom g, const float* __res
   }
 }
 
-// PE rows of `n_tok` tokens.  Lanes own 16-byte chunk columns (U per pass, descriptors in registers),
-// warps stride the tokens; per token all U loads of tokens and table rows are issued before the
-// first add/store (the compiler cannot reorder them itself because tokens may alias out).
+// One pass of the streaming loop: lanes own U chunk columns c0 + 32u (descriptors in registers), warps
+// stride the tokens; per token all loads (tokens + table rows) are issued before the first add/store --
+// the compiler cannot reorder them itself because tokens may alias out.  GUARD: columns may be past
+// the end of the row (tail pass).  STRADDLE: chunks may touch two slots.  ADD: fused token add.
+template <typename OutT, int U, bool GUARD, bool STRADDLE, bool ADD>
+__device__ __forceinline__ void stream_pass(int c0, int cpt, int E, int n_tok, int n_off, const OutT* __restrict__ table,
+                                            const int* s_off, const int* s_flag, const ChunkDesc* s_desc, const OutT* tokens,
+                                            OutT* out) {
+  constexpr int kWarps = kThreads / 32;
+  const int warp = threadIdx.x >> 5;
+  uint32_t sa[U], ka[U], sb[U], kb[U];
+  bool act[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int c8 = c0 + 32 * u;
+    act[u] = !GUARD || c8 < cpt;
+    const uint2 d = act[u] ? lds_u2(s_desc + c8) : make_uint2(0u, 0u);
+    sa[u] = (d.x >> 16) * 4u;  // byte offset into the token's offset list
+    ka[u] = d.x & 0xffffu;
+    sb[u] = (d.y >> 16) * 4u;
+    kb[u] = d.y & 0xffffu;
+  }
+  const uint32_t off_base = smem_u32(s_off);
+  const uint32_t flag_base = smem_u32(s_flag);
+  for (int tok = warp; tok < n_tok; tok += kWarps) {
+    int flag;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(flag) : "r"(flag_base + 4u * tok));
+    if (flag) continue;
+    const uint32_t off = off_base + (uint32_t)(tok * n_off) * 4u;
+    const size_t row = (size_t)tok * E + (size_t)c0 * 8;
+    const OutT* tp = ADD ? tokens + row : nullptr;
+    OutT* op = out + row;
+    Chunk<OutT> tv[U], pe[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (act[u]) {
+        if (ADD) tv[u] = chunk_ld_stream(tp + u * 256);
+        int o;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + sa[u]));
+        pe[u] = chunk_ldg(table + (uint32_t)o + ka[u]);
+        if (STRADDLE) {
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + sb[u]));
+          chunk_or(pe[u], chunk_ldg(table + (uint32_t)o + kb[u]));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (act[u]) chunk_st_stream(op + u * 256, ADD ? chunk_add(tv[u], pe[u]) : pe[u]);
+    }
+  }
+}
+
+template <typename OutT, int U, bool STRADDLE, bool ADD>
+__device__ __forceinline__ void stream_rows(int cpt, int E, int n_tok, int n_off, const OutT* __restrict__ table, const int* s_off,
+                                            const int* s_flag, const ChunkDesc* s_desc, const OutT* tokens, OutT* out) {
+  const int lane = threadIdx.x & 31;
+  const int full = cpt / (32 * U) * (32 * U);
+  for (int c0 = 0; c0 < full; c0 += 32 * U)
+    stream_pass<OutT, U, false, STRADDLE, ADD>(c0 + lane, cpt, E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
+  if (full < cpt) stream_pass<OutT, U, true, STRADDLE, ADD>(full + lane, cpt, E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
+}
+
+// PE rows of `n_tok` tokens.
 //   s_pts  [n_tok][n_slots]    coordinates the PE is evaluated on
 //   s_off  [n_tok][n_slots+1]  element offset of each slot's table row (-1 = evaluate directly);
 //                              entry n_slots is the zero row
@@ -339,42 +400,18 @@ template <typename OutT, int U>
 __device__ __forceinline__ void stream_pe(const PeGeom& g, const float* __restrict__ dim_t, const OutT* __restrict__ table,
                                           const float* s_pts, const int* s_off, const int* s_flag, const ChunkDesc* s_desc,
                                           int n_tok, const OutT* tokens, OutT* out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5;
   constexpr int kWarps = kThreads / 32;
   const int n_off = g.n_slots + 1;
   if ((g.E & 7) == 0) {
-    const bool straddle = (g.nf & 7) != 0;
-    for (int c0 = lane; c0 < g.cpt; c0 += 32 * U) {
-      uint32_t sa[U], ka[U], sb[U], kb[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int c8 = c0 + 32 * u;
-        const uint2 d = (c8 < g.cpt) ? lds_u2(s_desc + c8) : make_uint2(0u, 0u);
-        sa[u] = (d.x >> 16) * 4u;  // byte offset into the token's offset list
-        ka[u] = d.x & 0xffffu;
-        sb[u] = (d.y >> 16) * 4u;
-        kb[u] = d.y & 0xffffu;
-      }
-      for (int tok = warp; tok < n_tok; tok += kWarps) {
-        if (lds_s32(s_flag + tok)) continue;
-        const unsigned char* off = reinterpret_cast<const unsigned char*>(s_off + tok * n_off);
-        const OutT* trow = tokens ? tokens + (size_t)tok * g.E : nullptr;
-        OutT* orow = out + (size_t)tok * g.E;
-        Chunk<OutT> tv[U], pe[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int c8 = c0 + 32 * u;
-          if (c8 < g.cpt) {
-            if (trow) tv[u] = chunk_ld_stream(trow + c8 * 8);
-            pe[u] = chunk_ldg(table + (uint32_t)lds_s32(off + sa[u]) + ka[u]);
-            if (straddle) chunk_or(pe[u], chunk_ldg(table + (uint32_t)lds_s32(off + sb[u]) + kb[u]));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int c8 = c0 + 32 * u;
-          if (c8 < g.cpt) chunk_st_stream(orow + c8 * 8, trow ? chunk_add(tv[u], pe[u]) : pe[u]);
-        }
+    if (table != nullptr) {
+      const bool straddle = (g.nf & 7) != 0;
+      if (tokens) {
+        if (straddle) stream_rows<OutT, U, true, true>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
+        else stream_rows<OutT, U, false, true>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
+      } else {
+        if (straddle) stream_rows<OutT, U, true, false>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
+        else stream_rows<OutT, U, false, false>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
       }
     }
     for (int tok = warp; tok < n_tok; tok += kWarps) {
@@ -442,7 +479,7 @@ __global__ void __launch_bounds__(kThreads) k_pe_sine3d(const float* __restrict_
       s_flag[i] = flag;
     }
     __syncthreads();
-    stream_pe<OutT, 3>(g, dim_t, table, s_pts, s_off, s_flag, s_desc, n_tok, tokens ? tokens + t0 * g.E : nullptr, out + t0 * g.E);
+    stream_pe<OutT, 2>(g, dim_t, table, s_pts, s_off, s_flag, s_desc, n_tok, tokens ? tokens + t0 * g.E : nullptr, out + t0 * g.E);
   }
 }
 
@@ -474,12 +511,20 @@ struct FusedParams {
   int col_lo_byte, span;
 };
 
+// xyz of one resampled row live in three planes of kPlane floats (x | y | z), double buffered.  The
+// plane stride is a compile-time constant so that the three stores of a pixel and the chain loads use
+// immediate offsets; 520 % 32 == 8 keeps the planes on different banks.
+#ifndef V3D_FUSED_MIN_BLOCKS
+#define V3D_FUSED_MIN_BLOCKS 4
+#endif
+static constexpr int kPlane = 520;  // >= 2 * kThreads columns, even
+
 __host__ __device__ inline size_t fused_smem_bytes(const FusedParams& p, bool stage_depth) {
   const size_t n_slots = (size_t)3 * p.n_points;
   size_t b = 16;                                              // mbarrier
   if (stage_depth) b += (size_t)p.patch * p.span;             // depth rows
-  b += (size_t)2 * 3 * p.Sp_pad * sizeof(float);              // double-buffered xyz row
-  b += (size_t)p.patch * 2 * sizeof(int);                     // source row index + (row - cy) per patch row
+  b += (size_t)2 * 3 * kPlane * sizeof(float);                // double-buffered xyz row
+  b += (size_t)p.patch * 2 * sizeof(float2);                  // {row - cy, fast flag} and source row per patch row
   b += (size_t)p.grid * (n_slots * sizeof(float) + (n_slots + 1) * sizeof(int) + sizeof(int));  // PE coords, row offsets, flags
   b = (b + 7) & ~(size_t)7;
   if (p.pe_mode != V3D_PE_NONE) b += (size_t)p.g.cpt * sizeof(ChunkDesc);
@@ -491,7 +536,7 @@ template <int PW>
 __device__ __forceinline__ float chain_add(float acc, const float* src, int P) {
   if constexpr (PW > 0) {
     if constexpr ((PW & 1) == 0) {
-      // even width: rows of a patch start 8-byte aligned (Sp_pad is even) -> 64-bit shared loads
+      // even width: rows of a patch start 8-byte aligned (kPlane is even) -> 64-bit shared loads
       if ((smem_u32(src) & 7) == 0) {
 #pragma unroll
         for (int dx = 0; dx < PW; dx += 2) {
@@ -510,22 +555,32 @@ __device__ __forceinline__ float chain_add(float acc, const float* src, int P) {
   return acc;
 }
 
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts_xyz(uint32_t addr, float x, float y, float z) {
+  asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+%4], %2;\n\tst.shared.f32 [%0+%5], %3;" ::"r"(addr), "f"(x), "f"(y),
+               "f"(z), "n"(kPlane * 4), "n"(2 * kPlane * 4)
+               : "memory");
+}
+
 template <int DT, bool FROM_DEPTH, bool USE_TMA, typename OutT>
-__global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
+__global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const FusedParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kEsz = (DT == V3D_DEPTH_U16) ? 2 : 4;
   const int t = threadIdx.x;
   const int f = blockIdx.x / p.grid, gi = blockIdx.x - f * p.grid;
   const int G = p.grid, P = p.patch, n_slots = 3 * p.n_points, n_off = n_slots + 1;
-  const int Sp_pad = p.Sp_pad;
 
   // ---- shared memory carve-up
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   unsigned char* s_depth = smem_raw + 16;
   float* s_row = reinterpret_cast<float*>(s_depth + ((FROM_DEPTH && USE_TMA) ? (size_t)P * p.span : 0));
-  int* s_srow = reinterpret_cast<int*>(s_row + 2 * 3 * Sp_pad);
-  float* s_vm = reinterpret_cast<float*>(s_srow + P);
-  float* s_pts = s_vm + P;
+  float2* s_vm = reinterpret_cast<float2*>(s_row + 2 * 3 * kPlane);  // {row - cy, 1.0 if the fast path may be used}
+  int* s_srow = reinterpret_cast<int*>(s_vm + P);
+  float* s_pts = reinterpret_cast<float*>(s_srow + 2 * P);
   int* s_off = reinterpret_cast<int*>(s_pts + G * n_slots);
   int* s_flag = s_off + G * n_off;
   ChunkDesc* s_desc = reinterpret_cast<ChunkDesc*>((reinterpret_cast<uintptr_t>(s_flag + G) + 7) & ~(uintptr_t)7);
@@ -554,45 +609,49 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
 
   Camera cam;
   Divisor ds;
+  // uint16 depth, rigid pose, all divisors and (u-cx),(v-cy) well inside the normal range: every
+  // dividend of the three divisions is either exactly zero (d == 0) or inside div_exact's fast range and
+  // every camera-space value is finite, so the per-pixel range tests and the w-division disappear.
+  bool frame_fast = false;
   if constexpr (FROM_DEPTH) {
     cam = load_camera(p.poses, p.intr, f);
     ds = make_divisor(p.depth_scale);
+    if constexpr (DT == V3D_DEPTH_U16 && USE_TMA) frame_fast = cam.rigid && ds.ok && cam.fx.ok && cam.fy.ok && ds.b > 0.f;
   }
   for (int dy = t; dy < P; dy += kThreads) {
     const int sr = FROM_DEPTH ? __ldg(p.row_map + gi * P + dy) : gi * P + dy;
+    const float vm = FROM_DEPTH ? __fsub_rn((float)sr, cam.cy) : 0.0f;
     s_srow[dy] = sr;
-    s_vm[dy] = FROM_DEPTH ? __fsub_rn((float)sr, cam.cy) : 0.0f;
+    s_vm[dy] = make_float2(vm, (frame_fast && fabsf(vm) >= 0x1p-20f && fabsf(vm) <= 0x1p20f) ? 1.0f : 0.0f);
   }
 
   // per-thread column constants: thread t owns dst column t and (second round, taken from the top of
   // the block so that the chain warps at the bottom get less unprojection work) 511 - t
   int col[2];
   float um[2];
-  bool um_ok[2];
-  size_t src_off[2];  // FROM_DEPTH: byte offset inside a staged row / element offset inside a global row
+  size_t src_off[2];     // FROM_DEPTH: byte offset inside a staged row / element offset inside a global row
+  uint32_t w_addr[2];    // shared address of this column's x slot in buffer 0
+  int fast_bits = 0;     // bit k: column k may use the branch-free uint16 path
   col[0] = (t < p.Sp) ? t : -1;
   col[1] = (kThreads + (kThreads - 1 - t) < p.Sp) ? kThreads + (kThreads - 1 - t) : -1;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     um[k] = 0.f;
-    um_ok[k] = false;
     src_off[k] = 0;
+    w_addr[k] = smem_u32(s_row + (col[k] >= 0 ? col[k] : 0));
     if (col[k] >= 0) {
       const int sc = FROM_DEPTH ? __ldg(p.col_map + col[k]) : col[k];
       if constexpr (FROM_DEPTH) {
         um[k] = __fsub_rn((float)sc, cam.cx);
-        um_ok[k] = fabsf(um[k]) >= 0x1p-20f && fabsf(um[k]) <= 0x1p20f;
+        if (frame_fast && fabsf(um[k]) >= 0x1p-20f && fabsf(um[k]) <= 0x1p20f) fast_bits |= 1 << k;
         src_off[k] = USE_TMA ? (size_t)(sc * kEsz - p.col_lo_byte) : (size_t)sc;
       } else {
         src_off[k] = (size_t)sc * 3;
       }
     }
   }
-  // uint16 depth, rigid pose, all divisors and (u-cx),(v-cy) well inside the normal range: every
-  // dividend of the three divisions is either exactly zero (d == 0) or inside div_exact's fast range and
-  // every camera-space value is finite, so the per-pixel range tests and the w-division disappear.
-  bool frame_fast = false;
-  if constexpr (FROM_DEPTH && DT == V3D_DEPTH_U16) frame_fast = cam.rigid && ds.ok && cam.fx.ok && cam.fy.ok && ds.b > 0.f;
+  asm volatile("" : "+r"(fast_bits));  // keep the flag in a register instead of re-deriving it per row
+  const uint32_t d_base = smem_u32(s_depth);
   __syncthreads();  // s_srow / s_vm / s_desc visible
   if constexpr (FROM_DEPTH && USE_TMA) mbar_wait(bar, 0);
 
@@ -602,38 +661,45 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
     const bool chain = t < 3 * G;
     const int a = chain ? t / G : 0, j = chain ? t - a * G : 0;
     float acc = 0.0f, mx = -CUDART_INF_F, mneg = -CUDART_INF_F;
-    const float* chain_src = s_row + a * Sp_pad + j * P;
-    for (int dy = 0; dy < P; ++dy) {
-      float* buf = s_row + (dy & 1) * 3 * Sp_pad;
-      const float vm = s_vm[dy];
-      const bool row_fast = frame_fast && fabsf(vm) >= 0x1p-20f && fabsf(vm) <= 0x1p20f;
+    const float* chain_src = s_row + a * kPlane + j * P;
+    uint32_t row_off = 0;  // byte offset of staged depth row dy
+    for (int dy = 0; dy < P; ++dy, row_off += (uint32_t)p.span) {
+      const uint32_t bsel = (dy & 1) ? (uint32_t)(3 * kPlane * 4) : 0u;
+      const float2 vmf = s_vm[dy];
+      const float vm = vmf.x;
+      const int row_bits = (vmf.y != 0.0f) ? fast_bits : 0;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         if (col[k] < 0) continue;
         float x, y, z;
         if constexpr (FROM_DEPTH) {
-          if (DT == V3D_DEPTH_U16 && USE_TMA && row_fast && um_ok[k]) {
-            const uint32_t raw = *reinterpret_cast<const uint16_t*>(s_depth + (size_t)dy * p.span + src_off[k]);
-            const float d = (float)raw;
-            const bool nz = raw != 0;
-            float q0 = __fmul_rn(d, ds.r);
-            float q1 = __fmaf_rn(ds.r, __fmaf_rn(-ds.b, q0, d), q0);
-            const float cz = nz ? q1 : q0;
-            const float ax = __fmul_rn(um[k], cz);
-            q0 = __fmul_rn(ax, cam.fx.r);
-            q1 = __fmaf_rn(cam.fx.r, __fmaf_rn(-cam.fx.b, q0, ax), q0);
-            const float cx_ = nz ? q1 : q0;
-            const float ay = __fmul_rn(vm, cz);
-            q0 = __fmul_rn(ay, cam.fy.r);
-            q1 = __fmaf_rn(cam.fy.r, __fmaf_rn(-cam.fy.b, q0, ay), q0);
-            const float cy_ = nz ? q1 : q0;
-            x = __fadd_rn(__fmaf_rn(cam.P[2], cz, __fmaf_rn(cam.P[1], cy_, __fmul_rn(cam.P[0], cx_))), cam.P[3]);
-            y = __fadd_rn(__fmaf_rn(cam.P[6], cz, __fmaf_rn(cam.P[5], cy_, __fmul_rn(cam.P[4], cx_))), cam.P[7]);
-            z = __fadd_rn(__fmaf_rn(cam.P[10], cz, __fmaf_rn(cam.P[9], cy_, __fmul_rn(cam.P[8], cx_))), cam.P[11]);
-          } else {
+          bool done = false;
+          if constexpr (DT == V3D_DEPTH_U16 && USE_TMA) {
+            if (row_bits & (1 << k)) {
+              const uint32_t raw = lds_u16(d_base + row_off + (uint32_t)src_off[k]);
+              const float d = (float)raw;
+              const bool nz = raw != 0;
+              float q0 = __fmul_rn(d, ds.r);
+              float q1 = __fmaf_rn(ds.r, __fmaf_rn(-ds.b, q0, d), q0);
+              const float cz = nz ? q1 : q0;
+              const float ax = __fmul_rn(um[k], cz);
+              q0 = __fmul_rn(ax, cam.fx.r);
+              q1 = __fmaf_rn(cam.fx.r, __fmaf_rn(-cam.fx.b, q0, ax), q0);
+              const float cx_ = nz ? q1 : q0;
+              const float ay = __fmul_rn(vm, cz);
+              q0 = __fmul_rn(ay, cam.fy.r);
+              q1 = __fmaf_rn(cam.fy.r, __fmaf_rn(-cam.fy.b, q0, ay), q0);
+              const float cy_ = nz ? q1 : q0;
+              x = __fadd_rn(__fmaf_rn(cam.P[2], cz, __fmaf_rn(cam.P[1], cy_, __fmul_rn(cam.P[0], cx_))), cam.P[3]);
+              y = __fadd_rn(__fmaf_rn(cam.P[6], cz, __fmaf_rn(cam.P[5], cy_, __fmul_rn(cam.P[4], cx_))), cam.P[7]);
+              z = __fadd_rn(__fmaf_rn(cam.P[10], cz, __fmaf_rn(cam.P[9], cy_, __fmul_rn(cam.P[8], cx_))), cam.P[11]);
+              done = true;
+            }
+          }
+          if (!done) {
             float d;
             if constexpr (USE_TMA) {
-              const unsigned char* sp = s_depth + (size_t)dy * p.span + src_off[k];
+              const unsigned char* sp = s_depth + row_off + src_off[k];
               if constexpr (DT == V3D_DEPTH_U16) d = (float)*reinterpret_cast<const uint16_t*>(sp);
               else if constexpr (DT == V3D_DEPTH_I32) d = (float)*reinterpret_cast<const int32_t*>(sp);
               else d = *reinterpret_cast<const float*>(sp);
@@ -653,13 +719,11 @@ __global__ void __launch_bounds__(kThreads) k_fused(const FusedParams p) {
           y = __ldg(src + 1);
           z = __ldg(src + 2);
         }
-        buf[col[k]] = x;
-        buf[Sp_pad + col[k]] = y;
-        buf[2 * Sp_pad + col[k]] = z;
+        sts_xyz(w_addr[k] + bsel, x, y, z);
       }
       __syncthreads();
       if (chain) {
-        const float* src = chain_src + (dy & 1) * 3 * Sp_pad;
+        const float* src = chain_src + ((dy & 1) ? 3 * kPlane : 0);
         if (p.pool_mode == V3D_POOL_AVG) {
           if (P == 14) acc = chain_add<14>(acc, src, P);
           else if (P == 27) acc = chain_add<27>(acc, src, P);
@@ -1008,7 +1072,7 @@ static int check_pool(int pool_mode, int patch, int grid, int* n_points) {
   *n_points = v3d_pool_points(pool_mode);
   V3D_REQUIRE(*n_points > 0, V3D_E_ARG, "unknown pool mode %d", pool_mode);
   V3D_REQUIRE(patch > 0 && grid > 0, V3D_E_ARG, "bad patch=%d grid=%d", patch, grid);
-  V3D_REQUIRE(patch * grid <= 2 * kThreads, V3D_E_UNSUPPORTED, "patch*grid=%d exceeds %d columns", patch * grid, 2 * kThreads);
+  V3D_REQUIRE(patch * grid <= 2 * kThreads && patch * grid <= kPlane, V3D_E_UNSUPPORTED, "patch*grid=%d exceeds %d columns", patch * grid, 2 * kThreads);
   V3D_REQUIRE(3 * grid <= kThreads, V3D_E_UNSUPPORTED, "grid=%d too large", grid);
   if (pool_mode >= V3D_POOL_SAMPLE9)
     V3D_REQUIRE(patch == 27 && grid == 14, V3D_E_UNSUPPORTED, "sample pooling is defined for patch 27 / grid 14 only (llava_arch.py:245)");
