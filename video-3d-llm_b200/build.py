@@ -46,7 +46,12 @@ def up_to_date() -> bool:
     return os.path.getmtime(LIB) >= max(os.path.getmtime(p) for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """defines/out: build an experimental variant (e.g. -DV3D_FUSED_MIN_BLOCKS=4) next to the default library."""
+    global LIB
+    if out:
+        LIB = os.path.join(OUT_DIR, out)
+        force = True
     if not force and up_to_date():
         return LIB
     nvcc = find_nvcc()
@@ -54,8 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in sources():
-        obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + (("." + out) if out else "") + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -77,4 +82,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libv3d.so")
+LIB_PATH = os.environ.get("V3D_LIB_PATH") or os.path.join(_HERE, "lib", "libv3d.so")  # override: experimental builds
 
 # enums of include/v3d.h
 V3D_OK, V3D_E_ARG, V3D_E_ALIGN, V3D_E_UNSUPPORTED, V3D_E_CUDA = 0, -1, -2, -3, -4

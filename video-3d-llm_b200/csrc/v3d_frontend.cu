@@ -328,67 +328,89 @@ __device__ __noinline__ void stream_pe_direct(const PeGeom g, const float* __res
   }
 }
 
-// One pass of the streaming loop: lanes own U chunk columns c0 + 32u (descriptors in registers), warps
-// stride the tokens; per token all loads (tokens + table rows) are issued before the first add/store --
-// the compiler cannot reorder them itself because tokens may alias out.  GUARD: columns may be past
-// the end of the row (tail pass).  STRADDLE: chunks may touch two slots.  ADD: fused token add.
+// One pass of the streaming loop.  Work is laid out over PAIRS of tokens: the 2*cpt chunks of two
+// consecutive token rows form one linear range L (cpt = 144 -> 288 = 9 x 32: no ragged tail), lane l
+// owns L = l0 + 32u for u < U (descriptor and token parity in registers), warps stride the pairs.  Per
+// pair all loads (tokens + table rows) are issued before the first add/store -- the compiler cannot
+// reorder them itself because tokens may alias out.  GUARD: L may be past 2*cpt.  STRADDLE: chunks may
+// touch two slots.  ADD: fused token add.
 template <typename OutT, int U, bool GUARD, bool STRADDLE, bool ADD>
-__device__ __forceinline__ void stream_pass(int c0, int cpt, int E, int n_tok, int n_off, const OutT* __restrict__ table,
+__device__ __forceinline__ void stream_pass(int l0, int cpt, int E, int n_tok, int n_off, const OutT* __restrict__ table,
                                             const int* s_off, const int* s_flag, const ChunkDesc* s_desc, const OutT* tokens,
                                             OutT* out) {
   constexpr int kWarps = kThreads / 32;
   const int warp = threadIdx.x >> 5;
   uint32_t sa[U], ka[U], sb[U], kb[U];
+  uint32_t rel[U];   // element offset of the chunk relative to the pair's first row
+  uint32_t osel[U];  // byte offset of the token's offset list relative to the pair's first list
+  int tsel[U];
   bool act[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const int c8 = c0 + 32 * u;
+    const int L = l0 + 32 * u;
+    tsel[u] = L >= cpt;
+    const int c8 = L - (tsel[u] ? cpt : 0);
     act[u] = !GUARD || c8 < cpt;
     const uint2 d = act[u] ? lds_u2(s_desc + c8) : make_uint2(0u, 0u);
     sa[u] = (d.x >> 16) * 4u;  // byte offset into the token's offset list
     ka[u] = d.x & 0xffffu;
     sb[u] = (d.y >> 16) * 4u;
     kb[u] = d.y & 0xffffu;
+    rel[u] = (uint32_t)(tsel[u] * E + c8 * 8);
+    osel[u] = (uint32_t)(tsel[u] * n_off) * 4u;
   }
   const uint32_t off_base = smem_u32(s_off);
   const uint32_t flag_base = smem_u32(s_flag);
-  for (int tok = warp; tok < n_tok; tok += kWarps) {
-    int flag;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(flag) : "r"(flag_base + 4u * tok));
-    if (flag) continue;
-    const uint32_t off = off_base + (uint32_t)(tok * n_off) * 4u;
-    const size_t row = (size_t)tok * E + (size_t)c0 * 8;
+  for (int t0 = 2 * warp; t0 < n_tok; t0 += 2 * kWarps) {
+    const uint32_t off = off_base + (uint32_t)(t0 * n_off) * 4u;
+    const size_t row = (size_t)t0 * E;
     const OutT* tp = ADD ? tokens + row : nullptr;
     OutT* op = out + row;
     Chunk<OutT> tv[U], pe[U];
+    bool go[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (act[u]) {
-        if (ADD) tv[u] = chunk_ld_stream(tp + u * 256);
+      go[u] = act[u] && (t0 + tsel[u] < n_tok);
+      if (go[u]) {
+        int flag;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(flag) : "r"(flag_base + 4u * (uint32_t)(t0 + tsel[u])));
+        go[u] = flag == 0;
+      }
+      if (go[u]) {
+        if (ADD) tv[u] = chunk_ld_stream(tp + rel[u]);
         int o;
-        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + sa[u]));
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + osel[u] + sa[u]));
         pe[u] = chunk_ldg(table + (uint32_t)o + ka[u]);
         if (STRADDLE) {
-          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + sb[u]));
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + osel[u] + sb[u]));
           chunk_or(pe[u], chunk_ldg(table + (uint32_t)o + kb[u]));
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (act[u]) chunk_st_stream(op + u * 256, ADD ? chunk_add(tv[u], pe[u]) : pe[u]);
+      if (go[u]) chunk_st_stream(op + rel[u], ADD ? chunk_add(tv[u], pe[u]) : pe[u]);
     }
   }
 }
 
 template <typename OutT, int U, bool STRADDLE, bool ADD>
+__device__ __forceinline__ void stream_rows_u(int cpt, int E, int n_tok, int n_off, const OutT* __restrict__ table, const int* s_off,
+                                              const int* s_flag, const ChunkDesc* s_desc, const OutT* tokens, OutT* out) {
+  const int lane = threadIdx.x & 31;
+  const int total = 2 * cpt;
+  const int full = total / (32 * U) * (32 * U);
+  for (int l0 = 0; l0 < full; l0 += 32 * U)
+    stream_pass<OutT, U, false, STRADDLE, ADD>(l0 + lane, cpt, E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
+  if (full < total) stream_pass<OutT, U, true, STRADDLE, ADD>(full + lane, cpt, E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
+}
+
+template <typename OutT, bool STRADDLE, bool ADD>
 __device__ __forceinline__ void stream_rows(int cpt, int E, int n_tok, int n_off, const OutT* __restrict__ table, const int* s_off,
                                             const int* s_flag, const ChunkDesc* s_desc, const OutT* tokens, OutT* out) {
-  const int lane = threadIdx.x & 31;
-  const int full = cpt / (32 * U) * (32 * U);
-  for (int c0 = 0; c0 < full; c0 += 32 * U)
-    stream_pass<OutT, U, false, STRADDLE, ADD>(c0 + lane, cpt, E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
-  if (full < cpt) stream_pass<OutT, U, true, STRADDLE, ADD>(full + lane, cpt, E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
+  // pick the batch size that leaves no ragged pass: 2*cpt/32 steps (9 for E=1152, 28 for E=3584)
+  if ((2 * cpt) % 96 == 0) stream_rows_u<OutT, 3, STRADDLE, ADD>(cpt, E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
+  else stream_rows_u<OutT, 2, STRADDLE, ADD>(cpt, E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
 }
 
 // PE rows of `n_tok` tokens.
@@ -396,7 +418,7 @@ __device__ __forceinline__ void stream_rows(int cpt, int E, int n_tok, int n_off
 //   s_off  [n_tok][n_slots+1]  element offset of each slot's table row (-1 = evaluate directly);
 //                              entry n_slots is the zero row
 //   s_flag [n_tok]             1 = some slot of the token needs direct evaluation
-template <typename OutT, int U>
+template <typename OutT>
 __device__ __forceinline__ void stream_pe(const PeGeom& g, const float* __restrict__ dim_t, const OutT* __restrict__ table,
                                           const float* s_pts, const int* s_off, const int* s_flag, const ChunkDesc* s_desc,
                                           int n_tok, const OutT* tokens, OutT* out) {
@@ -407,11 +429,11 @@ __device__ __forceinline__ void stream_pe(const PeGeom& g, const float* __restri
     if (table != nullptr) {
       const bool straddle = (g.nf & 7) != 0;
       if (tokens) {
-        if (straddle) stream_rows<OutT, U, true, true>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
-        else stream_rows<OutT, U, false, true>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
+        if (straddle) stream_rows<OutT, true, true>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
+        else stream_rows<OutT, false, true>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
       } else {
-        if (straddle) stream_rows<OutT, U, true, false>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
-        else stream_rows<OutT, U, false, false>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
+        if (straddle) stream_rows<OutT, true, false>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
+        else stream_rows<OutT, false, false>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
       }
     }
     for (int tok = warp; tok < n_tok; tok += kWarps) {
@@ -479,7 +501,7 @@ __global__ void __launch_bounds__(kThreads) k_pe_sine3d(const float* __restrict_
       s_flag[i] = flag;
     }
     __syncthreads();
-    stream_pe<OutT, 2>(g, dim_t, table, s_pts, s_off, s_flag, s_desc, n_tok, tokens ? tokens + t0 * g.E : nullptr, out + t0 * g.E);
+    stream_pe<OutT>(g, dim_t, table, s_pts, s_off, s_flag, s_desc, n_tok, tokens ? tokens + t0 * g.E : nullptr, out + t0 * g.E);
   }
 }
 
@@ -566,6 +588,72 @@ __device__ __forceinline__ void sts_xyz(uint32_t addr, float x, float y, float z
                : "memory");
 }
 
+// State of one chain thread (axis a, patch j): running sum / max / max of negatives.
+struct ChainAcc {
+  float acc, mx, mneg;
+};
+
+__device__ __forceinline__ void chain_row(ChainAcc& c, const float* src, int P, int pool_mode) {
+  if (pool_mode == V3D_POOL_AVG) {
+    if (P == 14) c.acc = chain_add<14>(c.acc, src, P);
+    else if (P == 27) c.acc = chain_add<27>(c.acc, src, P);
+    else c.acc = chain_add<0>(c.acc, src, P);
+  } else {
+    for (int dx = 0; dx < P; ++dx) {
+      const float v = src[dx];
+      if (v > c.mx || v != v) c.mx = v;
+      const float nv = -v;
+      if (nv > c.mneg || nv != nv) c.mneg = nv;
+    }
+  }
+}
+
+// The row loop when EVERY pixel of the CTA qualifies for the branch-free path: uint16 depth staged by
+// TMA, rigid pose, depth scale / fx / fy and all (u-cx), (v-cy) well inside the normal range.  Each
+// dividend of the three divisions is then either exactly zero (d == 0, where a*r is the correctly
+// signed zero) or inside div_exact's fast range, and every camera-space value is finite, so no range
+// test, no fallback and no w-division remain in the loop.
+__device__ __forceinline__ void pool_rows_fast(const Camera& cam, const Divisor& ds, int P, uint32_t span, int n_px,
+                                               const float um[2], const uint32_t d_addr[2], const uint32_t w_addr[2],
+                                               const float2* s_vm, bool chain, const float* chain_src, int pool_mode,
+                                               const Clamp& clamp, ChainAcc& c) {
+  uint32_t row_off = 0;
+  for (int dy = 0; dy < P; ++dy, row_off += span) {
+    const uint32_t bsel = (dy & 1) ? (uint32_t)(3 * kPlane * 4) : 0u;
+    const float vm = s_vm[dy].x;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k < n_px) {
+        const uint32_t raw = lds_u16(d_addr[k] + row_off);
+        const float d = (float)raw;
+        const bool nz = raw != 0;
+        float q0 = __fmul_rn(d, ds.r);
+        float q1 = __fmaf_rn(ds.r, __fmaf_rn(-ds.b, q0, d), q0);
+        const float cz = nz ? q1 : q0;
+        const float ax = __fmul_rn(um[k], cz);
+        q0 = __fmul_rn(ax, cam.fx.r);
+        q1 = __fmaf_rn(cam.fx.r, __fmaf_rn(-cam.fx.b, q0, ax), q0);
+        const float cx_ = nz ? q1 : q0;
+        const float ay = __fmul_rn(vm, cz);
+        q0 = __fmul_rn(ay, cam.fy.r);
+        q1 = __fmaf_rn(cam.fy.r, __fmaf_rn(-cam.fy.b, q0, ay), q0);
+        const float cy_ = nz ? q1 : q0;
+        float x = __fadd_rn(__fmaf_rn(cam.P[2], cz, __fmaf_rn(cam.P[1], cy_, __fmul_rn(cam.P[0], cx_))), cam.P[3]);
+        float y = __fadd_rn(__fmaf_rn(cam.P[6], cz, __fmaf_rn(cam.P[5], cy_, __fmul_rn(cam.P[4], cx_))), cam.P[7]);
+        float z = __fadd_rn(__fmaf_rn(cam.P[10], cz, __fmaf_rn(cam.P[9], cy_, __fmul_rn(cam.P[8], cx_))), cam.P[11]);
+        if (clamp.on) {
+          x = apply_clamp(clamp, x, 0);
+          y = apply_clamp(clamp, y, 1);
+          z = apply_clamp(clamp, z, 2);
+        }
+        sts_xyz(w_addr[k] + bsel, x, y, z);
+      }
+    }
+    __syncthreads();
+    if (chain) chain_row(c, chain_src + ((dy & 1) ? 3 * kPlane : 0), P, pool_mode);
+  }
+}
+
 template <int DT, bool FROM_DEPTH, bool USE_TMA, typename OutT>
 __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const FusedParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -578,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   unsigned char* s_depth = smem_raw + 16;
   float* s_row = reinterpret_cast<float*>(s_depth + ((FROM_DEPTH && USE_TMA) ? (size_t)P * p.span : 0));
-  float2* s_vm = reinterpret_cast<float2*>(s_row + 2 * 3 * kPlane);  // {row - cy, 1.0 if the fast path may be used}
+  float2* s_vm = reinterpret_cast<float2*>(s_row + 2 * 3 * kPlane);  // {row - cy, unused}
   int* s_srow = reinterpret_cast<int*>(s_vm + P);
   float* s_pts = reinterpret_cast<float*>(s_srow + 2 * P);
   int* s_off = reinterpret_cast<int*>(s_pts + G * n_slots);
@@ -609,20 +697,18 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
 
   Camera cam;
   Divisor ds;
-  // uint16 depth, rigid pose, all divisors and (u-cx),(v-cy) well inside the normal range: every
-  // dividend of the three divisions is either exactly zero (d == 0) or inside div_exact's fast range and
-  // every camera-space value is finite, so the per-pixel range tests and the w-division disappear.
-  bool frame_fast = false;
+  bool fast_ok = false;  // this thread's pixels qualify for pool_rows_fast
   if constexpr (FROM_DEPTH) {
     cam = load_camera(p.poses, p.intr, f);
     ds = make_divisor(p.depth_scale);
-    if constexpr (DT == V3D_DEPTH_U16 && USE_TMA) frame_fast = cam.rigid && ds.ok && cam.fx.ok && cam.fy.ok && ds.b > 0.f;
+    if constexpr (DT == V3D_DEPTH_U16 && USE_TMA) fast_ok = cam.rigid && ds.ok && cam.fx.ok && cam.fy.ok && ds.b > 0.f;
   }
   for (int dy = t; dy < P; dy += kThreads) {
     const int sr = FROM_DEPTH ? __ldg(p.row_map + gi * P + dy) : gi * P + dy;
     const float vm = FROM_DEPTH ? __fsub_rn((float)sr, cam.cy) : 0.0f;
     s_srow[dy] = sr;
-    s_vm[dy] = make_float2(vm, (frame_fast && fabsf(vm) >= 0x1p-20f && fabsf(vm) <= 0x1p20f) ? 1.0f : 0.0f);
+    s_vm[dy] = make_float2(vm, 0.0f);
+    fast_ok = fast_ok && fabsf(vm) >= 0x1p-20f && fabsf(vm) <= 0x1p20f;
   }
 
   // per-thread column constants: thread t owns dst column t and (second round, taken from the top of
@@ -631,28 +717,29 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
   float um[2];
   size_t src_off[2];     // FROM_DEPTH: byte offset inside a staged row / element offset inside a global row
   uint32_t w_addr[2];    // shared address of this column's x slot in buffer 0
-  int fast_bits = 0;     // bit k: column k may use the branch-free uint16 path
+  uint32_t d_addr[2];    // shared address of this column's depth sample in staged row 0
   col[0] = (t < p.Sp) ? t : -1;
   col[1] = (kThreads + (kThreads - 1 - t) < p.Sp) ? kThreads + (kThreads - 1 - t) : -1;
+  if (p.Sp < kThreads) fast_ok = false;  // the fast loop assumes every thread owns column t
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     um[k] = 0.f;
     src_off[k] = 0;
     w_addr[k] = smem_u32(s_row + (col[k] >= 0 ? col[k] : 0));
+    d_addr[k] = smem_u32(s_depth);
     if (col[k] >= 0) {
       const int sc = FROM_DEPTH ? __ldg(p.col_map + col[k]) : col[k];
       if constexpr (FROM_DEPTH) {
         um[k] = __fsub_rn((float)sc, cam.cx);
-        if (frame_fast && fabsf(um[k]) >= 0x1p-20f && fabsf(um[k]) <= 0x1p20f) fast_bits |= 1 << k;
+        fast_ok = fast_ok && fabsf(um[k]) >= 0x1p-20f && fabsf(um[k]) <= 0x1p20f;
         src_off[k] = USE_TMA ? (size_t)(sc * kEsz - p.col_lo_byte) : (size_t)sc;
+        d_addr[k] += (uint32_t)src_off[k];
       } else {
         src_off[k] = (size_t)sc * 3;
       }
     }
   }
-  asm volatile("" : "+r"(fast_bits));  // keep the flag in a register instead of re-deriving it per row
-  const uint32_t d_base = smem_u32(s_depth);
-  __syncthreads();  // s_srow / s_vm / s_desc visible
+  const int all_fast = __syncthreads_and(fast_ok);  // also makes s_srow / s_vm / s_desc visible
   if constexpr (FROM_DEPTH && USE_TMA) mbar_wait(bar, 0);
 
   const bool is_sample = p.pool_mode >= V3D_POOL_SAMPLE9;
@@ -660,43 +747,21 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
     // ---- chains: thread q < 3G owns (axis a = q / G, patch j = q % G)
     const bool chain = t < 3 * G;
     const int a = chain ? t / G : 0, j = chain ? t - a * G : 0;
-    float acc = 0.0f, mx = -CUDART_INF_F, mneg = -CUDART_INF_F;
+    ChainAcc ca = {0.0f, -CUDART_INF_F, -CUDART_INF_F};
     const float* chain_src = s_row + a * kPlane + j * P;
-    uint32_t row_off = 0;  // byte offset of staged depth row dy
-    for (int dy = 0; dy < P; ++dy, row_off += (uint32_t)p.span) {
-      const uint32_t bsel = (dy & 1) ? (uint32_t)(3 * kPlane * 4) : 0u;
-      const float2 vmf = s_vm[dy];
-      const float vm = vmf.x;
-      const int row_bits = (vmf.y != 0.0f) ? fast_bits : 0;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (col[k] < 0) continue;
-        float x, y, z;
-        if constexpr (FROM_DEPTH) {
-          bool done = false;
-          if constexpr (DT == V3D_DEPTH_U16 && USE_TMA) {
-            if (row_bits & (1 << k)) {
-              const uint32_t raw = lds_u16(d_base + row_off + (uint32_t)src_off[k]);
-              const float d = (float)raw;
-              const bool nz = raw != 0;
-              float q0 = __fmul_rn(d, ds.r);
-              float q1 = __fmaf_rn(ds.r, __fmaf_rn(-ds.b, q0, d), q0);
-              const float cz = nz ? q1 : q0;
-              const float ax = __fmul_rn(um[k], cz);
-              q0 = __fmul_rn(ax, cam.fx.r);
-              q1 = __fmaf_rn(cam.fx.r, __fmaf_rn(-cam.fx.b, q0, ax), q0);
-              const float cx_ = nz ? q1 : q0;
-              const float ay = __fmul_rn(vm, cz);
-              q0 = __fmul_rn(ay, cam.fy.r);
-              q1 = __fmaf_rn(cam.fy.r, __fmaf_rn(-cam.fy.b, q0, ay), q0);
-              const float cy_ = nz ? q1 : q0;
-              x = __fadd_rn(__fmaf_rn(cam.P[2], cz, __fmaf_rn(cam.P[1], cy_, __fmul_rn(cam.P[0], cx_))), cam.P[3]);
-              y = __fadd_rn(__fmaf_rn(cam.P[6], cz, __fmaf_rn(cam.P[5], cy_, __fmul_rn(cam.P[4], cx_))), cam.P[7]);
-              z = __fadd_rn(__fmaf_rn(cam.P[10], cz, __fmaf_rn(cam.P[9], cy_, __fmul_rn(cam.P[8], cx_))), cam.P[11]);
-              done = true;
-            }
-          }
-          if (!done) {
+    if (all_fast) {
+      pool_rows_fast(cam, ds, P, (uint32_t)p.span, col[1] >= 0 ? 2 : 1, um, d_addr, w_addr, s_vm, chain, chain_src, p.pool_mode,
+                     p.clamp, ca);
+    } else {
+      uint32_t row_off = 0;  // byte offset of staged depth row dy
+      for (int dy = 0; dy < P; ++dy, row_off += (uint32_t)p.span) {
+        const uint32_t bsel = (dy & 1) ? (uint32_t)(3 * kPlane * 4) : 0u;
+        const float vm = s_vm[dy].x;
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
+          if (col[k] < 0) continue;
+          float x, y, z;
+          if constexpr (FROM_DEPTH) {
             float d;
             if constexpr (USE_TMA) {
               const unsigned char* sp = s_depth + row_off + src_off[k];
@@ -707,37 +772,24 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
               d = load_depth<DT>(p.depth, ((size_t)f * p.H + s_srow[dy]) * p.W + src_off[k]);
             }
             unproject_px(cam, d, um[k], vm, ds, x, y, z);
+            if (p.clamp.on) {
+              x = apply_clamp(p.clamp, x, 0);
+              y = apply_clamp(p.clamp, y, 1);
+              z = apply_clamp(p.clamp, z, 2);
+            }
+          } else {
+            const float* src = p.coords_in + ((size_t)f * p.S + s_srow[dy]) * p.S * 3 + src_off[k];
+            x = __ldg(src);
+            y = __ldg(src + 1);
+            z = __ldg(src + 2);
           }
-          if (p.clamp.on) {
-            x = apply_clamp(p.clamp, x, 0);
-            y = apply_clamp(p.clamp, y, 1);
-            z = apply_clamp(p.clamp, z, 2);
-          }
-        } else {
-          const float* src = p.coords_in + ((size_t)f * p.S + s_srow[dy]) * p.S * 3 + src_off[k];
-          x = __ldg(src);
-          y = __ldg(src + 1);
-          z = __ldg(src + 2);
+          sts_xyz(w_addr[k] + bsel, x, y, z);
         }
-        sts_xyz(w_addr[k] + bsel, x, y, z);
-      }
-      __syncthreads();
-      if (chain) {
-        const float* src = chain_src + ((dy & 1) ? 3 * kPlane : 0);
-        if (p.pool_mode == V3D_POOL_AVG) {
-          if (P == 14) acc = chain_add<14>(acc, src, P);
-          else if (P == 27) acc = chain_add<27>(acc, src, P);
-          else acc = chain_add<0>(acc, src, P);
-        } else {
-          for (int dx = 0; dx < P; ++dx) {
-            const float v = src[dx];
-            if (v > mx || v != v) mx = v;
-            const float nv = -v;
-            if (nv > mneg || nv != nv) mneg = nv;
-          }
-        }
+        __syncthreads();
+        if (chain) chain_row(ca, chain_src + ((dy & 1) ? 3 * kPlane : 0), P, p.pool_mode);
       }
     }
+    const float acc = ca.acc, mx = ca.mx, mneg = ca.mneg;
     if (chain) {
       const size_t tok = ((size_t)f * G + gi) * G + j;
       const bool have_table = p.table != nullptr;
@@ -805,7 +857,7 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
   // ---- stream the PE rows of this patch row (G tokens x E channels), fused token add
   const size_t row0 = ((size_t)f * G + gi) * G;
   const OutT* tokens = reinterpret_cast<const OutT*>(p.tokens_in);
-  stream_pe<OutT, 3>(p.g, p.dim_t, reinterpret_cast<const OutT*>(p.table), s_pts, s_off, s_flag, s_desc, G,
+  stream_pe<OutT>(p.g, p.dim_t, reinterpret_cast<const OutT*>(p.table), s_pts, s_off, s_flag, s_desc, G,
                      tokens ? tokens + row0 * p.g.E : nullptr, reinterpret_cast<OutT*>(p.pe_out) + row0 * p.g.E);
 }
 
