@@ -413,7 +413,97 @@ __device__ __forceinline__ void stream_rows(int cpt, int E, int n_tok, int n_off
   else stream_rows_u<OutT, 2, STRADDLE, ADD>(cpt, E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
 }
 
-// PE rows of `n_tok` tokens.
+// The streaming loop when no token of the CTA needs direct evaluation (the normal case with
+// discretised coordinates): same token-pair layout as stream_pass, stripped of every per-token test.
+// Per chunk: one shared load (row offset), two 128-bit global loads, four packed adds, one store.
+template <typename OutT, int U, bool STRADDLE, bool ADD>
+__device__ __forceinline__ void stream_pairs_clean(int l0, int cpt, int E, int n_pairs, int n_off, const OutT* __restrict__ table,
+                                                   const int* s_off, const ChunkDesc* s_desc, const OutT* tokens, OutT* out) {
+  constexpr int kWarps = kThreads / 32;
+  const int warp = threadIdx.x >> 5;
+  uint32_t offa[U], offb[U], ka[U], kb[U], rel[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int L = l0 + 32 * u;
+    const int ts = L >= cpt;
+    const int c8 = L - (ts ? cpt : 0);
+    const uint2 d = lds_u2(s_desc + c8);
+    offa[u] = (uint32_t)(ts * n_off + (int)(d.x >> 16)) * 4u;
+    ka[u] = d.x & 0xffffu;
+    offb[u] = (uint32_t)(ts * n_off + (int)(d.y >> 16)) * 4u;
+    kb[u] = d.y & 0xffffu;
+    rel[u] = (uint32_t)(ts * E + c8 * 8);
+  }
+  uint32_t off = smem_u32(s_off) + (uint32_t)(warp * 2 * n_off) * 4u;
+  const uint32_t off_step = (uint32_t)(kWarps * 2 * n_off) * 4u;
+  const size_t row_step = (size_t)kWarps * 2 * E;
+  const OutT* tp = ADD ? tokens + (size_t)warp * 2 * E : nullptr;
+  OutT* op = out + (size_t)warp * 2 * E;
+  for (int pair = warp; pair < n_pairs; pair += kWarps, off += off_step, op += row_step) {
+    Chunk<OutT> tv[U], pe[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (ADD) tv[u] = chunk_ld_stream(tp + rel[u]);
+      int o;
+      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + offa[u]));
+      pe[u] = chunk_ldg(table + ((uint32_t)o + ka[u]));
+      if (STRADDLE) {
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + offb[u]));
+        chunk_or(pe[u], chunk_ldg(table + ((uint32_t)o + kb[u])));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) chunk_st_stream(op + rel[u], ADD ? chunk_add(tv[u], pe[u]) : pe[u]);
+    if (ADD) tp += row_step;
+  }
+}
+
+// one token row, lanes stride its chunks (the odd last token of a CTA)
+template <typename OutT, bool STRADDLE, bool ADD>
+__device__ __forceinline__ void stream_single_clean(int tok, int cpt, int E, int n_off, const OutT* __restrict__ table,
+                                                    const int* s_off, const ChunkDesc* s_desc, const OutT* tokens, OutT* out) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t off = smem_u32(s_off) + (uint32_t)(tok * n_off) * 4u;
+  const OutT* tp = ADD ? tokens + (size_t)tok * E : nullptr;
+  OutT* op = out + (size_t)tok * E;
+#pragma unroll 2
+  for (int c8 = lane; c8 < cpt; c8 += 32) {
+    const uint2 d = lds_u2(s_desc + c8);
+    Chunk<OutT> tv;
+    if (ADD) tv = chunk_ld_stream(tp + c8 * 8);
+    int o;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + (d.x >> 16) * 4u));
+    Chunk<OutT> pe = chunk_ldg(table + ((uint32_t)o + (d.x & 0xffffu)));
+    if (STRADDLE) {
+      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + (d.y >> 16) * 4u));
+      chunk_or(pe, chunk_ldg(table + ((uint32_t)o + (d.y & 0xffffu))));
+    }
+    chunk_st_stream(op + c8 * 8, ADD ? chunk_add(tv, pe) : pe);
+  }
+}
+
+template <typename OutT, bool STRADDLE, bool ADD>
+__device__ __forceinline__ void stream_rows_clean(int cpt, int E, int n_tok, int n_off, const OutT* __restrict__ table,
+                                                  const int* s_off, const ChunkDesc* s_desc, const OutT* tokens, OutT* out) {
+  constexpr int kWarps = kThreads / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_pairs = n_tok >> 1;
+  const int total = 2 * cpt;
+  if (total % 96 == 0) {
+    for (int l0 = 0; l0 < total; l0 += 96)
+      stream_pairs_clean<OutT, 3, STRADDLE, ADD>(l0 + lane, cpt, E, n_pairs, n_off, table, s_off, s_desc, tokens, out);
+  } else if (total % 64 == 0) {
+    for (int l0 = 0; l0 < total; l0 += 64)
+      stream_pairs_clean<OutT, 2, STRADDLE, ADD>(l0 + lane, cpt, E, n_pairs, n_off, table, s_off, s_desc, tokens, out);
+  } else {
+    for (int tok = warp; tok < 2 * n_pairs; tok += kWarps)
+      stream_single_clean<OutT, STRADDLE, ADD>(tok, cpt, E, n_off, table, s_off, s_desc, tokens, out);
+  }
+  if ((n_tok & 1) && warp == (n_pairs % kWarps))
+    stream_single_clean<OutT, STRADDLE, ADD>(n_tok - 1, cpt, E, n_off, table, s_off, s_desc, tokens, out);
+}
+
+// PE rows of `n_tok` tokens; must be called by every thread of the CTA.
 //   s_pts  [n_tok][n_slots]    coordinates the PE is evaluated on
 //   s_off  [n_tok][n_slots+1]  element offset of each slot's table row (-1 = evaluate directly);
 //                              entry n_slots is the zero row
@@ -426,8 +516,21 @@ __device__ __forceinline__ void stream_pe(const PeGeom& g, const float* __restri
   constexpr int kWarps = kThreads / 32;
   const int n_off = g.n_slots + 1;
   if ((g.E & 7) == 0) {
+    int mine = 0;
+    for (int i = threadIdx.x; i < n_tok; i += kThreads) mine |= s_flag[i];
+    const int any_direct = __syncthreads_or(mine);
+    const bool straddle = (g.nf & 7) != 0;
+    if (table != nullptr && !any_direct) {
+      if (tokens) {
+        if (straddle) stream_rows_clean<OutT, true, true>(g.cpt, g.E, n_tok, n_off, table, s_off, s_desc, tokens, out);
+        else stream_rows_clean<OutT, false, true>(g.cpt, g.E, n_tok, n_off, table, s_off, s_desc, tokens, out);
+      } else {
+        if (straddle) stream_rows_clean<OutT, true, false>(g.cpt, g.E, n_tok, n_off, table, s_off, s_desc, tokens, out);
+        else stream_rows_clean<OutT, false, false>(g.cpt, g.E, n_tok, n_off, table, s_off, s_desc, tokens, out);
+      }
+      return;
+    }
     if (table != nullptr) {
-      const bool straddle = (g.nf & 7) != 0;
       if (tokens) {
         if (straddle) stream_rows<OutT, true, true>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
         else stream_rows<OutT, false, true>(g.cpt, g.E, n_tok, n_off, table, s_off, s_flag, s_desc, tokens, out);
