@@ -776,6 +776,15 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
   int* s_flag = s_off + G * n_off;
   ChunkDesc* s_desc = reinterpret_cast<ChunkDesc*>((reinterpret_cast<uintptr_t>(s_flag + G) + 7) & ~(uintptr_t)7);
 
+  // ---- the token rows this CTA will add the PE to are independent of everything computed below:
+  // have the TMA unit pull them into L2 now, so that the streaming phase finds them there
+  if (p.pe_mode != V3D_PE_NONE && p.tokens_in != nullptr && t == 32) {
+    const size_t row_bytes = (size_t)G * p.g.E * sizeof(OutT);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.tokens_in) + ((size_t)f * G + gi) * row_bytes;
+    if ((row_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      for (size_t o = 0; o < row_bytes; o += 32768) tma_prefetch_l2(src + o, (uint32_t)min((size_t)32768, row_bytes - o));
+    }
+  }
   // ---- stage the P depth rows of this patch row with the TMA unit
   if constexpr (FROM_DEPTH && USE_TMA) {
     if (t == 0) {
