@@ -16,3 +16,46 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session")
+def D(golden_dir):
+    import json
+
+    with open(os.path.join(golden_dir, "dataset.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def dataset(tmp_path_factory, D):
+    """The on-disk fixture of the golden run, plus the reference's own select-frames JSON."""
+    import json
+
+    import fixtures
+
+    root = str(tmp_path_factory.mktemp("scannet_like"))
+    metas = D["scenes"]
+    infos = {"train": [], "val": [], "test": []}
+    boxes = {"train": {}, "val": {}}
+    pcs = {}
+    import pickle
+    for name, m in metas.items():
+        info, bx, pc, sc = fixtures.write_scene(root, m["seed"], m["n_total"], m["H"], m["W"], m["split"])
+        infos[m["split"]].append(info)
+        boxes["val" if m["split"] == "val" else "train"][info["sample_idx"]] = bx
+        pcs[name] = [tuple(int(t) for t in v) for v in pc]
+    os.makedirs(os.path.join(root, "data", "embodiedscan"), exist_ok=True)
+    os.makedirs(os.path.join(root, "data", "metadata"), exist_ok=True)
+    for split in infos:
+        with open(os.path.join(root, "data", "embodiedscan", f"embodiedscan_infos_{split}.pkl"), "wb") as f:
+            pickle.dump({"data_list": infos[split]}, f)
+    for k, fn in (("train", "scannet_train_gt_box.json"), ("val", "scannet_val_pred_box.json")):
+        with open(os.path.join(root, "data", "metadata", fn), "w") as f:
+            json.dump(boxes[k], f)
+    with open(os.path.join(root, "data", "metadata", "pcd_discrete_0.1.pkl"), "wb") as f:
+        pickle.dump(pcs, f)
+    with open(os.path.join(root, "data", "metadata", "scannet_select_frames.json"), "w") as f:
+        json.dump(D["select_frames"], f)
+    return root
+
+

@@ -465,3 +465,60 @@ def test_exact_division_exhaustive(divisor):
     cabi.check(lib.v3d_selftest_division(float(np.float32(divisor)), bad.data_ptr(), cabi.stream_ptr(DEV)))
     torch.cuda.synchronize()
     assert int(bad.item()) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# VideoProcessor end to end on the on-disk fixture, against the reference's own outputs
+# ---------------------------------------------------------------------------------------------
+def _vp(root, strategy, **kw):
+    return VU.VideoProcessor(video_folder=os.path.join(root, "data"), annotation_dir=os.path.join(root, "data", "embodiedscan"),
+                             voxel_size=0.1, min_xyz_range=[-15, -15, -5], max_xyz_range=[15, 15, 5],
+                             frame_sampling_strategy=strategy, metadata_dir=os.path.join(root, "data", "metadata"), **kw)
+
+
+@pytest.mark.parametrize("strategy", ["uniform", "mc-ratio95", "mc-ratio95-norm"])
+@pytest.mark.parametrize("lazy", [False, True])
+def test_video_processor_matches_reference(dataset, D, strategy, lazy, monkeypatch):
+    import hashlib
+
+    monkeypatch.chdir(dataset)  # the MC frame lists hold paths relative to the working directory, like upstream
+
+    name = "scene0003_00"
+    gold = D["video_processor"][strategy][name]
+    vp = _vp(dataset, strategy, lazy=lazy)
+    d = vp.process_3d_video(f"scannet/{name}", fixtures.FakeImageProcessor(384), force_sample=True, frames_upbound=3)
+    wc = d["world_coords"]
+    full = wc.materialize() if lazy else wc
+    assert full.is_cuda and list(full.shape) == gold["world_coords_shape"]
+    got = full.cpu().numpy()
+    np.testing.assert_array_equal(got[:, ::61, ::67], np.array(gold["world_coords_sample"], np.float32))
+    assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == gold["world_coords_sha"]
+    np.testing.assert_array_equal(np.asarray(d["boundry"].tolist(), np.float32), np.array(gold["boundry"], np.float32))
+    assert d["objects"].tolist() == gold["objects"] and d["video_size"] == gold["video_size"]
+
+
+def test_lazy_handle_through_the_reference_call_structure(dataset, D, monkeypatch):
+    monkeypatch.chdir(dataset)
+    """What prepare_inputs_labels_for_multimodal does with video_dict (llava_arch.py:386-420, 506-517), on a
+    lazy handle: per-scene pooling straight from depth, discretisation, PE + add -- equal to the eager path."""
+    vp_l, vp_e = _vp(dataset, "uniform", lazy=True), _vp(dataset, "uniform", lazy=False)
+    ip = fixtures.FakeImageProcessor(384)
+    dl = vp_l.process_3d_video("scannet/scene0003_00", ip, force_sample=True, frames_upbound=3)
+    de = vp_e.process_3d_video("scannet/scene0003_00", ip, force_sample=True, frames_upbound=3)
+    dl["box_input"] = de["box_input"] = None
+    ml, me = VU.merge_video_dict([dl]), VU.merge_video_dict([de])
+    wl = ml["world_coords"].to(DEV).to(torch.bfloat16)  # Trainer moves + casts float tensors to bf16
+    we = me["world_coords"].to(DEV)
+    _ = wl.view(1, -1, 3).min(dim=1)[0]  # llava_arch.py:387: accepted, never evaluated
+    pooled_l = [C.average_coordinate_in_patch(c) for c in wl]
+    pooled_e = [C.average_coordinate_in_patch(c) for c in we]
+    assert pooled_l[0].dtype == torch.bfloat16 and pooled_l[0].shape == (3, 14, 14, 3)
+    assert torch.equal(pooled_l[0].float(), pooled_e[0].to(torch.bfloat16).float())
+    disc = C.discrete_coords(pooled_e[0], None)
+    mod = PositionEmbeddingSine3D(3584)
+    tokens = synthetic.make_tokens(5, 3, 196, 3584).to(DEV)
+    out = tokens + mod(disc.flatten(1, 2).to(torch.bfloat16))
+    assert out.shape == (3, 196, 3584)
+    # slicing like the object-proposal code (llava_arch.py:360-373) materialises on demand
+    sl = ml["world_coords"].to(DEV)[0][:, :378, :378, :]
+    assert torch.equal(sl, we[0][:, :378, :378, :])
