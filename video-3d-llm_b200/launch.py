@@ -1,0 +1,92 @@
+"""Overlay launcher: run the reference's own scripts, unchanged, on top of the CUDA front end.
+
+    torchrun ... -m video_3d_llm_b200.launch llava/train/train_3d.py <the script's own args>
+    python -m video_3d_llm_b200.launch llava/eval/model_scanqa.py --frame_sampling_strategy mc-ratio95 ...
+    python -m video_3d_llm_b200.launch scripts/3d/preprocessing/max_coverage_sampling.py --voxel_size 0.1
+
+`install()` rebinds, before the script is executed,
+  llava.video_utils.{unproject, VideoProcessor, merge_video_dict}          (bound by `from ... import` at
+      script import: train_3d.py:48, model_scanqa.py:18, max_coverage_sampling.py:6)
+  llava.model.position_encoding.{PositionEmbeddingSine3D, PositionEmbeddingMLP}   (imported lazily inside
+      LlavaMetaModel.__init__, llava_arch.py:49)
+  LlavaMetaForCausalLM.{average_coordinate_in_patch, minmax_coordinate_in_patch, sample_n_points,
+      discrete_coords}                                                      (called at llava_arch.py:396-420)
+The 500-line prepare_inputs_labels_for_multimodal itself is left alone: with VideoProcessor(lazy=True) the
+`world_coords` it receives is a handle over raw depth/pose/intrinsics, so the first patched helper it
+calls runs the fused kernel and the (V,384,384,3) tensor is never built (video_utils.LazyWorldCoords).
+"""
+from __future__ import annotations
+
+import os
+import runpy
+import sys
+
+
+def install(lazy: bool | None = None) -> dict:
+    """Patch the reference modules in place; returns {dotted name: replacement} for inspection."""
+    import importlib
+
+    from . import coords, position_encoding, video_utils
+
+    if lazy is None:
+        lazy = os.environ.get("V3D_LAZY", "1") != "0"
+    done = {}
+
+    vu = importlib.import_module("llava.video_utils")
+
+    class VideoProcessor(video_utils.VideoProcessor):
+        def __init__(self, *a, **kw):
+            kw.setdefault("lazy", lazy)
+            super().__init__(*a, **kw)
+
+    for name, obj in (("unproject", video_utils.unproject), ("VideoProcessor", VideoProcessor),
+                      ("merge_video_dict", video_utils.merge_video_dict)):
+        setattr(vu, name, obj)
+        done[f"llava.video_utils.{name}"] = obj
+
+    pe = importlib.import_module("llava.model.position_encoding")
+    for name in ("PositionEmbeddingSine3D", "PositionEmbeddingMLP"):
+        setattr(pe, name, getattr(position_encoding, name))
+        done[f"llava.model.position_encoding.{name}"] = getattr(position_encoding, name)
+
+    arch = importlib.import_module("llava.model.llava_arch")
+    cls = arch.LlavaMetaForCausalLM
+
+    def average_coordinate_in_patch(self, world_coords, patch_size=27):
+        return coords.average_coordinate_in_patch(world_coords, patch_size)
+
+    def minmax_coordinate_in_patch(self, world_coords, patch_size=27):
+        return coords.minmax_coordinate_in_patch(world_coords, patch_size)
+
+    def sample_n_points(self, world_coords, n_points=9):
+        return coords.sample_n_points(world_coords, n_points)
+
+    def discrete_coords(self, world_coords, xyz_min):
+        return coords.discrete_coords(world_coords, xyz_min, voxel_size=self.config.voxel_size,
+                                      min_xyz_range=self.config.min_xyz_range, max_xyz_range=self.config.max_xyz_range)
+
+    for fn in (average_coordinate_in_patch, minmax_coordinate_in_patch, sample_n_points, discrete_coords):
+        setattr(cls, fn.__name__, fn)
+        done[f"llava.model.llava_arch.LlavaMetaForCausalLM.{fn.__name__}"] = fn
+    return done
+
+
+def main(argv=None) -> None:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv:
+        raise SystemExit(__doc__)
+    script = argv[0]
+    if os.path.basename(script) == "max_coverage_sampling.py":
+        # the offline MC script is replaced wholesale: same CLI, same JSON (mc_sampling.main)
+        from . import mc_sampling
+
+        sys.argv = argv
+        runpy.run_module(mc_sampling.__name__, run_name="__main__")
+        return
+    install()
+    sys.argv = argv
+    runpy.run_path(script, run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()
