@@ -207,7 +207,7 @@ def mc_leg(rank: int, world: int, dev, steps: int, warmup: int):
     from video_3d_llm_b200.mc_sampling import MCSampler
     from video_3d_llm_b200 import sharding
 
-    n_scenes, cand = 8, 150
+    n_scenes, cand = 16, 150
     scenes = []
     for s in range(n_scenes):
         seed = 1000 * rank + 500 + s

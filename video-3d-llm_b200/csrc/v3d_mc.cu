@@ -78,6 +78,30 @@ __device__ __forceinline__ int voxel_id(float w, const Divisor& voxel, float rcp
 
 static constexpr int kPxPerThread = 8;
 
+// rint(RN(w / voxel)) without the division when it provably does not matter: t = w * r approximates the
+// IEEE quotient q within |t| * 2^-22 (r is within an ulp of 1/voxel, one more rounding for the product),
+// so if t is farther than that (with a 2x safety factor) from every half-integer, rint(q) == rint(t).
+// About one coordinate in 10^4 lands in the guard band and takes the exact division.
+__device__ __forceinline__ int voxel_id_fast(float w, const Divisor& voxel) {
+  const float t = __fmul_rn(w, voxel.r);
+  const float n = rintf(t);
+  const float margin = __fmaf_rn(fabsf(t), -0x1p-21f, 0.5f);
+  if (fabsf(__fsub_rn(t, n)) < margin && fabsf(t) < 1.0e9f) return (int)n;
+  return voxel_id(w, voxel, 0.f, V3D_DIV_IEEE);
+}
+
+struct Vox {
+  int i, j, k;
+};
+__device__ __forceinline__ bool vox_eq(const Vox& a, const Vox& b) { return a.i == b.i && a.j == b.j && a.k == b.k; }
+
+// Candidate voxels of one block iteration are queued in shared memory so that the hash probes run with
+// dense lanes (a probe is a dependent chain of L2 loads; run inline, 2-4 of 32 lanes would be active).
+__device__ __forceinline__ void mc_push(int3* s_q, int* s_qn, const Vox& v) {
+  const int pos = atomicAdd(s_qn, 1);
+  s_q[pos] = make_int3(v.i, v.j, v.k);
+}
+
 template <int DT>
 __global__ void __launch_bounds__(kMcThreads) k_mc_voxelize(const v3d_mc_scene* __restrict__ scenes, int H, int W,
                                                             float depth_scale, float voxel, int div_mode, int slabs_per_frame,
@@ -90,50 +114,102 @@ __global__ void __launch_bounds__(kMcThreads) k_mc_voxelize(const v3d_mc_scene* 
   const Divisor ds = make_divisor(depth_scale);
   const Divisor dv = make_divisor(voxel);
   const int groups_per_row = (W + kPxPerThread - 1) / kPxPerThread;
+  const int lane = threadIdx.x & 31;
+  __shared__ int3 s_q[kMcThreads * kPxPerThread];  // 24 KB
+  __shared__ int s_qn;
+  if (threadIdx.x == 0) s_qn = 0;
+  __syncthreads();
   for (int item = blockIdx.x; item < sc.n_frames * slabs_per_frame; item += gridDim.x) {
     const int f = item / slabs_per_frame, r0 = (item - f * slabs_per_frame) * rows_per_slab;
     const int r1 = min(r0 + rows_per_slab, H);
     const Camera cam = load_camera(sc.poses, sc.intr, f);
+    // uint16 depth + rigid pose + divisors well inside the normal range: branch-free unprojection (see
+    // pool_rows_fast in v3d_frontend.cu) and division-free voxel ids
+    const bool frame_fast = DT == V3D_DEPTH_U16 && div_mode == V3D_DIV_IEEE && cam.rigid && ds.ok && cam.fx.ok && cam.fy.ok &&
+                            ds.b > 0.f && dv.ok;
     uint32_t* bits = sc.bitsets + (size_t)f * words;
-    for (int g = threadIdx.x; g < (r1 - r0) * groups_per_row; g += kMcThreads) {
-      const int r = r0 + g / groups_per_row, c0 = (g - (g / groups_per_row) * groups_per_row) * kPxPerThread;
-      const float vm = __fsub_rn((float)r, cam.cy);
-      const size_t base = ((size_t)f * H + r) * W + c0;
-      float d[kPxPerThread];
-      if constexpr (DT == V3D_DEPTH_U16) {
-        if (c0 + kPxPerThread <= W && ((base * 2 + reinterpret_cast<uintptr_t>(sc.depth)) & 15) == 0) {
-          const uint4 raw = ld_stream_v4(reinterpret_cast<const uint16_t*>(sc.depth) + base);
-          const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+    const int n_groups = (r1 - r0) * groups_per_row;
+    // all threads of the block iterate together (barriers and shuffles below); whole warps past the end idle
+    for (int g0 = 0; g0 < n_groups; g0 += kMcThreads) {
+      const int g = g0 + threadIdx.x;
+      const bool valid = g < n_groups;
+      Vox first = {0x7fffffff, 0x7fffffff, 0x7fffffff}, prev = first;
+      int n_px = 0, c0 = 0;
+      if (valid) {
+        const int gr = g / groups_per_row;
+        const int r = r0 + gr;
+        c0 = (g - gr * groups_per_row) * kPxPerThread;
+        n_px = min(kPxPerThread, W - c0);
+        const float vm = __fsub_rn((float)r, cam.cy);
+        const size_t base = ((size_t)f * H + r) * W + c0;
+        bool fast = false;
+        if constexpr (DT == V3D_DEPTH_U16) {
+          const float um0 = __fsub_rn((float)c0, cam.cx), um7 = __fsub_rn((float)(c0 + kPxPerThread - 1), cam.cx);
+          // (u - cx) of the 8 columns lies between um0 and um7: all are in the fast range unless that
+          // interval comes within 2^-20 of zero
+          fast = frame_fast && n_px == kPxPerThread && ((base * 2 + reinterpret_cast<uintptr_t>(sc.depth)) & 15) == 0 &&
+                 fabsf(vm) >= 0x1p-20f && fabsf(vm) <= 0x1p20f && fabsf(um0) <= 0x1p20f && fabsf(um7) <= 0x1p20f &&
+                 (um0 > 0x1p-20f || um7 < -0x1p-20f);
+        }
+        if (fast) {
+          const uint4 q = ld_stream_v4(reinterpret_cast<const uint16_t*>(sc.depth) + base);
+          const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            d[2 * e] = (float)(w4[e] & 0xffffu);
-            d[2 * e + 1] = (float)(w4[e] >> 16);
+          for (int e = 0; e < kPxPerThread; ++e) {
+            const uint32_t raw = (e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xffffu);
+            const float df = (float)raw;
+            const bool nz = raw != 0;
+            const float um = __fsub_rn((float)(c0 + e), cam.cx);
+            float q0 = __fmul_rn(df, ds.r);
+            float q1 = __fmaf_rn(ds.r, __fmaf_rn(-ds.b, q0, df), q0);
+            const float cz = nz ? q1 : q0;
+            const float ax = __fmul_rn(um, cz);
+            q0 = __fmul_rn(ax, cam.fx.r);
+            q1 = __fmaf_rn(cam.fx.r, __fmaf_rn(-cam.fx.b, q0, ax), q0);
+            const float cx_ = nz ? q1 : q0;
+            const float ay = __fmul_rn(vm, cz);
+            q0 = __fmul_rn(ay, cam.fy.r);
+            q1 = __fmaf_rn(cam.fy.r, __fmaf_rn(-cam.fy.b, q0, ay), q0);
+            const float cy_ = nz ? q1 : q0;
+            const float x = __fadd_rn(__fmaf_rn(cam.P[2], cz, __fmaf_rn(cam.P[1], cy_, __fmul_rn(cam.P[0], cx_))), cam.P[3]);
+            const float y = __fadd_rn(__fmaf_rn(cam.P[6], cz, __fmaf_rn(cam.P[5], cy_, __fmul_rn(cam.P[4], cx_))), cam.P[7]);
+            const float z = __fadd_rn(__fmaf_rn(cam.P[10], cz, __fmaf_rn(cam.P[9], cy_, __fmul_rn(cam.P[8], cx_))), cam.P[11]);
+            const Vox v = {voxel_id_fast(x, dv), voxel_id_fast(y, dv), voxel_id_fast(z, dv)};
+            if (e == 0) first = v;
+            else if (!vox_eq(v, prev)) mc_push(s_q, &s_qn, v);
+            prev = v;
           }
         } else {
-#pragma unroll
-          for (int e = 0; e < kPxPerThread; ++e) d[e] = (c0 + e < W) ? load_depth<DT>(sc.depth, base + e) : 0.f;
+#pragma unroll 1
+          for (int e = 0; e < n_px; ++e) {
+            float x, y, z;
+            unproject_px(cam, load_depth<DT>(sc.depth, base + e), __fsub_rn((float)(c0 + e), cam.cx), vm, ds, x, y, z);
+            const Vox v = {voxel_id(x, dv, rcp, div_mode), voxel_id(y, dv, rcp, div_mode), voxel_id(z, dv, rcp, div_mode)};
+            if (e == 0) first = v;
+            else if (!vox_eq(v, prev)) mc_push(s_q, &s_qn, v);
+            prev = v;
+          }
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < kPxPerThread; ++e) d[e] = (c0 + e < W) ? load_depth<DT>(sc.depth, base + e) : 0.f;
       }
-      int li = 0x7fffffff, lj = 0x7fffffff, lk = 0x7fffffff;  // previous pixel's voxel (run-length dedup)
-#pragma unroll
-      for (int e = 0; e < kPxPerThread; ++e) {
-        if (c0 + e >= W) break;
-        float x, y, z;
-        unproject_px(cam, d[e], __fsub_rn((float)(c0 + e), cam.cx), vm, ds, x, y, z);
-        const int vi = voxel_id(x, dv, rcp, div_mode), vj = voxel_id(y, dv, rcp, div_mode), vk = voxel_id(z, dv, rcp, div_mode);
-        if (vi == li && vj == lj && vk == lk) continue;
-        li = vi;
-        lj = vj;
-        lk = vk;
-        const int b = hash_find(tab, mask, vi, vj, vk);
+      // the first pixel of a group is a duplicate if it equals the last pixel of the left neighbour lane
+      Vox left;
+      left.i = __shfl_up_sync(0xffffffffu, prev.i, 1);
+      left.j = __shfl_up_sync(0xffffffffu, prev.j, 1);
+      left.k = __shfl_up_sync(0xffffffffu, prev.k, 1);
+      const int left_px = __shfl_up_sync(0xffffffffu, n_px, 1);
+      if (n_px > 0 && (lane == 0 || left_px != kPxPerThread || c0 == 0 || !vox_eq(first, left))) mc_push(s_q, &s_qn, first);
+      __syncthreads();
+      const int qn = s_qn;
+      for (int i = threadIdx.x; i < qn; i += kMcThreads) {
+        const int3 v = s_q[i];
+        const int b = hash_find(tab, mask, v.x, v.y, v.z);
         if (b >= 0) {
           const uint32_t m = 1u << (b & 31);
           if (!(bits[b >> 5] & m)) atomicOr(bits + (b >> 5), m);
         }
       }
+      __syncthreads();
+      if (threadIdx.x == 0) s_qn = 0;
     }
   }
 }
@@ -347,7 +423,8 @@ static int launch_voxelize(const v3d_mc_scene* dev_scenes, int n_scenes, int max
     bx = bx < 1 ? 1 : (bx > 1024 ? 1024 : bx);
     k_mc_build<<<dim3(bx, n_scenes), kMcThreads, 0, s>>>(dev_scenes);
   }
-  const int rows_per_slab = 8;
+  // 16 rows x (640/8) groups = 1280 = 5 full block iterations for ScanNet-shaped depth
+  const int rows_per_slab = 16;
   const int slabs = (H + rows_per_slab - 1) / rows_per_slab;
   // enough CTAs per scene to fill the machine a few times over, grid.y = scene
   long want = ((long)num_sms() * 16 + n_scenes - 1) / n_scenes;
