@@ -1,9 +1,383 @@
-// v3d_mlp.cu -- learned-projection PE (PositionEmbeddingMLP) on tcgen05/TMEM.  Placeholder until
-// the tensor-core kernel lands: the entry point exists (include/v3d.h) and fails loudly.
+// v3d_mlp.cu -- learned-projection PE on tcgen05 / TMEM (C ABI: v3d_pe_mlp, include/v3d.h).
+//
+// Replaces llava/model/position_encoding.py:52-84 (`PositionEmbeddingMLP.forward`) + the add of
+// llava/model/llava_arch.py:515:
+//     out = tokens + Linear(512,E)( ReLU( LayerNorm(512)( Linear(3,512)(coords) ) ) )
+// The 512-wide hidden activations are produced inside the kernel and never touch HBM; the 512 -> E
+// contraction (the only dense contraction on the path) runs on the 5th-generation tensor cores.
+//
+// One persistent CTA per SM, 256 threads, warp-specialised:
+//   warp 0    TMA producer: W2 tiles (BLOCK_N rows x 64 k, 128-byte swizzle) through a ring of mbarriers
+//   warp 1    MMA issuer  : tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16; owns TMEM alloc
+//   warps 4-7 (a) build the A operand of an M tile (128 tokens x 512 hidden, bf16) straight into the
+//             canonical K-major SWIZZLE_128B layout the MMA reads: Linear(3,512) + LayerNorm + ReLU
+//             per token (one thread per token row = one TMEM lane);
+//             (b) epilogue: tcgen05.ld the fp32 accumulator, + bias, round to bf16, + tokens, store.
+// Accumulators are double buffered in TMEM (2 x BLOCK_N columns), so the MMAs of N tile i+1 overlap the
+// epilogue of N tile i.  A (128 KB) stays resident in shared memory for all N tiles of its M tile.
+#include <cuda.h>
+
 #include "v3d_common.cuh"
 
-extern "C" int v3d_pe_mlp(const float*, int, int, const float*, const float*, const float*, const float*, float, const void*,
-                          const float*, const void*, void*, v3d_stream_t) {
-  v3d::set_error("v3d_pe_mlp: tcgen05 kernel not built into this library yet");
-  return V3D_E_UNSUPPORTED;
+namespace v3d {
+
+static constexpr int kMlpThreads = 256;
+static constexpr int kHidden = 512;          // nn.Linear(3, 512) of the reference module
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;           // 64 bf16 = 128 bytes = one swizzle atom
+static constexpr int kNumKBlocks = kHidden / kBlockK;  // 8
+static constexpr int kStages = 3;            // W2 ring
+static constexpr int kABytes = kBlockM * kHidden * 2;  // 131072
+static constexpr int kAKBlockBytes = kBlockM * kBlockK * 2;  // 16384
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4
+// in bits [0,14), LBO (unused for one swizzle atom along K) in [16,30), SBO = 8 rows x 128 B = 1024 B
+// (>> 4) in [32,46), version 1 in [46,48), layout type SWIZZLE_128B (2) in [61,64).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(const void* smem_ptr) {
+  const uint64_t addr = (uint64_t)((smem_u32(smem_ptr) & 0x3FFFFu) >> 4);
+  return addr | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = fp32, A = B = bf16, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every tcgen05 operation issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct MlpParams {
+  const float* coords;   // (M,3)
+  const float* w1;       // (512,3)
+  const float* b1;       // (512)
+  const float* gamma;    // (512)
+  const float* beta;     // (512)
+  const float* b2;       // (E)
+  const __nv_bfloat16* tokens;  // (M,E) or null
+  __nv_bfloat16* out;    // (M,E)
+  int M, E;
+  float eps;
+};
+
+// shared memory map (dynamic, 1024-byte aligned base):
+//   [0, 128K)                A operand: 8 k-blocks of [128 rows][128 B], SWIZZLE_128B
+//   [128K, 128K + S*BN*128)  W2 ring
+//   then: float4 w1b1[512], float2 gb[512], barriers, tmem base
+template <int BLOCK_N>
+struct MlpSmem {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kOffB = kABytes;
+  static constexpr int kOffW1 = kOffB + kStages * kBBytes;
+  static constexpr int kOffGB = kOffW1 + kHidden * 16;
+  static constexpr int kOffBar = kOffGB + kHidden * 8;
+  // barriers: b_full[S], b_empty[S], a_full, tmem_full[2], tmem_empty[2]
+  static constexpr int kNumBars = 2 * kStages + 1 + 4;
+  static constexpr int kOffTmem = kOffBar + kNumBars * 8;
+  static constexpr int kTotal = kOffTmem + 16;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant__ CUtensorMap w2_map, const MlpParams p) {
+  using S = MlpSmem<BLOCK_N>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  unsigned char* s_a = smem;
+  unsigned char* s_b = smem + S::kOffB;
+  float4* s_w1 = reinterpret_cast<float4*>(smem + S::kOffW1);
+  float2* s_gb = reinterpret_cast<float2*>(smem + S::kOffGB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* b_full = bars;
+  uint64_t* b_empty = bars + kStages;
+  uint64_t* a_full = bars + 2 * kStages;
+  uint64_t* t_full = bars + 2 * kStages + 1;
+  uint64_t* t_empty = bars + 2 * kStages + 3;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + S::kOffTmem);
+
+  constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+
+  // ---- one-time setup
+  for (int k = threadIdx.x; k < kHidden; k += kMlpThreads) {
+    s_w1[k] = make_float4(__ldg(p.w1 + 3 * k), __ldg(p.w1 + 3 * k + 1), __ldg(p.w1 + 3 * k + 2), __ldg(p.b1 + k));
+    s_gb[k] = make_float2(__ldg(p.gamma + k), __ldg(p.beta + k));
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&w2_map) : "memory");
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(b_full + i, 1);
+      mbar_init(b_empty + i, 1);
+    }
+    mbar_init(a_full, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(t_full + i, 1);
+      mbar_init(t_empty + i, 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int n_tiles = p.E / BLOCK_N;
+
+  if (warp == 0) {
+    // ================= TMA producer: W2 tiles for every (m tile, n tile, k block) =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
+        for (int nt = 0; nt < n_tiles; ++nt)
+          for (int kb = 0; kb < kNumKBlocks; ++kb, ++it) {
+            const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
+            mbar_wait(b_empty + stage, phase ^ 1);
+            mbar_arrive_expect_tx(b_full + stage, (uint32_t)S::kBBytes);
+            tma_load_2d(s_b + stage * S::kBBytes, &w2_map, kb * kBlockK, nt * BLOCK_N, b_full + stage);
+          }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+      uint32_t it = 0, acc_it = 0, a_phase = 0;
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, a_phase ^= 1) {
+        mbar_wait(a_full, a_phase);  // A operand of this M tile is in shared memory
+        tcgen05_fence_after();
+        for (int nt = 0; nt < n_tiles; ++nt, ++acc_it) {
+          const uint32_t acc = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
+          mbar_wait(t_empty + acc, acc_phase ^ 1);  // epilogue has drained this accumulator
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+          for (int kb = 0; kb < kNumKBlocks; ++kb, ++it) {
+            const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
+            mbar_wait(b_full + stage, phase);
+            tcgen05_fence_after();
+            const uint64_t da = make_kmajor_sw128_desc(s_a + kb * kAKBlockBytes);
+            const uint64_t db = make_kmajor_sw128_desc(s_b + stage * S::kBBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes: +2 in the >>4 address field
+              umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            umma_commit(b_empty + stage);  // frees the W2 slot when these MMAs have read it
+          }
+          umma_commit(t_full + acc);  // accumulator complete
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= A producer + epilogue: thread = token row = TMEM lane =====================
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;       // row inside the M tile
+    uint32_t acc_it = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+      const int m = mt * kBlockM + r;
+      const bool row_ok = m < p.M;
+      // ---- (a) hidden activations of this token: Linear(3,512) -> LayerNorm -> ReLU -> bf16
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+      if (row_ok) {
+        c0 = __ldg(p.coords + 3 * (size_t)m);
+        c1 = __ldg(p.coords + 3 * (size_t)m + 1);
+        c2 = __ldg(p.coords + 3 * (size_t)m + 2);
+      }
+      // LayerNorm statistics, shifted by the first element for stability (biased variance, as torch)
+      float h0;
+      {
+        const float4 w = s_w1[0];
+        h0 = fmaf(w.x, c0, fmaf(w.y, c1, fmaf(w.z, c2, w.w)));
+      }
+      float sum = 0.f, sq = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < kHidden; ++k) {
+        const float4 w = s_w1[k];
+        const float d = fmaf(w.x, c0, fmaf(w.y, c1, fmaf(w.z, c2, w.w))) - h0;
+        sum += d;
+        sq = fmaf(d, d, sq);
+      }
+      const float mean_d = sum * (1.0f / kHidden);
+      const float var = fmaxf(sq * (1.0f / kHidden) - mean_d * mean_d, 0.f);
+      const float rstd = rsqrtf(var + p.eps);
+      const float mean = h0 + mean_d;
+      for (int kc = 0; kc < kHidden / 8; ++kc) {  // 8 features = one 16-byte chunk
+        uint32_t packed[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float y[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int k = kc * 8 + 2 * i + j;
+            const float4 w = s_w1[k];
+            const float2 gb = s_gb[k];
+            const float h = fmaf(w.x, c0, fmaf(w.y, c1, fmaf(w.z, c2, w.w)));
+            y[j] = fmaxf(fmaf((h - mean) * rstd, gb.x, gb.y), 0.f);
+          }
+          const __nv_bfloat162 b = __floats2bfloat162_rn(y[0], y[1]);
+          packed[i] = *reinterpret_cast<const uint32_t*>(&b);
+        }
+        // canonical K-major SWIZZLE_128B: k-block kb, row r at r*128, 16-byte chunk c at position c ^ (r & 7)
+        const int kb = kc >> 3, c = kc & 7;
+        unsigned char* dst = s_a + kb * kAKBlockBytes + r * 128 + ((c ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(a_full);
+
+      // ---- (b) epilogue of every N tile of this M tile
+      for (int nt = 0; nt < n_tiles; ++nt, ++acc_it) {
+        const uint32_t acc = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
+        mbar_wait(t_full + acc, acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+        const size_t row_off = (size_t)m * p.E + (size_t)nt * BLOCK_N;
+#pragma unroll 1
+        for (int cc = 0; cc < BLOCK_N / 32; ++cc) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + cc * 32, v);
+          uint4 tok[4];
+          if (row_ok && p.tokens) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tok[i] = ld_stream_v4(p.tokens + row_off + cc * 32 + i * 8);
+          }
+          tmem_ld_wait();
+          if (row_ok) {
+            const float* bias = p.b2 + nt * BLOCK_N + cc * 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int e = i * 8 + 2 * j;
+                // Linear output in bf16 (fp32 accumulate + bias, one rounding), then the bf16 add of llava_arch.py:515
+                __nv_bfloat162 pe = __floats2bfloat162_rn(__uint_as_float(v[e]) + __ldg(bias + e), __uint_as_float(v[e + 1]) + __ldg(bias + e + 1));
+                if (p.tokens) {
+                  const uint32_t tw = (j == 0) ? tok[i].x : (j == 1) ? tok[i].y : (j == 2) ? tok[i].z : tok[i].w;
+                  pe = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&tw), pe);
+                }
+                o[j] = *reinterpret_cast<const uint32_t*>(&pe);
+              }
+              st_stream_v4(p.out + row_off + cc * 32 + i * 8, make_uint4(o[0], o[1], o[2], o[3]));
+            }
+          }
+        }
+        tcgen05_fence_before();
+        mbar_arrive(t_empty + acc);  // 128 arrivals release the accumulator
+      }
+    }
+  }
+  // ---- teardown
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+template <int BLOCK_N>
+static int launch_mlp(const MlpParams& p, const void* w2, cudaStream_t s) {
+  EncodeTiledFn encode = get_encode_tiled();
+  V3D_REQUIRE(encode != nullptr, V3D_E_CUDA, "v3d_pe_mlp: cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMap map;
+  const cuuint64_t gdim[2] = {(cuuint64_t)kHidden, (cuuint64_t)p.E};        // inner = k, outer = output channel
+  const cuuint64_t gstride[1] = {(cuuint64_t)kHidden * 2};                  // bytes between rows of W2
+  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BLOCK_N};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w2), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  V3D_REQUIRE(r == CUDA_SUCCESS, V3D_E_CUDA, "v3d_pe_mlp: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  using S = MlpSmem<BLOCK_N>;
+  const int smem = S::kTotal + 1024;  // slack for the 1024-byte alignment of the dynamic window
+  auto kern = k_pe_mlp<BLOCK_N>;
+  V3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int grid = m_tiles < num_sms() ? m_tiles : num_sms();
+  kern<<<grid, kMlpThreads, smem, s>>>(map, p);
+  return check_launch("k_pe_mlp");
+}
+
+}  // namespace v3d
+
+using namespace v3d;
+
+extern "C" int v3d_pe_mlp(const float* coords, int M, int E, const float* w1, const float* b1, const float* gamma,
+                          const float* beta, float ln_eps, const void* w2_bf16, const float* b2, const void* tokens_in,
+                          void* out, v3d_stream_t stream) {
+  V3D_REQUIRE(coords && w1 && b1 && gamma && beta && w2_bf16 && b2 && out, V3D_E_ARG, "v3d_pe_mlp: null pointer");
+  V3D_REQUIRE(M >= 0 && E > 0, V3D_E_ARG, "v3d_pe_mlp: bad shape M=%d E=%d", M, E);
+  V3D_REQUIRE(E % 64 == 0, V3D_E_UNSUPPORTED, "v3d_pe_mlp: embedding size %d is not a multiple of 64", E);
+  V3D_REQUIRE(((reinterpret_cast<uintptr_t>(w2_bf16) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(tokens_in)) & 15) == 0,
+              V3D_E_ALIGN, "v3d_pe_mlp: w2/out/tokens must be 16-byte aligned");
+  if (M == 0) return V3D_OK;
+  MlpParams p;
+  p.coords = coords;
+  p.w1 = w1;
+  p.b1 = b1;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.b2 = b2;
+  p.tokens = reinterpret_cast<const __nv_bfloat16*>(tokens_in);
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.M = M;
+  p.E = E;
+  p.eps = ln_eps;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (E % 128 == 0) return launch_mlp<128>(p, w2_bf16, s);
+  return launch_mlp<64>(p, w2_bf16, s);
 }
