@@ -6,7 +6,7 @@ DEV = torch.device('cuda:0')
 res = {}
 for E, M in ((1152, 512 * 729), (3584, 512 * 196)):
     mod = PositionEmbeddingMLP(E).to(DEV).eval()
-    x = (torch.rand((1, M, 3), device=DEV) * 20 - 10)
+    x = (torch.rand((1, M, 3), device=DEV) * 20 - 10).to(torch.bfloat16)  # coordinates arrive in the model dtype
     tok = torch.randn((1, M, E), device=DEV).to(torch.bfloat16)
     with torch.no_grad():
         for _ in range(3): mod(x, add_to=tok)
@@ -18,7 +18,7 @@ for E, M in ((1152, 512 * 729), (3584, 512 * 196)):
         ms = e0.elapsed_time(e1) / 10
         # torch baseline (cuBLAS + elementwise) for context
         mod_bf = PositionEmbeddingMLP(E).to(DEV).to(torch.bfloat16).eval(); mod_bf.load_state_dict(mod.state_dict())
-        xb = x.to(torch.bfloat16)
+        xb = x
         for _ in range(3): tok + mod_bf.mlp(xb)
         torch.cuda.synchronize(); e0.record()
         for _ in range(10): tok + mod_bf.mlp(xb)

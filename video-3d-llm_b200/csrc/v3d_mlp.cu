@@ -26,7 +26,13 @@ static constexpr int kHidden = 512;          // nn.Linear(3, 512) of the referen
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;           // 64 bf16 = 128 bytes = one swizzle atom
 static constexpr int kNumKBlocks = kHidden / kBlockK;  // 8
-static constexpr int kStages = 3;            // W2 ring
+#ifndef V3D_MLP_STAGES
+#define V3D_MLP_STAGES 3
+#endif
+#ifndef V3D_MLP_PREFETCH
+#define V3D_MLP_PREFETCH 0
+#endif
+static constexpr int kStages = V3D_MLP_STAGES;  // W2 ring (16 KB per stage at BLOCK_N = 128)
 static constexpr int kABytes = kBlockM * kHidden * 2;  // 131072
 static constexpr int kAKBlockBytes = kBlockM * kBlockK * 2;  // 16384
 
@@ -111,7 +117,10 @@ struct MlpSmem {
   // barriers: b_full[S], b_empty[S], a_full, tmem_full[2], tmem_empty[2]
   static constexpr int kNumBars = 2 * kStages + 1 + 4;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
-  static constexpr int kTotal = kOffTmem + 16;
+  static constexpr int kOffMom = kOffTmem + 16;   // 16 floats: LayerNorm moment data
+  static constexpr int kOffStage = (kOffMom + 64 + 127) & ~127;  // epilogue staging: 4 warps x 32 rows x BLOCK_N bf16
+  static constexpr int kStageBytesPerWarp = 32 * BLOCK_N * 2;
+  static constexpr int kTotal = kOffStage + 4 * kStageBytesPerWarp;
 };
 
 template <int BLOCK_N>
@@ -135,9 +144,46 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
   constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
 
   // ---- one-time setup
+  // LayerNorm statistics in closed form.  h_k = w_k . c + b_k is affine in the token's coordinates c, so
+  //   mean_k h      = wbar . c + bbar
+  //   var_k  h      = c^T S c + 2 u . c + v,   S = mean (w_k-wbar)(w_k-wbar)^T, u = mean (w_k-wbar)(b_k-bbar), v = mean (b_k-bbar)^2
+  // (all moments centred, so nothing cancels against the mean).  One warp reduces the 512 rows once per CTA;
+  // per token the statistics then cost ~20 flops instead of a 512-long pass.
+  float* s_mom = reinterpret_cast<float*>(smem + S::kOffMom);
+  if (warp == 3) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < kHidden; k += 32) {
+      a[0] += __ldg(p.w1 + 3 * k);
+      a[1] += __ldg(p.w1 + 3 * k + 1);
+      a[2] += __ldg(p.w1 + 3 * k + 2);
+      a[3] += __ldg(p.b1 + k);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      for (int o = 16; o; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+      a[i] *= (1.0f / kHidden);
+    }
+    float m[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // S00 S01 S02 S11 S12 S22 u0 u1 u2 v
+    for (int k = lane; k < kHidden; k += 32) {
+      const float d0 = __ldg(p.w1 + 3 * k) - a[0], d1 = __ldg(p.w1 + 3 * k + 1) - a[1], d2 = __ldg(p.w1 + 3 * k + 2) - a[2];
+      const float db = __ldg(p.b1 + k) - a[3];
+      m[0] += d0 * d0; m[1] += d0 * d1; m[2] += d0 * d2; m[3] += d1 * d1; m[4] += d1 * d2; m[5] += d2 * d2;
+      m[6] += d0 * db; m[7] += d1 * db; m[8] += d2 * db; m[9] += db * db;
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      for (int o = 16; o; o >>= 1) m[i] += __shfl_xor_sync(0xffffffffu, m[i], o);
+      if (lane == 0) s_mom[4 + i] = m[i] * (1.0f / kHidden);
+    }
+    if (lane == 0) {
+      s_mom[0] = a[0]; s_mom[1] = a[1]; s_mom[2] = a[2]; s_mom[3] = a[3];
+    }
+  }
   for (int k = threadIdx.x; k < kHidden; k += kMlpThreads) {
-    s_w1[k] = make_float4(__ldg(p.w1 + 3 * k), __ldg(p.w1 + 3 * k + 1), __ldg(p.w1 + 3 * k + 2), __ldg(p.b1 + k));
-    s_gb[k] = make_float2(__ldg(p.gamma + k), __ldg(p.beta + k));
+    const float g = __ldg(p.gamma + k);
+    // gamma folded into the first Linear: y_k = relu(rstd * (gw_k . c + gb_k) + (beta_k - rstd * mean * gamma_k))
+    s_w1[k] = make_float4(g * __ldg(p.w1 + 3 * k), g * __ldg(p.w1 + 3 * k + 1), g * __ldg(p.w1 + 3 * k + 2), g * __ldg(p.b1 + k));
+    s_gb[k] = make_float2(g, __ldg(p.beta + k));
   }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&w2_map) : "memory");
@@ -213,6 +259,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
       const int m = mt * kBlockM + r;
       const bool row_ok = m < p.M;
+      // L2 prefetch of the token rows by the TMA unit, one M tile ahead of their use in the epilogue (the very
+      // first tile is requested here, before its A operand is built)
+      if (V3D_MLP_PREFETCH && threadIdx.x == 128 && p.tokens != nullptr) {
+        for (int t = (mt == (int)blockIdx.x ? mt : mt + (int)gridDim.x); t <= mt + (int)gridDim.x && t < m_tiles; t += gridDim.x) {
+          const size_t rows = (size_t)min(kBlockM, p.M - t * kBlockM);
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(p.tokens + (size_t)t * kBlockM * p.E);
+          const size_t bytes = rows * (size_t)p.E * 2;
+          for (size_t o = 0; o < bytes; o += 32768) tma_prefetch_l2(src + o, (uint32_t)min((size_t)32768, bytes - o));
+        }
+      }
       // ---- (a) hidden activations of this token: Linear(3,512) -> LayerNorm -> ReLU -> bf16
       float c0 = 0.f, c1 = 0.f, c2 = 0.f;
       if (row_ok) {
@@ -220,24 +276,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
         c1 = __ldg(p.coords + 3 * (size_t)m + 1);
         c2 = __ldg(p.coords + 3 * (size_t)m + 2);
       }
-      // LayerNorm statistics, shifted by the first element for stability (biased variance, as torch)
-      float h0;
-      {
-        const float4 w = s_w1[0];
-        h0 = fmaf(w.x, c0, fmaf(w.y, c1, fmaf(w.z, c2, w.w)));
-      }
-      float sum = 0.f, sq = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < kHidden; ++k) {
-        const float4 w = s_w1[k];
-        const float d = fmaf(w.x, c0, fmaf(w.y, c1, fmaf(w.z, c2, w.w))) - h0;
-        sum += d;
-        sq = fmaf(d, d, sq);
-      }
-      const float mean_d = sum * (1.0f / kHidden);
-      const float var = fmaxf(sq * (1.0f / kHidden) - mean_d * mean_d, 0.f);
+      // LayerNorm statistics of this token in closed form (biased variance, as torch)
+      const float mean = fmaf(s_mom[0], c0, fmaf(s_mom[1], c1, fmaf(s_mom[2], c2, s_mom[3])));
+      float var = s_mom[4] * c0 * c0 + s_mom[7] * c1 * c1 + s_mom[9] * c2 * c2 +
+                  2.0f * (s_mom[5] * c0 * c1 + s_mom[6] * c0 * c2 + s_mom[8] * c1 * c2) +
+                  2.0f * (s_mom[10] * c0 + s_mom[11] * c1 + s_mom[12] * c2) + s_mom[13];
+      var = fmaxf(var, 0.f);
       const float rstd = rsqrtf(var + p.eps);
-      const float mean = h0 + mean_d;
+      const float nmr = -mean * rstd;
+#pragma unroll 2
       for (int kc = 0; kc < kHidden / 8; ++kc) {  // 8 features = one 16-byte chunk
         uint32_t packed[4];
 #pragma unroll
@@ -246,10 +293,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const int k = kc * 8 + 2 * i + j;
-            const float4 w = s_w1[k];
-            const float2 gb = s_gb[k];
-            const float h = fmaf(w.x, c0, fmaf(w.y, c1, fmaf(w.z, c2, w.w)));
-            y[j] = fmaxf(fmaf((h - mean) * rstd, gb.x, gb.y), 0.f);
+            const float4 w = s_w1[k];   // gamma-scaled first layer
+            const float2 gb = s_gb[k];  // {gamma, beta}
+            const float t = fmaf(w.x, c0, fmaf(w.y, c1, fmaf(w.z, c2, w.w)));
+            y[j] = fmaxf(fmaf(rstd, t, fmaf(nmr, gb.x, gb.y)), 0.f);
           }
           const __nv_bfloat162 b = __floats2bfloat162_rn(y[0], y[1]);
           packed[i] = *reinterpret_cast<const uint32_t*>(&b);
@@ -262,45 +309,88 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(a_full);
 
-      // ---- (b) epilogue of every N tile of this M tile
-      for (int nt = 0; nt < n_tiles; ++nt, ++acc_it) {
+      // ---- (b) epilogue of every N tile of this M tile.
+      // Global traffic is warp-coalesced: a warp instruction moves 512 contiguous bytes (2 rows x 256 B at
+      // BLOCK_N = 128) of the warp's own 32 rows, and a per-warp staging tile in shared memory (XOR-swizzled,
+      // conflict-free both ways) turns that into the row-per-thread order of the TMEM accumulator and back.
+      // The token segment of the NEXT N tile is requested before the current accumulator is touched, so
+      // its latency hides behind this tile's TMEM loads, math and stores.
+      constexpr int kChunks = BLOCK_N / 8;            // 16-byte chunks per row per N tile
+      constexpr int kRowsPerInst = 32 / kChunks;      // rows covered by one warp instruction
+      constexpr int kInst = 32 / kRowsPerInst;        // warp instructions per N tile (= kChunks)
+      unsigned char* stage = smem + S::kOffStage + q * S::kStageBytesPerWarp;
+      const int my_chunk = lane % kChunks, my_rsub = lane / kChunks;
+      const int row0 = mt * kBlockM + q * 32;        // first global row of this warp
+      const bool add = p.tokens != nullptr;
+      uint4 tok_a[kInst], tok_b[kInst];
+      auto load_tokens = [&](uint4 (&t)[kInst], int nt) {
+        if (add && nt < n_tiles) {
+#pragma unroll
+          for (int i = 0; i < kInst; ++i) {
+            const int gr = row0 + i * kRowsPerInst + my_rsub;
+            if (gr < p.M) t[i] = ld_stream_v4(p.tokens + (size_t)gr * p.E + (size_t)nt * BLOCK_N + my_chunk * 8);
+          }
+        }
+      };
+      auto stage_addr = [&](int row, int chunk) -> unsigned char* {
+        return stage + row * (BLOCK_N * 2) + ((chunk ^ (row & (kChunks - 1))) << 4);
+      };
+      auto epilogue_tile = [&](const uint4 (&t)[kInst], int nt) {
         const uint32_t acc = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
+        if (add) {
+#pragma unroll
+          for (int i = 0; i < kInst; ++i) *reinterpret_cast<uint4*>(stage_addr(i * kRowsPerInst + my_rsub, my_chunk)) = t[i];
+          __syncwarp();
+        }
         mbar_wait(t_full + acc, acc_phase);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
-        const size_t row_off = (size_t)m * p.E + (size_t)nt * BLOCK_N;
-#pragma unroll 1
+#pragma unroll
         for (int cc = 0; cc < BLOCK_N / 32; ++cc) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + cc * 32, v);
-          uint4 tok[4];
-          if (row_ok && p.tokens) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) tok[i] = ld_stream_v4(p.tokens + row_off + cc * 32 + i * 8);
-          }
           tmem_ld_wait();
-          if (row_ok) {
-            const float* bias = p.b2 + nt * BLOCK_N + cc * 32;
+          const float* bias = p.b2 + nt * BLOCK_N + cc * 32;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint32_t o[4];
+          for (int i = 0; i < 4; ++i) {
+            uint32_t o[4];
+            uint4* slot = reinterpret_cast<uint4*>(stage_addr(lane, cc * 4 + i));
+            uint4 tk = make_uint4(0u, 0u, 0u, 0u);
+            if (add) tk = *slot;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int e = i * 8 + 2 * j;
-                // Linear output in bf16 (fp32 accumulate + bias, one rounding), then the bf16 add of llava_arch.py:515
-                __nv_bfloat162 pe = __floats2bfloat162_rn(__uint_as_float(v[e]) + __ldg(bias + e), __uint_as_float(v[e + 1]) + __ldg(bias + e + 1));
-                if (p.tokens) {
-                  const uint32_t tw = (j == 0) ? tok[i].x : (j == 1) ? tok[i].y : (j == 2) ? tok[i].z : tok[i].w;
-                  pe = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&tw), pe);
-                }
-                o[j] = *reinterpret_cast<const uint32_t*>(&pe);
+            for (int j = 0; j < 4; ++j) {
+              const int e = i * 8 + 2 * j;
+              // Linear output in bf16 (fp32 accumulate + bias, one rounding), then the bf16 add of llava_arch.py:515
+              __nv_bfloat162 pe = __floats2bfloat162_rn(__uint_as_float(v[e]) + __ldg(bias + e), __uint_as_float(v[e + 1]) + __ldg(bias + e + 1));
+              if (add) {
+                const uint32_t tw = (j == 0) ? tk.x : (j == 1) ? tk.y : (j == 2) ? tk.z : tk.w;
+                pe = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&tw), pe);
               }
-              st_stream_v4(p.out + row_off + cc * 32 + i * 8, make_uint4(o[0], o[1], o[2], o[3]));
+              o[j] = *reinterpret_cast<const uint32_t*>(&pe);
             }
+            *slot = make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
         tcgen05_fence_before();
         mbar_arrive(t_empty + acc);  // 128 arrivals release the accumulator
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < kInst; ++i) {
+          const int gr = row0 + i * kRowsPerInst + my_rsub;
+          const uint4 val = *reinterpret_cast<const uint4*>(stage_addr(i * kRowsPerInst + my_rsub, my_chunk));
+          if (gr < p.M) st_stream_v4(p.out + (size_t)gr * p.E + (size_t)nt * BLOCK_N + my_chunk * 8, val);
+        }
+        __syncwarp();
+        ++acc_it;
+      };
+      load_tokens(tok_a, 0);
+      for (int nt = 0; nt < n_tiles; nt += 2) {
+        load_tokens(tok_b, nt + 1);
+        epilogue_tile(tok_a, nt);
+        if (nt + 1 < n_tiles) {
+          load_tokens(tok_a, nt + 2);
+          epilogue_tile(tok_b, nt + 1);
+        }
       }
     }
   }
