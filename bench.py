@@ -256,6 +256,46 @@ def mc_leg(rank: int, world: int, dev, steps: int, warmup: int):
     }
 
 
+def mlp_leg(dev, steps: int):
+    """Secondary: the learned-projection PE variant (PositionEmbeddingMLP) on tcgen05 at the config-2 token count:
+    M = 16*32*729 tokens, K = 512, N = 1152, fused bias + token add.  Kernel-only time through the C ABI."""
+    from video_3d_llm_b200 import cabi
+    from video_3d_llm_b200.position_encoding import PositionEmbeddingMLP
+
+    lib = cabi.load()
+    M, E = SCENES * FRAMES * GRID * GRID, EMB
+    torch.manual_seed(0)
+    mod = PositionEmbeddingMLP(E).to(dev).eval()
+    x = torch.rand((M, 3), device=dev) * 20 - 10
+    tok = torch.randn((M, E), device=dev).to(torch.bfloat16)
+    out = torch.empty_like(tok)
+    l1, ln, l2 = mod.mlp[0], mod.mlp[1], mod.mlp[3]
+    w2 = l2.weight.detach().to(torch.bfloat16).contiguous()
+    a = (x.data_ptr(), M, E, l1.weight.data_ptr(), l1.bias.data_ptr(), ln.weight.data_ptr(), ln.bias.data_ptr(), float(ln.eps),
+         w2.data_ptr(), l2.bias.data_ptr(), tok.data_ptr(), out.data_ptr(), cabi.stream_ptr(dev))
+    for _ in range(3):
+        cabi.check(lib.v3d_pe_mlp(*a), "v3d_pe_mlp")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        lib.v3d_pe_mlp(*a)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    flops = 2.0 * M * 512 * E
+    byts = 2.0 * M * E * 2 + M * 12 + E * 512 * 2
+    peak_tf = 1599.5
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak_tf = float(json.load(f)["bf16_tflops"])
+    except OSError:
+        pass
+    return {"kernel": "k_pe_mlp (tcgen05.mma cta_group::1 M128 N128 K16, TMEM accumulators)", "tokens": M, "K": 512, "N": E,
+            "ms": ms, "tflops": flops / ms / 1e9, "frac_of_measured_bf16_peak": flops / ms / 1e9 / peak_tf,
+            "hbm_gbs": byts / ms / 1e6, "frames_per_s": SCENES * FRAMES / (ms / 1e3)}
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -333,6 +373,7 @@ def run_ours(args):
     d2h = h_coords.numel() * 4
 
     mc = mc_leg(rank, world, dev, steps=max(2, min(K, 5)), warmup=1)
+    mlp = mlp_leg(dev, steps=5) if rank == 0 else None
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -356,6 +397,7 @@ def run_ours(args):
             "gpu_launches": K,
             "clocks": clk,
             "mc": mc,
+            "mlp_pe": mlp,
         }
         if world == 1 and not args.no_cpu:
             r = cpu_reference_leg(steps=3, warmup=1)
