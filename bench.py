@@ -305,6 +305,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout for the one JSON line: NCCL's banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from video_3d_llm_b200 import cabi
     from video_3d_llm_b200.frontend import FrontEnd
@@ -332,7 +334,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    # the timed region lasts milliseconds; keep the identical launches going for ~1 s (untimed) so that the
+    # 200 ms nvidia-smi sampler sees clocks and throttle reasons under this load
+    t_soak = time.perf_counter()
+    while time.perf_counter() - t_soak < 1.0:
+        for _ in range(50):
+            fe(depth, poses, intr, tokens=tokens, out=out)
+        torch.cuda.synchronize()
     clk = clocks.stop()
+    clk["window"] = "timed region + 1 s continuation of the same launches"
     ms_local = e0.elapsed_time(e1)
     t = torch.tensor([ms_local], device=dev)
     if world > 1:
@@ -372,6 +382,27 @@ def run_ours(args):
     h2d = h_depth.numel() * h_depth.element_size() + h_poses.numel() * 4 + h_intr.numel() * 4
     d2h = h_coords.numel() * 4
 
+    # secondary: the reference's default recipe geometry (27-pixel windows -> 14x14 grid, E = 3584)
+    recipe = None
+    if rank == 0:
+        fe2 = FrontEnd(device=dev, patch_size=27, embedding_size=3584)
+        tok2 = torch.randn((n_frames, 196, 3584), device=dev, dtype=torch.float32).to(torch.bfloat16)
+        out2 = torch.empty_like(tok2)
+        for _ in range(3):
+            fe2(depth, poses, intr, tokens=tok2, out=out2)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(10):
+            fe2(depth, poses, intr, tokens=tok2, out=out2)
+        r1.record()
+        torch.cuda.synchronize()
+        rms = r0.elapsed_time(r1) / 10
+        rbytes = (BYTES_IN_PER_FRAME + 2 * 196 * 3584 * 2) * n_frames
+        recipe = {"workload": "same depth batch, patch 27 -> 14x14 grid, E=3584, fused add (train_multi.sh:82-87 defaults)",
+                  "ms": rms, "frames_per_s": n_frames / (rms / 1e3), "hbm_gbs": rbytes / rms / 1e6,
+                  "frac_of_measured_hbm_peak": rbytes / rms / 1e6 / measured_peaks()[0]}
+        del tok2, out2
     mc = mc_leg(rank, world, dev, steps=max(2, min(K, 5)), warmup=1)
     mlp = mlp_leg(dev, steps=5) if rank == 0 else None
 
@@ -396,6 +427,7 @@ def run_ours(args):
                     "device by the vision tower and stay resident; per-token voxel coordinates read back"},
             "gpu_launches": K,
             "clocks": clk,
+            "default_recipe_geometry": recipe,
             "mc": mc,
             "mlp_pe": mlp,
         }
