@@ -522,3 +522,81 @@ def test_lazy_handle_through_the_reference_call_structure(dataset, D, monkeypatc
     # slicing like the object-proposal code (llava_arch.py:360-373) materialises on demand
     sl = ml["world_coords"].to(DEV)[0][:, :378, :378, :]
     assert torch.equal(sl, we[0][:, :378, :378, :])
+
+
+# ---------------------------------------------------------------------------------------------
+# the offline scripts: mesh universe and the MC command line (same files in, same JSON out)
+# ---------------------------------------------------------------------------------------------
+def test_mesh_to_voxels_matches_convert_pcd_to_voxel():
+    """convert_pcd_to_voxel.py:69-82: unique round(xyz / 0.1) of the mesh vertices (CPU IEEE division)."""
+    rng = np.random.default_rng(3)
+    xyz = rng.uniform(-6, 6, (200000, 3)).astype(np.float32)
+    xyz[:5] = [[0.05, 0.15, -0.25], [0.0, 0.0, 0.0], [-0.05, 2.25, 1.35], [5.95, -5.95, 0.049999], [1e-9, -1e-9, 3.0]]
+    got = sorted(mc_sampling.mesh_to_voxels(torch.from_numpy(xyz).to(DEV), 0.1))
+    ref = sorted(set(map(tuple, np.rint(xyz / np.float32(0.1)).astype(np.int32).tolist())))
+    assert got == ref
+
+
+def test_mc_command_line_reproduces_the_reference_json(dataset, D, monkeypatch, tmp_path):
+    """`python -m video_3d_llm_b200.mc_sampling` on the on-disk fixture writes what the reference's
+    max_coverage_sampling.main wrote (tests/golden/dataset.json), scene by scene under random.seed(scene seed)."""
+    import types
+
+    monkeypatch.chdir(dataset)
+    gold = {s["video_id"]: s for s in D["select_frames"]}
+    for name, meta in D["scenes"].items():
+        vd = tmp_path / f"only_{name}"
+        (vd / name).mkdir(parents=True)
+        args = types.SimpleNamespace(voxel_size=0.1, video_dir=str(vd), output_file=str(tmp_path / f"sel_{name}.json"),
+                                     seed=meta["seed"], batch_scenes=4)
+        out = mc_sampling.main(args)
+        with open(args.output_file) as f:
+            assert json.load(f) == out
+        assert len(out) == 1
+        g = gold[f"scannet/{name}"]
+        assert out[0]["video_id"] == g["video_id"]
+        assert out[0]["frame_files"] == g["frame_files"]
+        assert out[0]["voxel_nums"] == g["voxel_nums"]
+        assert out[0]["num_all_voxels"] == g["num_all_voxels"] and out[0]["num_select_voxels"] == g["num_select_voxels"]
+
+
+# ---------------------------------------------------------------------------------------------
+# empty / degenerate inputs
+# ---------------------------------------------------------------------------------------------
+def test_empty_and_degenerate_inputs():
+    z = torch.zeros((0, 480, 640), dtype=torch.int16, device=DEV)
+    m = torch.zeros((0, 4, 4), device=DEV)
+    assert VU.unproject(m, m, z).shape == (0, 480, 640, 3)
+    fe = FrontEnd(device=DEV, patch_size=14, embedding_size=1152)
+    assert fe(z, m, m).shape == (0, 729, 1152)
+    assert PositionEmbeddingSine3D(96)(torch.zeros((0, 5, 3), device=DEV)).shape == (0, 5, 96)
+    assert C.discrete_coords(torch.zeros((0, 3), device=DEV)).shape == (0, 3)
+    # a frame of all-invalid depth: every pixel unprojects to the camera centre, PE rows are all equal
+    sc = synthetic.make_scene(2, 1, n_total=5, device="cpu")
+    d0 = torch.zeros_like(sc.depth).to(DEV)
+    out, pooled, pe_coords = fe(d0, sc.poses.to(DEV), sc.intrinsics.to(DEV), want_coords=True)
+    ref = O.frontend(np.zeros((1, 480, 640), np.uint16), sc.poses.numpy(), sc.intrinsics.numpy(), patch_size=14, embedding_size=1152)
+    np.testing.assert_array_equal(pooled.cpu().numpy(), ref["pooled"])
+    assert torch.equal(out[0, 0], out[0, -1])
+    # saturated depth (65535 mm) and a frame far outside the discretisation range clamp to the table's last row
+    d1 = torch.full_like(sc.depth, -1).to(DEV)  # 0xFFFF
+    out1, pooled1, pc1 = fe(d1, sc.poses.to(DEV), sc.intrinsics.to(DEV), want_coords=True)
+    ref1 = O.frontend(np.full((1, 480, 640), 65535, np.uint16), sc.poses.numpy(), sc.intrinsics.numpy(), patch_size=14, embedding_size=1152)
+    np.testing.assert_array_equal(pooled1.cpu().numpy(), ref1["pooled"])
+    np.testing.assert_array_equal(pc1.cpu().numpy().reshape(1, 729, 3), ref1["pe_coords"])
+    assert_bf16_close(bf16_bits(out1), ref1["pe_bf16"], max_frac=5e-4)
+
+
+def test_nan_pose_propagates_like_the_reference():
+    sc = synthetic.make_scene(6, 2, n_total=8, device="cpu")
+    p = sc.poses.clone()
+    p[1, 1, 3] = float("nan")
+    fe = FrontEnd(device=DEV, patch_size=27, embedding_size=3584)
+    out, pooled, pe_coords = fe(sc.depth.to(DEV), p.to(DEV), sc.intrinsics.to(DEV), want_coords=True)
+    ref = O.frontend(sc.depth_u16(), p.numpy(), sc.intrinsics.numpy(), patch_size=27, embedding_size=3584)
+    np.testing.assert_array_equal(pooled.cpu().numpy(), ref["pooled"])  # NaN in y of frame 1, everything else intact
+    np.testing.assert_array_equal(pe_coords.cpu().numpy().reshape(2, 196, 3), ref["pe_coords"])
+    got = out.float().cpu().numpy()
+    exp = O.bf16_bits_to_f32(ref["pe_bf16"])
+    assert np.array_equal(np.isnan(got), np.isnan(exp))
+    assert np.isnan(got[1, :, 1194:2388]).all() and not np.isnan(got[0]).any()

@@ -648,7 +648,7 @@ __host__ __device__ inline size_t fused_smem_bytes(const FusedParams& p, bool st
   const size_t n_slots = (size_t)3 * p.n_points;
   size_t b = 16;                                              // mbarrier
   if (stage_depth) b += (size_t)p.patch * p.span;             // depth rows
-  b += (size_t)2 * 3 * kPlane * sizeof(float);                // double-buffered xyz row
+  b += (size_t)4 * 3 * kPlane * sizeof(float);                // xyz rows: 2 buffers x 2 rows
   b += (size_t)p.patch * 2 * sizeof(float2);                  // {row - cy, fast flag} and source row per patch row
   b += (size_t)p.grid * (n_slots * sizeof(float) + (n_slots + 1) * sizeof(int) + sizeof(int));  // PE coords, row offsets, flags
   b = (b + 7) & ~(size_t)7;
@@ -720,40 +720,53 @@ __device__ __forceinline__ void pool_rows_fast(const Camera& cam, const Divisor&
                                                const float um[2], const uint32_t d_addr[2], const uint32_t w_addr[2],
                                                const float2* s_vm, bool chain, const float* chain_src, int pool_mode,
                                                const Clamp& clamp, ChainAcc& c) {
+  // two resampled rows per barrier: the row buffers hold 2 x 2 rows, halving the number of block-wide
+  // synchronisations (the chain threads add row dy, then row dy+1, so the summation order is unchanged)
   uint32_t row_off = 0;
-  for (int dy = 0; dy < P; ++dy, row_off += span) {
-    const uint32_t bsel = (dy & 1) ? (uint32_t)(3 * kPlane * 4) : 0u;
-    const float vm = s_vm[dy].x;
+  for (int dy = 0; dy < P; dy += 2) {
+    const uint32_t bsel = ((dy >> 1) & 1) ? (uint32_t)(6 * kPlane * 4) : 0u;
+    const int n_rows = (dy + 1 < P) ? 2 : 1;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (k < n_px) {
-        const uint32_t raw = lds_u16(d_addr[k] + row_off);
-        const float d = (float)raw;
-        const bool nz = raw != 0;
-        float q0 = __fmul_rn(d, ds.r);
-        float q1 = __fmaf_rn(ds.r, __fmaf_rn(-ds.b, q0, d), q0);
-        const float cz = nz ? q1 : q0;
-        const float ax = __fmul_rn(um[k], cz);
-        q0 = __fmul_rn(ax, cam.fx.r);
-        q1 = __fmaf_rn(cam.fx.r, __fmaf_rn(-cam.fx.b, q0, ax), q0);
-        const float cx_ = nz ? q1 : q0;
-        const float ay = __fmul_rn(vm, cz);
-        q0 = __fmul_rn(ay, cam.fy.r);
-        q1 = __fmaf_rn(cam.fy.r, __fmaf_rn(-cam.fy.b, q0, ay), q0);
-        const float cy_ = nz ? q1 : q0;
-        float x = __fadd_rn(__fmaf_rn(cam.P[2], cz, __fmaf_rn(cam.P[1], cy_, __fmul_rn(cam.P[0], cx_))), cam.P[3]);
-        float y = __fadd_rn(__fmaf_rn(cam.P[6], cz, __fmaf_rn(cam.P[5], cy_, __fmul_rn(cam.P[4], cx_))), cam.P[7]);
-        float z = __fadd_rn(__fmaf_rn(cam.P[10], cz, __fmaf_rn(cam.P[9], cy_, __fmul_rn(cam.P[8], cx_))), cam.P[11]);
-        if (clamp.on) {
-          x = apply_clamp(clamp, x, 0);
-          y = apply_clamp(clamp, y, 1);
-          z = apply_clamp(clamp, z, 2);
+    for (int rr = 0; rr < 2; ++rr) {
+      if (rr < n_rows) {
+        const float vm = s_vm[dy + rr].x;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (k < n_px) {
+            const uint32_t raw = lds_u16(d_addr[k] + row_off);
+            const float d = (float)raw;
+            const bool nz = raw != 0;
+            float q0 = __fmul_rn(d, ds.r);
+            float q1 = __fmaf_rn(ds.r, __fmaf_rn(-ds.b, q0, d), q0);
+            const float cz = nz ? q1 : q0;
+            const float ax = __fmul_rn(um[k], cz);
+            q0 = __fmul_rn(ax, cam.fx.r);
+            q1 = __fmaf_rn(cam.fx.r, __fmaf_rn(-cam.fx.b, q0, ax), q0);
+            const float cx_ = nz ? q1 : q0;
+            const float ay = __fmul_rn(vm, cz);
+            q0 = __fmul_rn(ay, cam.fy.r);
+            q1 = __fmaf_rn(cam.fy.r, __fmaf_rn(-cam.fy.b, q0, ay), q0);
+            const float cy_ = nz ? q1 : q0;
+            float x = __fadd_rn(__fmaf_rn(cam.P[2], cz, __fmaf_rn(cam.P[1], cy_, __fmul_rn(cam.P[0], cx_))), cam.P[3]);
+            float y = __fadd_rn(__fmaf_rn(cam.P[6], cz, __fmaf_rn(cam.P[5], cy_, __fmul_rn(cam.P[4], cx_))), cam.P[7]);
+            float z = __fadd_rn(__fmaf_rn(cam.P[10], cz, __fmaf_rn(cam.P[9], cy_, __fmul_rn(cam.P[8], cx_))), cam.P[11]);
+            if (clamp.on) {
+              x = apply_clamp(clamp, x, 0);
+              y = apply_clamp(clamp, y, 1);
+              z = apply_clamp(clamp, z, 2);
+            }
+            sts_xyz(w_addr[k] + bsel + (uint32_t)(rr * 3 * kPlane * 4), x, y, z);
+          }
         }
-        sts_xyz(w_addr[k] + bsel, x, y, z);
+        row_off += span;
       }
     }
     __syncthreads();
-    if (chain) chain_row(c, chain_src + ((dy & 1) ? 3 * kPlane : 0), P, pool_mode);
+    if (chain) {
+      const float* src = chain_src + (((dy >> 1) & 1) ? 6 * kPlane : 0);
+      chain_row(c, src, P, pool_mode);
+      if (n_rows == 2) chain_row(c, src + 3 * kPlane, P, pool_mode);
+    }
   }
 }
 
@@ -769,7 +782,7 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   unsigned char* s_depth = smem_raw + 16;
   float* s_row = reinterpret_cast<float*>(s_depth + ((FROM_DEPTH && USE_TMA) ? (size_t)P * p.span : 0));
-  float2* s_vm = reinterpret_cast<float2*>(s_row + 2 * 3 * kPlane);  // {row - cy, unused}
+  float2* s_vm = reinterpret_cast<float2*>(s_row + 4 * 3 * kPlane);  // {row - cy, unused}
   int* s_srow = reinterpret_cast<int*>(s_vm + P);
   float* s_pts = reinterpret_cast<float*>(s_srow + 2 * P);
   int* s_off = reinterpret_cast<int*>(s_pts + G * n_slots);
@@ -1223,10 +1236,10 @@ static int launch_fused_dt(int depth_dtype, bool use_tma, const FusedParams& p, 
     switch (depth_dtype) {
       case V3D_DEPTH_U16:
         return use_tma ? launch_fused<V3D_DEPTH_U16, true, true, OutT>(p, s) : launch_fused<V3D_DEPTH_U16, true, false, OutT>(p, s);
-      case V3D_DEPTH_I32:
-        return use_tma ? launch_fused<V3D_DEPTH_I32, true, true, OutT>(p, s) : launch_fused<V3D_DEPTH_I32, true, false, OutT>(p, s);
-      case V3D_DEPTH_F32:
-        return use_tma ? launch_fused<V3D_DEPTH_F32, true, true, OutT>(p, s) : launch_fused<V3D_DEPTH_F32, true, false, OutT>(p, s);
+      // int32 / float32 depth (the reference's in-memory dtypes) are API-compatibility inputs: they take the
+      // plain-load variant, which keeps the number of kernel instantiations (and the build time) down
+      case V3D_DEPTH_I32: return launch_fused<V3D_DEPTH_I32, true, false, OutT>(p, s);
+      case V3D_DEPTH_F32: return launch_fused<V3D_DEPTH_F32, true, false, OutT>(p, s);
       default: set_error("unknown depth dtype %d", depth_dtype); return V3D_E_ARG;
     }
   }
