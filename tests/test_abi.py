@@ -41,6 +41,7 @@ def test_version_and_pure_host_helpers():
 
 def test_argument_errors_are_reported_without_a_gpu():
     lib = cabi.load()
+    assert lib.v3d_discretize(None, 0, None, None, 0, 0.1, 0, None, None) == cabi.V3D_OK  # empty input: nothing to do
     rc = lib.v3d_discretize(None, 4, None, None, 0, 0.1, 0, None, None)
     assert rc == cabi.V3D_E_ARG and b"null pointer" in lib.v3d_last_error()
     with pytest.raises(ValueError):

@@ -1113,6 +1113,7 @@ int v3d_pool_points(int pool_mode) {
 int v3d_unproject(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
                   float depth_scale, const int32_t* row_map, const int32_t* col_map, int out_h, int out_w,
                   const float* clamp_lo_hi_host, float* world_out, v3d_stream_t stream) {
+  if (V == 0) return V3D_OK;  // empty batch: nothing to read or write (pointers may be null)
   V3D_REQUIRE(depth && poses && intr && world_out, V3D_E_ARG, "v3d_unproject: null pointer");
   V3D_REQUIRE(V >= 0 && H > 0 && W > 0, V3D_E_ARG, "v3d_unproject: bad shape V=%d H=%d W=%d", V, H, W);
   V3D_REQUIRE((row_map == nullptr) == (col_map == nullptr), V3D_E_ARG, "v3d_unproject: give both maps or none");
@@ -1160,6 +1161,7 @@ int v3d_boundary(const void* depth, int depth_dtype, const float* poses, const f
 
 int v3d_discretize(const float* coords, size_t n_points, const float* min_xyz_host, const float* max_xyz_host,
                    int has_range, float voxel_size, int div_mode, float* out, v3d_stream_t stream) {
+  if (n_points == 0) return V3D_OK;
   V3D_REQUIRE(coords && out, V3D_E_ARG, "v3d_discretize: null pointer");
   V3D_REQUIRE(!has_range || (min_xyz_host && max_xyz_host), V3D_E_ARG, "v3d_discretize: range requested but not given");
   V3D_REQUIRE(voxel_size > 0.f, V3D_E_ARG, "v3d_discretize: voxel_size must be positive");
@@ -1194,6 +1196,7 @@ int v3d_pe_table_build(const float* dim_t, int E, int n_points, int rows, int dt
 
 int v3d_pe_sine3d(const float* coords, size_t n_tokens, int n_points, int E, const float* dim_t, const void* table,
                   int rows, int dtype, const void* tokens_in, void* out, v3d_stream_t stream) {
+  if (n_tokens == 0) return V3D_OK;
   V3D_REQUIRE(coords && dim_t && out, V3D_E_ARG, "v3d_pe_sine3d: null pointer");
   PeGeom g;
   int rc = make_pe_geom(E, n_points, table ? rows : 0, &g);
@@ -1259,6 +1262,7 @@ static int check_pool(int pool_mode, int patch, int grid, int* n_points) {
 extern "C" {
 
 int v3d_pool_coords(const float* coords, int V, int S, int patch, int grid, int pool_mode, float* out, v3d_stream_t stream) {
+  if (V == 0) return V3D_OK;
   V3D_REQUIRE(coords && out, V3D_E_ARG, "v3d_pool_coords: null pointer");
   V3D_REQUIRE(V >= 0 && S > 0, V3D_E_ARG, "v3d_pool_coords: bad shape");
   int n_points;
@@ -1284,6 +1288,7 @@ int v3d_pool_coords(const float* coords, int V, int S, int patch, int grid, int 
 
 int v3d_frontend_pe(const v3d_frontend_desc* d, v3d_stream_t stream) {
   V3D_REQUIRE(d, V3D_E_ARG, "v3d_frontend_pe: null descriptor");
+  if (d->n_frames == 0) return V3D_OK;
   V3D_REQUIRE(d->depth && d->poses && d->intr && d->row_map && d->col_map, V3D_E_ARG, "v3d_frontend_pe: null input pointer");
   V3D_REQUIRE(d->n_frames >= 0 && d->H > 0 && d->W > 0, V3D_E_ARG, "v3d_frontend_pe: bad shape");
   int n_points;
