@@ -9,12 +9,14 @@
 // One persistent CTA per SM, 256 threads, warp-specialised:
 //   warp 0    TMA producer: W2 tiles (BLOCK_N rows x 64 k, 128-byte swizzle) through a ring of mbarriers
 //   warp 1    MMA issuer  : tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16; owns TMEM alloc
-//   warps 4-7 (a) build the A operand of an M tile (128 tokens x 512 hidden, bf16) straight into the
-//             canonical K-major SWIZZLE_128B layout the MMA reads: Linear(3,512) + LayerNorm + ReLU
-//             per token (one thread per token row = one TMEM lane);
+//   warps 4-7 (a) build the A operand of an M tile (128 tokens x 512 hidden, bf16): Linear(3,512) + LayerNorm
+//             + ReLU per token, one thread per token row = one TMEM lane, written with tcgen05.st straight
+//             into TENSOR MEMORY (256 columns: two bf16 per 32-bit cell), from where the MMA reads it;
 //             (b) epilogue: tcgen05.ld the fp32 accumulator, + bias, round to bf16, + tokens, store.
-// Accumulators are double buffered in TMEM (2 x BLOCK_N columns), so the MMAs of N tile i+1 overlap the
-// epilogue of N tile i.  A (128 KB) stays resident in shared memory for all N tiles of its M tile.
+// TMEM map (512 columns): [0, 2*BLOCK_N) double-buffered fp32 accumulators (the MMAs of N tile i+1 overlap
+// the epilogue of N tile i), [256, 512) the A operand, resident for all N tiles of its M tile.  Keeping A out
+// of shared memory leaves room for a deep W2 ring: with A in smem (128 KB) only 3 x 16 KB of W2 fitted in
+// flight and the tensor pipe starved on W2 tiles (24 % active, profiles/r1i_*).
 #include <cuda.h>
 
 #include "v3d_common.cuh"
@@ -27,14 +29,13 @@ static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;           // 64 bf16 = 128 bytes = one swizzle atom
 static constexpr int kNumKBlocks = kHidden / kBlockK;  // 8
 #ifndef V3D_MLP_STAGES
-#define V3D_MLP_STAGES 3
+#define V3D_MLP_STAGES 8
 #endif
 #ifndef V3D_MLP_PREFETCH
 #define V3D_MLP_PREFETCH 0
 #endif
 static constexpr int kStages = V3D_MLP_STAGES;  // W2 ring (16 KB per stage at BLOCK_N = 128)
-static constexpr int kABytes = kBlockM * kHidden * 2;  // 131072
-static constexpr int kAKBlockBytes = kBlockM * kBlockK * 2;  // 16384
+static constexpr uint32_t kTmemColsA = 256;  // first TMEM column of the A operand (128 lanes x 256 cols x 2 bf16)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -73,6 +74,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in tensor memory (lane = row, 32-bit column c = k elements 2c, 2c+1)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // arrive on an mbarrier once every tcgen05 operation issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -104,13 +129,12 @@ struct MlpParams {
 };
 
 // shared memory map (dynamic, 1024-byte aligned base):
-//   [0, 128K)                A operand: 8 k-blocks of [128 rows][128 B], SWIZZLE_128B
-//   [128K, 128K + S*BN*128)  W2 ring
-//   then: float4 w1b1[512], float2 gb[512], barriers, tmem base
+//   [0, S*BN*128)            W2 ring: S stages of [BLOCK_N rows][128 B], SWIZZLE_128B
+//   then: float4 gw1[512], float2 gb[512], barriers, tmem base, LN moments, epilogue staging
 template <int BLOCK_N>
 struct MlpSmem {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kOffB = kABytes;
+  static constexpr int kOffB = 0;
   static constexpr int kOffW1 = kOffB + kStages * kBBytes;
   static constexpr int kOffGB = kOffW1 + kHidden * 16;
   static constexpr int kOffBar = kOffGB + kHidden * 8;
@@ -129,7 +153,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  unsigned char* s_a = smem;
   unsigned char* s_b = smem + S::kOffB;
   float4* s_w1 = reinterpret_cast<float4*>(smem + S::kOffW1);
   float2* s_gb = reinterpret_cast<float2*>(smem + S::kOffGB);
@@ -141,7 +164,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
   uint64_t* t_empty = bars + 2 * kStages + 3;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + S::kOffTmem);
 
-  constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static_assert(2 * BLOCK_N <= (int)kTmemColsA, "accumulators overlap the A operand");
+  constexpr uint32_t kTmemCols = 512;
 
   // ---- one-time setup
   // LayerNorm statistics in closed form.  h_k = w_k . c + b_k is affine in the token's coordinates c, so
@@ -229,7 +253,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
       uint32_t it = 0, acc_it = 0, a_phase = 0;
       for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, a_phase ^= 1) {
-        mbar_wait(a_full, a_phase);  // A operand of this M tile is in shared memory
+        mbar_wait(a_full, a_phase);  // A operand of this M tile is in tensor memory
         tcgen05_fence_after();
         for (int nt = 0; nt < n_tiles; ++nt, ++acc_it) {
           const uint32_t acc = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
@@ -240,11 +264,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
             const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
             mbar_wait(b_full + stage, phase);
             tcgen05_fence_after();
-            const uint64_t da = make_kmajor_sw128_desc(s_a + kb * kAKBlockBytes);
+            const uint32_t ta = tmem_base + kTmemColsA + kb * (kBlockK / 2);
             const uint64_t db = make_kmajor_sw128_desc(s_b + stage * S::kBBytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes: +2 in the >>4 address field
-              umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < kBlockK / 16; ++k)  // UMMA_K = 16 bf16: 8 TMEM columns of A, 32 bytes (+2 in the >>4 field) of B
+              umma_bf16_ts(tmem_d, ta + 8 * k, db + 2 * k, idesc, (kb | k) != 0);
             umma_commit(b_empty + stage);  // frees the W2 slot when these MMAs have read it
           }
           umma_commit(t_full + acc);  // accumulator complete
@@ -284,29 +308,28 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
       var = fmaxf(var, 0.f);
       const float rstd = rsqrtf(var + p.eps);
       const float nmr = -mean * rstd;
-#pragma unroll 2
-      for (int kc = 0; kc < kHidden / 8; ++kc) {  // 8 features = one 16-byte chunk
-        uint32_t packed[4];
+      const uint32_t ta_row = tmem_base + ((uint32_t)(q * 32) << 16) + kTmemColsA;
+#pragma unroll 1
+      for (int kb = 0; kb < kNumKBlocks; ++kb) {  // 64 features = 32 TMEM columns per store
+        uint32_t packed[32];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 32; ++i) {
           float y[2];
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const int k = kc * 8 + 2 * i + j;
+            const int k = kb * kBlockK + 2 * i + j;
             const float4 w = s_w1[k];   // gamma-scaled first layer
             const float2 gb = s_gb[k];  // {gamma, beta}
             const float t = fmaf(w.x, c0, fmaf(w.y, c1, fmaf(w.z, c2, w.w)));
             y[j] = fmaxf(fmaf(rstd, t, fmaf(nmr, gb.x, gb.y)), 0.f);
           }
-          const __nv_bfloat162 b = __floats2bfloat162_rn(y[0], y[1]);
+          const __nv_bfloat162 b = __floats2bfloat162_rn(y[0], y[1]);  // low half = even k
           packed[i] = *reinterpret_cast<const uint32_t*>(&b);
         }
-        // canonical K-major SWIZZLE_128B: k-block kb, row r at r*128, 16-byte chunk c at position c ^ (r & 7)
-        const int kb = kc >> 3, c = kc & 7;
-        unsigned char* dst = s_a + kb * kAKBlockBytes + r * 128 + ((c ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        tmem_st_32x32b_x32(ta_row + kb * (kBlockK / 2), packed);
       }
-      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      tmem_st_wait();
+      tcgen05_fence_before();  // order the TMEM stores before the MMA thread's reads
       mbar_arrive(a_full);
 
       // ---- (b) epilogue of every N tile of this M tile.
