@@ -356,7 +356,7 @@ def run_ours(args):
     h_coords = torch.empty((n_frames, GRID, GRID, 3), dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        d_depth.copy_(h_depth, non_blocking=True)
+        fe.upload(h_depth, out=d_depth)  # only the depth window the kernel reads (58 % of the frame bytes)
         d_poses.copy_(h_poses, non_blocking=True)
         d_intr.copy_(h_intr, non_blocking=True)
         _, _, pe_coords = fe(d_depth, d_poses, d_intr, tokens=tokens, out=out, want_coords=True)
@@ -379,7 +379,7 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dist.barrier()
     e2e_value = world * n_frames * Ke / float(te.item())
-    h2d = h_depth.numel() * h_depth.element_size() + h_poses.numel() * 4 + h_intr.numel() * 4
+    h2d = fe.upload_bytes(n_frames, h_depth.element_size()) + h_poses.numel() * 4 + h_intr.numel() * 4
     d2h = h_coords.numel() * 4
 
     # secondary: the reference's default recipe geometry (27-pixel windows -> 14x14 grid, E = 3584)
@@ -423,7 +423,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": BYTES_PER_FRAME_FUSED_ADD * n_frames, "kernel": "k_fused",
                          "avg_launch_us": kernel_s * 1e6},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": Ke, "note": "pinned host depth/pose/intrinsics -> device each step; vision tokens are produced on the "
+                    "steps": Ke, "note": "pinned host depth (the 4-of-5 rows x column window the kernel reads, one strided DMA)/pose/intrinsics -> device each step; vision tokens are produced on the "
                     "device by the vision tower and stay resident; per-token voxel coordinates read back"},
             "gpu_launches": K,
             "clocks": clk,

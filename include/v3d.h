@@ -70,6 +70,16 @@ int v3d_unproject(const void* depth, int depth_dtype, const float* poses, const 
 int v3d_boundary(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
                  float depth_scale, const float* clamp_lo_hi_host, float* out6, v3d_stream_t stream);
 
+/* Host -> device upload of ONLY the depth samples the front end reads.  The nearest-neighbour resize + centre
+ * crop (llava/video_utils.py:291-308) references a column window and, for ScanNet's 480 -> 384 rows, 4 of every
+ * 5 rows: 58 % of the bytes of a frame.  depth_host (pinned) and depth_dev have the same (n_rows_total, pitch)
+ * layout; the copy moves, for each group of `row_period` rows, the first `rows_keep` rows, bytes
+ * [x_off_bytes, x_off_bytes + width_bytes) of each -- one strided DMA (cudaMemcpy3DAsync), stream-ordered.
+ * Everything outside the window is left untouched on the device and is never read by v3d_frontend_pe. */
+int v3d_upload_depth_window(const void* depth_host, void* depth_dev, size_t pitch_bytes, size_t n_rows_total,
+                            size_t x_off_bytes, size_t width_bytes, size_t row_period, size_t rows_keep,
+                            v3d_stream_t stream);
+
 /* ---- helpers on materialised coordinates (API parity with the reference's call structure) --
  * v3d_pool_coords replaces llava/model/llava_arch.py:213-223 `average_coordinate_in_patch`,
  * :225-239 `minmax_coordinate_in_patch`, :241-257 `sample_n_points`.

@@ -600,3 +600,27 @@ def test_nan_pose_propagates_like_the_reference():
     exp = O.bf16_bits_to_f32(ref["pe_bf16"])
     assert np.array_equal(np.isnan(got), np.isnan(exp))
     assert np.isnan(got[1, :, 1194:2388]).all() and not np.isnan(got[0]).any()
+
+
+def test_windowed_depth_upload_feeds_the_same_result(scene):
+    """FrontEnd.upload copies only the depth samples the kernel reads; the result equals a full upload."""
+    fe = FrontEnd(device=DEV, patch_size=14, embedding_size=1152)
+    assert fe.upload_window(2) == (160, 944, 5, 4)  # ScanNet geometry: columns 80..551, rows 4 of 5
+    assert fe.upload_bytes(3) == 3 * 96 * 4 * 944
+    h = scene.depth.pin_memory()
+    poison = torch.full(h.shape, 12345, dtype=h.dtype, device=DEV)
+    d = fe.upload(h, out=poison)
+    torch.cuda.synchronize()
+    got = d.cpu().view(3, 96, 5, 640)
+    ref = scene.depth.view(3, 96, 5, 640)
+    assert torch.equal(got[:, :, :4, 80:552], ref[:, :, :4, 80:552])
+    assert bool((got[:, :, 4, :] == 12345).all()) and bool((got[:, :, :, :80] == 12345).all())  # untouched outside the window
+    p, k = scene.poses.to(DEV), scene.intrinsics.to(DEV)
+    a = fe(d, p, k)
+    b = fe(scene.depth.to(DEV), p, k)
+    assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+    # the 'resize' strategy squeezes all 640 columns into 384: the window starts at column 0 (rows still 4 of 5)
+    fe2 = FrontEnd(device=DEV, patch_size=27, embedding_size=3584, strategy="resize")
+    x_off, width, period, keep = fe2.upload_window(2)
+    assert (x_off, period, keep) == (0, 5, 4) and width <= 1280
+    assert torch.equal(fe2(fe2.upload(h), p, k).view(torch.int16), fe2(scene.depth.to(DEV), p, k).view(torch.int16))

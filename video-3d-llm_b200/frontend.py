@@ -71,6 +71,48 @@ class FrontEnd:
     def tokens_per_frame(self) -> int:
         return self.cfg.grid * self.cfg.grid
 
+    def upload_window(self, esize: int = 2):
+        """(x_off_bytes, width_bytes, row_period, rows_keep) of the depth samples this geometry reads: the 16-byte
+        aligned column window and, when the row map has a regular keep-k-of-p structure (ScanNet: 4 of 5), that
+        structure; (.., 1, 1) = every row."""
+        cfg = self.cfg
+        lo = (self.src_col_min * esize) & ~15
+        hi = min(((self.src_col_max + 1) * esize + 15) & ~15, cfg.W * esize)
+        rows, _ = geometry.resample_maps_host(cfg.H, cfg.W, cfg.crop_size, cfg.strategy)
+        used = set(rows[: cfg.grid * cfg.patch_size])
+        period, keep = 1, 1
+        for per in range(2, 9):
+            if cfg.H % per:
+                continue
+            k = max(r % per for r in used) + 1
+            if k < per:
+                period, keep = per, k
+                break
+        return lo, hi - lo, period, keep
+
+    def upload(self, depth_host: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Stream-ordered host -> device copy of only the depth samples the kernel reads (v3d_upload_depth_window):
+        58 % of the bytes for ScanNet-shaped frames.  depth_host: pinned (V,H,W) uint16/int16-bits/int32/float32.
+        The rest of the returned device tensor is unspecified and never read by __call__."""
+        if depth_host.is_cuda or not depth_host.is_pinned():
+            raise ValueError("upload() takes a pinned host tensor")
+        depth_host = depth_host.contiguous()
+        V, H, W = depth_host.shape
+        if (H, W) != (self.cfg.H, self.cfg.W):
+            raise ValueError(f"depth is {H}x{W}, front end was configured for {self.cfg.H}x{self.cfg.W}")
+        if out is None:
+            out = torch.empty(depth_host.shape, dtype=depth_host.dtype, device=self.device)
+        es = depth_host.element_size()
+        x_off, width, period, keep = self.upload_window(es)
+        with torch.cuda.device(self.device):
+            cabi.check(self.lib.v3d_upload_depth_window(depth_host.data_ptr(), out.data_ptr(), W * es, V * H, x_off, width, period, keep,
+                                                        cabi.stream_ptr(self.device)), "v3d_upload_depth_window")
+        return out
+
+    def upload_bytes(self, n_frames: int, esize: int = 2) -> int:
+        x_off, width, period, keep = self.upload_window(esize)
+        return n_frames * (self.cfg.H // period) * keep * width
+
     def __call__(self, depth, poses, intrinsics, tokens=None, out=None, clamp=None, want_coords=False):
         """depth (V,H,W) uint16/int16-bits/int32/float32, poses & intrinsics (V,4,4) float32, all on the
         device.  tokens: optional (V, G*G, E) in cfg.dtype to add the PE to (may be `out`).
