@@ -355,13 +355,30 @@ def run_ours(args):
     d_depth, d_poses, d_intr = torch.empty_like(depth), torch.empty_like(poses), torch.empty_like(intr)
     h_coords = torch.empty((n_frames, GRID, GRID, 3), dtype=torch.float32).pin_memory()
 
+    # the step is split into chunks so that the upload of chunk i+1 (copy stream) overlaps the kernel of chunk i
+    n_chunks = 4
+    bounds = [(i * n_frames // n_chunks, (i + 1) * n_frames // n_chunks) for i in range(n_chunks)]
+    up = torch.cuda.Stream(device=dev)
+    d_coords = torch.empty((n_frames, GRID, GRID, 3), dtype=torch.float32, device=dev)
+
     def e2e_step():
-        fe.upload(h_depth, out=d_depth)  # only the depth window the kernel reads (58 % of the frame bytes)
-        d_poses.copy_(h_poses, non_blocking=True)
-        d_intr.copy_(h_intr, non_blocking=True)
-        _, _, pe_coords = fe(d_depth, d_poses, d_intr, tokens=tokens, out=out, want_coords=True)
-        h_coords.copy_(pe_coords, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        cur = torch.cuda.current_stream(dev)
+        up.wait_stream(cur)  # the previous step's kernels are done with the device buffers
+        events = []
+        with torch.cuda.stream(up):
+            d_poses.copy_(h_poses, non_blocking=True)
+            d_intr.copy_(h_intr, non_blocking=True)
+            for a, b in bounds:
+                fe.upload(h_depth[a:b], out=d_depth[a:b])  # only the depth window the kernel reads (58 % of the frame bytes)
+                ev = torch.cuda.Event()
+                ev.record(up)
+                events.append(ev)
+        for (a, b), ev in zip(bounds, events):
+            cur.wait_event(ev)
+            _, _, pe_coords = fe(d_depth[a:b], d_poses[a:b], d_intr[a:b], tokens=tokens[a:b], out=out[a:b], want_coords=True)
+            d_coords[a:b].copy_(pe_coords)
+        h_coords.copy_(d_coords, non_blocking=True)
+        cur.synchronize()
 
     for _ in range(2):
         e2e_step()
@@ -425,7 +442,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": Ke, "note": "pinned host depth (the 4-of-5 rows x column window the kernel reads, one strided DMA)/pose/intrinsics -> device each step; vision tokens are produced on the "
                     "device by the vision tower and stay resident; per-token voxel coordinates read back"},
-            "gpu_launches": K,
+            "gpu_launches": K,  # timed region: K launches of k_fused (the e2e leg launches 4 per step, the mc leg 4 per step)
             "clocks": clk,
             "default_recipe_geometry": recipe,
             "mc": mc,
