@@ -1,6 +1,6 @@
 """Timing of the tcgen05 MLP-PE kernel at config-2 size (M = 512*729 tokens, E = 1152) and E = 3584."""
 import sys, json, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from video_3d_llm_b200.position_encoding import PositionEmbeddingMLP
 DEV = torch.device('cuda:0')
 res = {}

@@ -1,8 +1,8 @@
 """Helpers to read .ncu-rep files brought back from the GPU box (no GPU needed here).
 
-    python tools_ncu.py summary gpurun_out/prof.ncu-rep          # key metrics per launch
-    python tools_ncu.py blocks  gpurun_out/prof.ncu-rep [n]      # hottest SASS blocks by executed instr
-    python tools_ncu.py sass    gpurun_out/prof.ncu-rep lo hi    # SASS lines [lo,hi) with counts + stalls
+    python tools/ncu_summary.py summary gpurun_out/prof.ncu-rep          # key metrics per launch
+    python tools/ncu_summary.py blocks  gpurun_out/prof.ncu-rep [n]      # hottest SASS blocks by executed instr
+    python tools/ncu_summary.py sass    gpurun_out/prof.ncu-rep lo hi    # SASS lines [lo,hi) with counts + stalls
 """
 import csv
 import io

@@ -1,5 +1,5 @@
 import sys, json, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from video_3d_llm_b200 import cabi
 from video_3d_llm_b200.position_encoding import PositionEmbeddingMLP
 DEV = torch.device('cuda:0'); lib = cabi.load()
