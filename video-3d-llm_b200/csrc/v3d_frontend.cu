@@ -719,13 +719,19 @@ __device__ __forceinline__ void chain_row(ChainAcc& c, const float* src, int P, 
 __device__ __forceinline__ void pool_rows_fast(const Camera& cam, const Divisor& ds, int P, uint32_t span, int n_px,
                                                const float um[2], const uint32_t d_addr[2], const uint32_t w_addr[2],
                                                const float2* s_vm, bool chain, const float* chain_src, int pool_mode,
-                                               const Clamp& clamp, ChainAcc& c) {
+                                               const Clamp& clamp, ChainAcc& c, const unsigned char* pf_src, size_t pf_bytes) {
+  // the token rows are pulled into L2 ~8 row pairs before the streaming phase needs them: early enough to hide
+  // DRAM latency, late enough that the output stream of the co-resident CTAs has not evicted them again
+  const int pf_dy = (P > 16) ? ((P - 16) & ~1) : 0;
   // two resampled rows per barrier: the row buffers hold 2 x 2 rows, halving the number of block-wide
   // synchronisations (the chain threads add row dy, then row dy+1, so the summation order is unchanged)
   uint32_t row_off = 0;
   for (int dy = 0; dy < P; dy += 2) {
     const uint32_t bsel = ((dy >> 1) & 1) ? (uint32_t)(6 * kPlane * 4) : 0u;
     const int n_rows = (dy + 1 < P) ? 2 : 1;
+    if (dy == pf_dy && pf_src != nullptr && threadIdx.x == 32) {
+      for (size_t o = 0; o < pf_bytes; o += 32768) tma_prefetch_l2(pf_src + o, (uint32_t)min((size_t)32768, pf_bytes - o));
+    }
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       if (rr < n_rows) {
@@ -789,13 +795,17 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
   int* s_flag = s_off + G * n_off;
   ChunkDesc* s_desc = reinterpret_cast<ChunkDesc*>((reinterpret_cast<uintptr_t>(s_flag + G) + 7) & ~(uintptr_t)7);
 
-  // ---- the token rows this CTA will add the PE to are independent of everything computed below:
-  // have the TMA unit pull them into L2 now, so that the streaming phase finds them there
-  if (p.pe_mode != V3D_PE_NONE && p.tokens_in != nullptr && t == 32) {
+  // ---- the token rows this CTA will add the PE to are independent of everything computed below: the TMA unit
+  // pulls them into L2 ahead of the streaming phase (issued inside the row loop on the fast path, see
+  // pool_rows_fast, otherwise right before the generic loop)
+  const unsigned char* pf_src = nullptr;
+  size_t pf_bytes = 0;
+  if (p.pe_mode != V3D_PE_NONE && p.tokens_in != nullptr) {
     const size_t row_bytes = (size_t)G * p.g.E * sizeof(OutT);
     const unsigned char* src = reinterpret_cast<const unsigned char*>(p.tokens_in) + ((size_t)f * G + gi) * row_bytes;
     if ((row_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-      for (size_t o = 0; o < row_bytes; o += 32768) tma_prefetch_l2(src + o, (uint32_t)min((size_t)32768, row_bytes - o));
+      pf_src = src;
+      pf_bytes = row_bytes;
     }
   }
   // ---- stage the P depth rows of this patch row with the TMA unit
@@ -876,8 +886,11 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
     const float* chain_src = s_row + a * kPlane + j * P;
     if (all_fast) {
       pool_rows_fast(cam, ds, P, (uint32_t)p.span, col[1] >= 0 ? 2 : 1, um, d_addr, w_addr, s_vm, chain, chain_src, p.pool_mode,
-                     p.clamp, ca);
+                     p.clamp, ca, pf_src, pf_bytes);
     } else {
+      if (pf_src != nullptr && t == 32) {
+        for (size_t o = 0; o < pf_bytes; o += 32768) tma_prefetch_l2(pf_src + o, (uint32_t)min((size_t)32768, pf_bytes - o));
+      }
       uint32_t row_off = 0;  // byte offset of staged depth row dy
       for (int dy = 0; dy < P; ++dy, row_off += (uint32_t)p.span) {
         const uint32_t bsel = (dy & 1) ? (uint32_t)(3 * kPlane * 4) : 0u;
