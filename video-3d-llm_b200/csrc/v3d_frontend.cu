@@ -422,6 +422,7 @@ __device__ __forceinline__ void stream_pairs_clean(int l0, int cpt, int E, int n
   constexpr int kWarps = kThreads / 32;
   const int warp = threadIdx.x >> 5;
   uint32_t offa[U], offb[U], ka[U], kb[U], rel[U];
+  bool two[U];  // this chunk column touches a second slot (only the 2-3 columns at slot boundaries do)
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int L = l0 + 32 * u;
@@ -432,6 +433,7 @@ __device__ __forceinline__ void stream_pairs_clean(int l0, int cpt, int E, int n
     ka[u] = d.x & 0xffffu;
     offb[u] = (uint32_t)(ts * n_off + (int)(d.y >> 16)) * 4u;
     kb[u] = d.y & 0xffffu;
+    two[u] = STRADDLE && (int)(d.y >> 16) != n_off - 1;
     rel[u] = (uint32_t)(ts * E + c8 * 8);
   }
   uint32_t off = smem_u32(s_off) + (uint32_t)(warp * 2 * n_off) * 4u;
@@ -448,8 +450,10 @@ __device__ __forceinline__ void stream_pairs_clean(int l0, int cpt, int E, int n
       asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + offa[u]));
       pe[u] = chunk_ldg(table + ((uint32_t)o + ka[u]));
       if (STRADDLE) {
-        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + offb[u]));
-        chunk_or(pe[u], chunk_ldg(table + ((uint32_t)o + kb[u])));
+        if (two[u]) {
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + offb[u]));
+          chunk_or(pe[u], chunk_ldg(table + ((uint32_t)o + kb[u])));
+        }
       }
     }
 #pragma unroll
@@ -722,7 +726,10 @@ __device__ __forceinline__ void pool_rows_fast(const Camera& cam, const Divisor&
                                                const Clamp& clamp, ChainAcc& c, const unsigned char* pf_src, size_t pf_bytes) {
   // the token rows are pulled into L2 ~8 row pairs before the streaming phase needs them: early enough to hide
   // DRAM latency, late enough that the output stream of the co-resident CTAs has not evicted them again
-  const int pf_dy = (P > 16) ? ((P - 16) & ~1) : 0;
+#ifndef V3D_PF_LEAD
+#define V3D_PF_LEAD 8
+#endif
+  const int pf_dy = (P > V3D_PF_LEAD) ? ((P - V3D_PF_LEAD) & ~1) : 0;
   // two resampled rows per barrier: the row buffers hold 2 x 2 rows, halving the number of block-wide
   // synchronisations (the chain threads add row dy, then row dy+1, so the summation order is unchanged)
   uint32_t row_off = 0;
