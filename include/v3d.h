@@ -197,6 +197,18 @@ int v3d_mc_greedy(const v3d_mc_scene* scenes_host, int n_scenes, int max_pick, v
 /* voxel ids of materialised world coordinates: int(round(w / voxel)) (max_coverage_sampling.py:44-45) */
 int v3d_mc_voxel_ids(const float* world, size_t n_points, float voxel_size, int div_mode, int32_t* ids, v3d_stream_t stream);
 
+/* ---- object proposals -------------------------------------------------------
+ * v3d_object_patch_masks replaces the per-object loop of llava/model/llava_arch.py:351-378: for each of K
+ * boxes (cx,cy,cz,w,h,l) and each patch of each frame, is the number of pixels whose world coordinate lies
+ * inside the box (closed interval per axis) >= threshold?  coords (V,S,S,3) fp32; masks_out (K,V,grid,grid)
+ * uint8.  "patch14": patch 14, grid 27, threshold int(14*14*0.5) = 98; "patch27": patch 27, grid 14,
+ * threshold int(27*27*0.25) = 182.
+ * v3d_masked_token_mean replaces :479-496: out[k] = mean over the tokens t with masks[k,t] != 0 of tokens[t]
+ * (fp32 accumulation, bf16 result; zeros when no token is selected).  tokens (T,C) bf16, masks (K,T) uint8. */
+int v3d_object_patch_masks(const float* coords, int V, int S, int patch, int grid, const float* boxes, int K, int threshold,
+                           uint8_t* masks_out, v3d_stream_t stream);
+int v3d_masked_token_mean(const void* tokens_bf16, int T, int C, const uint8_t* masks, int K, void* out_bf16, v3d_stream_t stream);
+
 /* ---- learned-projection PE (tensor cores) ----------------------------------------------------
  * Replaces llava/model/position_encoding.py:52-84 `PositionEmbeddingMLP.forward` (+ the add of
  * llava_arch.py:515): Linear(3,512) -> LayerNorm(512) -> ReLU -> Linear(512,E) (+ tokens).

@@ -300,6 +300,51 @@ def golden_dataset():
     print("dataset.json written")
 
 
+def golden_objects():
+    """Object-proposal patch masks: the reference's own lines (llava_arch.py:351-378) are read from the mounted
+    reference at run time, dedented and executed against a stand-in `self` -- they sit in the middle of a
+    500-line method and cannot be called on their own."""
+    import textwrap
+
+    vu = ref_import.video_utils()
+    with open(os.path.join(ref_import.REF_ROOT, "llava", "model", "llava_arch.py")) as f:
+        lines = f.read().splitlines()
+    block = textwrap.dedent("\n".join(lines[350:378]))
+    assert block.lstrip().startswith("object_boxes = None") and "patch14" in block and "patch27" in block, "reference lines moved"
+    sc = synthetic.make_scene(0, 2, n_total=30, H=480, W=640, device="cpu")
+    world = vu.unproject(sc.intrinsics, sc.poses, torch.from_numpy(sc.depth_u16().astype(np.int32)).float())
+    res = [cv2.resize(c.numpy(), (512, 384), interpolation=cv2.INTER_NEAREST)[:, 64:448, :] for c in world]
+    coords = torch.from_numpy(np.stack(res))
+    room, rng = sc.room, np.random.default_rng(17)
+    boxes = [[float((b[0, a] + b[1, a]) / 2) for a in range(3)] + [float(b[1, a] - b[0, a]) for a in range(3)] for b in sc.boxes]
+    boxes.append([0.0, 0.0, float(room[1, 2] / 2), float(room[1, 0] - room[0, 0]) + 1, float(room[1, 1] - room[0, 1]) + 1, float(room[1, 2]) + 1])  # whole room
+    boxes.append([50.0, 50.0, 50.0, 1.0, 1.0, 1.0])  # far away: no patch
+    for _ in range(12):
+        c = rng.uniform(room[0], room[1])
+        boxes.append([float(c[0]), float(c[1]), float(c[2]), *[float(v) for v in rng.uniform(0.3, 2.5, 3)]])
+    boxes_t = torch.tensor(boxes, dtype=torch.float32)
+    g = {"boxes": boxes_t.numpy(), "in_depth_sha": sha(sc.depth_u16()), "coords_sha": sha(coords.numpy())}
+    for kind in ("patch14", "patch27"):
+        ns = {"torch": torch, "use_object_proposals": True,
+              "video_dict": {"objects": boxes_t[None], "world_coords": coords[None]},
+              "self": types.SimpleNamespace(config=types.SimpleNamespace(object_feature_type=kind + "-pe"))}
+        exec(block, ns)
+        masks = torch.stack(ns["object_patch"]).numpy()  # (K,V,G,G)
+        g[f"masks_{kind}"] = np.packbits(masks)
+        g[f"masks_{kind}_shape"] = np.array(masks.shape)
+        g[f"masks_{kind}_count"] = masks.reshape(len(boxes), -1).sum(1)
+    # llava_arch.py:479-496 on random bf16 tokens with the patch27 masks (torch's own indexing + mean)
+    masks27 = torch.stack(ns["object_patch"])
+    feats = synthetic.make_tokens(0, 2, 196, 256)
+    objf = []
+    for l in range(len(boxes)):
+        cur = feats.reshape(-1, 256)[masks27[l].reshape(-1)]
+        objf.append(torch.zeros(256, dtype=feats.dtype) if len(cur) == 0 else cur.mean(dim=0))
+    g["objfeat_patch27"] = torch.stack(objf).float().numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "objects.npz"), **g)
+    print("objects.npz written")
+
+
 def golden_mt():
     """CPython `random` known answers for the in-kernel MT19937 (tie-break protocol)."""
     out = {}
@@ -324,5 +369,7 @@ if __name__ == "__main__":
         golden_mt()
     if a.only in ("", "frontend"):
         golden_frontend()
+    if a.only in ("", "objects"):
+        golden_objects()
     if a.only in ("", "dataset"):
         golden_dataset()

@@ -395,3 +395,40 @@ def mc_prefix_cut(order_files, voxel_nums, num_all_voxels, strategy: str, frames
         files = out
     files.sort(key=lambda s: int(str(s).split("/")[-1].split(".")[0]))
     return files
+
+
+# ------------------------------------------------------------------------------------------
+# object proposals
+# ------------------------------------------------------------------------------------------
+def object_patch_masks(coords: np.ndarray, boxes: np.ndarray, object_feature_type: str = "patch14") -> np.ndarray:
+    """llava/model/llava_arch.py:361-376.  coords (V,384,384,3), boxes (K,6) centre+size -> bool (K,V,G,G):
+    count of pixels with min <= xyz <= max (all three axes) per patch >= int(p*p*ratio)."""
+    if "patch27" in object_feature_type:
+        p, g, thr = 27, 14, int(27 * 27 * 0.25)
+    elif "patch14" in object_feature_type:
+        p, g, thr = 14, 27, int(14 * 14 * 0.5)
+    else:
+        raise NotImplementedError
+    c = _f32(coords)[:, :378, :378, :]
+    V = c.shape[0]
+    c = c.reshape(V, g, p, g, p, 3).transpose(0, 1, 3, 2, 4, 5).reshape(V, g, g, p * p, 3)
+    b = _f32(boxes)
+    out = np.zeros((len(b), V, g, g), bool)
+    for k in range(len(b)):
+        half = b[k, 3:] / np.float32(2)
+        lo, hi = b[k, :3] - half, b[k, :3] + half
+        inside = np.all((lo <= c) & (c <= hi), axis=-1)
+        out[k] = inside.sum(axis=3) >= thr
+    return out
+
+
+def object_features(tokens_bf16_bits: np.ndarray, masks: np.ndarray) -> np.ndarray:
+    """llava/model/llava_arch.py:479-496: per object the mean (fp32 accumulate, bf16 result) of the selected token
+    rows, zeros when none.  tokens (T,C) bf16 bits, masks (K,T) -> (K,C) bf16 bits."""
+    t = bf16_bits_to_f32(tokens_bf16_bits).astype(np.float64)
+    m = np.asarray(masks).reshape(len(masks), -1)
+    out = np.zeros((len(m), t.shape[1]), np.float32)
+    for k in range(len(m)):
+        if m[k].any():
+            out[k] = t[m[k]].mean(axis=0).astype(np.float32)
+    return f32_to_bf16_bits(out)

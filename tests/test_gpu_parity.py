@@ -624,3 +624,43 @@ def test_windowed_depth_upload_feeds_the_same_result(scene):
     x_off, width, period, keep = fe2.upload_window(2)
     assert (x_off, period, keep) == (0, 5, 4) and width <= 1280
     assert torch.equal(fe2(fe2.upload(h), p, k).view(torch.int16), fe2(scene.depth.to(DEV), p, k).view(torch.int16))
+
+
+# ---------------------------------------------------------------------------------------------
+# object proposals
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["patch14", "patch27"])
+def test_object_patch_masks_bit_exact(golden_dir, kind):
+    GO = np.load(os.path.join(golden_dir, "objects.npz"))
+    sc = synthetic.make_scene(0, 2, n_total=30, device="cpu")
+    from video_3d_llm_b200 import geometry
+    rm, cm = geometry.resample_maps(480, 640, 384, "center_crop", DEV)
+    coords = VU.unproject(sc.intrinsics, sc.poses, sc.depth, row_map=rm, col_map=cm)
+    boxes = torch.from_numpy(GO["boxes"])
+    got = C.object_patch_masks(coords, boxes, kind + "-pe").cpu().numpy()
+    shape = tuple(GO[f"masks_{kind}_shape"])
+    gold = np.unpackbits(GO[f"masks_{kind}"])[: int(np.prod(shape))].reshape(shape).astype(bool)
+    np.testing.assert_array_equal(got, gold)  # the reference's own masks
+    np.testing.assert_array_equal(got, O.object_patch_masks(coords.cpu().numpy(), GO["boxes"], kind))
+    # a lazy handle gives the same masks (materialised on demand)
+    lazy = VU.LazyWorldCoords(sc.depth, sc.poses, sc.intrinsics)
+    assert torch.equal(C.object_patch_masks(lazy, boxes, kind), torch.from_numpy(gold).to(DEV))
+
+
+def test_object_features_match_reference(golden_dir):
+    GO = np.load(os.path.join(golden_dir, "objects.npz"))
+    shape = tuple(GO["masks_patch27_shape"])
+    masks = torch.from_numpy(np.unpackbits(GO["masks_patch27"])[: int(np.prod(shape))].reshape(shape).astype(bool)).to(DEV)
+    feats = synthetic.make_tokens(0, 2, 196, 256).to(DEV)
+    got = C.object_features(feats, masks)
+    assert got.dtype == torch.bfloat16 and got.shape == (shape[0], 256)
+    np.testing.assert_allclose(got.float().cpu().numpy(), GO["objfeat_patch27"], rtol=0, atol=2.0 ** -7)
+    empty = GO["masks_patch27_count"] == 0
+    assert empty.any() and bool((got[torch.from_numpy(empty).to(DEV)] == 0).all())
+    # larger, dense case against the oracle
+    rng = np.random.default_rng(4)
+    m = torch.from_numpy(rng.random((37, 2, 27, 27)) < 0.2).to(DEV)
+    tok = synthetic.make_tokens(9, 2, 729, 1152).to(DEV)
+    got2 = C.object_features(tok, m)
+    ref2 = O.object_features(bf16_bits(tok).reshape(-1, 1152), m.cpu().numpy())
+    assert_bf16_close(bf16_bits(got2), ref2, max_frac=5e-3)

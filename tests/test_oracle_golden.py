@@ -252,3 +252,21 @@ def test_torch_port_bit_exact(G, scene0):
     pe, pooled14, disc14 = TP.frontend(depth, scene0.poses, scene0.intrinsics, 14, 1152)
     np.testing.assert_array_equal(pooled14.numpy(), G["avg14"])
     assert sha(pe.view(torch.int16).numpy()) == str(G["pe1152_bf16_sha"])
+
+
+# ---------------------------------------------------------------------------------------------
+# object proposals (section 8 f1)
+# ---------------------------------------------------------------------------------------------
+def test_object_patch_masks_and_features(golden_dir, stages):
+    GO = np.load(os.path.join(golden_dir, "objects.npz"))
+    assert sha(stages["coords"]) == str(GO["coords_sha"])
+    for kind in ("patch14", "patch27"):
+        shape = tuple(GO[f"masks_{kind}_shape"])
+        ref = np.unpackbits(GO[f"masks_{kind}"])[: int(np.prod(shape))].reshape(shape).astype(bool)
+        mine = O.object_patch_masks(stages["coords"], GO["boxes"], kind)
+        np.testing.assert_array_equal(mine, ref)
+        assert ref.reshape(shape[0], -1).sum(1).tolist() == GO[f"masks_{kind}_count"].tolist()
+    assert GO["masks_patch27_count"].max() > 50 and (GO["masks_patch27_count"] == 0).any()  # the fixture exercises both
+    tokens = synthetic.make_tokens(0, 2, 196, 256).view(torch.int16).numpy().view(np.uint16).reshape(-1, 256)
+    feat = O.object_features(tokens, O.object_patch_masks(stages["coords"], GO["boxes"], "patch27"))
+    np.testing.assert_allclose(O.bf16_bits_to_f32(feat), GO["objfeat_patch27"], rtol=0, atol=2.0 ** -7)

@@ -72,6 +72,54 @@ def discrete_coords(world_coords, xyz_min=None, *, voxel_size=0.1, min_xyz_range
     return out.to(world_coords.dtype)
 
 
+_OBJECT_GEOMETRY = {"patch14": (14, 27, int(14 * 14 * 0.5)), "patch27": (27, 14, int(27 * 27 * 0.25))}
+
+
+def object_patch_masks(world_coords, object_boxes, object_feature_type: str = "patch14"):
+    """llava/model/llava_arch.py:351-378 for all objects at once.  world_coords (V,384,384,3) (tensor or lazy
+    handle), object_boxes (K,6) centre+size -> bool (K,V,G,G): patches with enough pixels inside each box
+    ("patch14": 27x27 grid, >= 98 of 196 pixels; "patch27": 14x14 grid, >= 182 of 729 pixels)."""
+    from .video_utils import LazyWorldCoords
+
+    for key, geom in _OBJECT_GEOMETRY.items():
+        if key in object_feature_type:
+            patch, grid, thr = geom
+            break
+    else:
+        raise NotImplementedError(object_feature_type)
+    if isinstance(world_coords, LazyWorldCoords):
+        world_coords = world_coords.materialize()
+    cabi.require_cuda(world_coords, "world_coords")
+    lib = cabi.load()
+    V, S = world_coords.shape[0], world_coords.shape[1]
+    src = world_coords.detach().to(torch.float32).contiguous()
+    boxes = object_boxes.detach().to(src.device, torch.float32).contiguous()
+    K = boxes.shape[0]
+    masks = torch.zeros((K, V, grid, grid), dtype=torch.uint8, device=src.device)
+    with torch.cuda.device(src.device):
+        cabi.check(lib.v3d_object_patch_masks(src.data_ptr(), V, S, patch, grid, boxes.data_ptr(), K, thr, masks.data_ptr(),
+                                              cabi.stream_ptr(src.device)), "v3d_object_patch_masks")
+    return masks.bool()
+
+
+def object_features(token_features, masks):
+    """llava/model/llava_arch.py:479-496: mean token feature of every object's patches, zeros for objects without
+    any.  token_features (V,T,C) or (V*T,C) bf16, masks bool/uint8 (K,V,G,G) with G*G == T -> (K,C) bf16."""
+    cabi.require_cuda(token_features, "token_features")
+    lib = cabi.load()
+    C = token_features.shape[-1]
+    feats = token_features.detach().reshape(-1, C).to(torch.bfloat16).contiguous()
+    K = masks.shape[0]
+    m = masks.reshape(K, -1).to(torch.uint8).contiguous()
+    if m.shape[1] != feats.shape[0]:
+        raise ValueError(f"masks cover {m.shape[1]} tokens, features have {feats.shape[0]}")
+    out = torch.empty((K, C), dtype=torch.bfloat16, device=feats.device)
+    with torch.cuda.device(feats.device):
+        cabi.check(lib.v3d_masked_token_mean(feats.data_ptr(), feats.shape[0], C, m.data_ptr(), K, out.data_ptr(),
+                                             cabi.stream_ptr(feats.device)), "v3d_masked_token_mean")
+    return out.to(token_features.dtype)
+
+
 def parse_world_position_embedding_type(kind: str) -> dict:
     """Substring semantics of llava/model/llava_arch.py:51-63, 395-429."""
     if "avg" in kind:
