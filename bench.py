@@ -180,7 +180,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -457,12 +457,26 @@ def run_ours(args):
                 line["cpu_baseline_c_oracle"] = cpu_c_oracle_leg()
             except Exception as e:  # the C oracle is optional for the bench
                 line["cpu_baseline_c_oracle"] = {"error": str(e)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line: dict) -> None:
+    """Write the one JSON line to the real stdout (see main: fd 1 is pointed at stderr while the bench runs, so that
+    banners printed by libraries -- e.g. NCCL's version line -- cannot end up next to it)."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT, data)
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
