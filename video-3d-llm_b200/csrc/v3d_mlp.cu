@@ -9,7 +9,8 @@
 // One persistent CTA per SM, 256 threads, warp-specialised:
 //   warp 0    TMA producer: W2 tiles (BLOCK_N rows x 64 k, 128-byte swizzle) through a ring of mbarriers
 //   warp 1    MMA issuer  : tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16; owns TMEM alloc
-//   warps 4-7 (a) build the A operand of an M tile (128 tokens x 512 hidden, bf16): Linear(3,512) + LayerNorm
+//   warps 4-11 (two per TMEM lane quadrant: one for each half of the k range / of an N tile's columns)
+//             (a) build the A operand of an M tile (128 tokens x 512 hidden, bf16): Linear(3,512) + LayerNorm
 //             + ReLU per token, one thread per token row = one TMEM lane, written with tcgen05.st straight
 //             into TENSOR MEMORY (256 columns: two bf16 per 32-bit cell), from where the MMA reads it;
 //             (b) epilogue: tcgen05.ld the fp32 accumulator, + bias, round to bf16, + tokens, store.
@@ -23,7 +24,8 @@
 
 namespace v3d {
 
-static constexpr int kMlpThreads = 256;
+static constexpr int kMlpThreads = 384;        // 12 warps: TMA, MMA, 2 spare, 8 producer/epilogue
+static constexpr int kEpiThreads = 256;        // warps 4-11
 static constexpr int kHidden = 512;          // nn.Linear(3, 512) of the reference module
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;           // 64 bf16 = 128 bytes = one swizzle atom
@@ -131,6 +133,8 @@ struct MlpParams {
 // shared memory map (dynamic, 1024-byte aligned base):
 //   [0, S*BN*128)            W2 ring: S stages of [BLOCK_N rows][128 B], SWIZZLE_128B
 //   then: float4 gw1[512], float2 gb[512], barriers, tmem base, LN moments, epilogue staging
+static constexpr int kMaxE = 8192;  // bias staged in shared memory
+
 template <int BLOCK_N>
 struct MlpSmem {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -143,8 +147,9 @@ struct MlpSmem {
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kOffMom = kOffTmem + 16;   // 16 floats: LayerNorm moment data
   static constexpr int kOffStage = (kOffMom + 64 + 127) & ~127;  // epilogue staging: 4 warps x 32 rows x BLOCK_N bf16
-  static constexpr int kStageBytesPerWarp = 32 * BLOCK_N * 2;
-  static constexpr int kTotal = kOffStage + 4 * kStageBytesPerWarp;
+  static constexpr int kStageBytesPerWarp = 32 * (BLOCK_N / 2) * 2;  // 32 rows x half an N tile, bf16
+  static constexpr int kOffBias = kOffStage + 8 * kStageBytesPerWarp;  // b2 (E floats, E <= kMaxE)
+  static constexpr int kTotal = kOffBias + kMaxE * 4;
 };
 
 template <int BLOCK_N>
@@ -203,6 +208,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
       s_mom[0] = a[0]; s_mom[1] = a[1]; s_mom[2] = a[2]; s_mom[3] = a[3];
     }
   }
+  float* s_bias = reinterpret_cast<float*>(smem + S::kOffBias);
+  for (int e = threadIdx.x; e < p.E; e += kMlpThreads) s_bias[e] = __ldg(p.b2 + e);
   for (int k = threadIdx.x; k < kHidden; k += kMlpThreads) {
     const float g = __ldg(p.gamma + k);
     // gamma folded into the first Linear: y_k = relu(rstd * (gw_k . c + gb_k) + (beta_k - rstd * mean * gamma_k))
@@ -215,10 +222,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
       mbar_init(b_full + i, 1);
       mbar_init(b_empty + i, 1);
     }
-    mbar_init(a_full, 128);
+    mbar_init(a_full, kEpiThreads);
     for (int i = 0; i < 2; ++i) {
       mbar_init(t_full + i, 1);
-      mbar_init(t_empty + i, 128);
+      mbar_init(t_empty + i, kEpiThreads);
     }
     mbar_fence_init();
   }
@@ -278,6 +285,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
   } else if (warp >= 4) {
     // ================= A producer + epilogue: thread = token row = TMEM lane =====================
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;  // which half of the k range (A production) / of the N tile's columns (epilogue)
     const int r = q * 32 + lane;       // row inside the M tile
     uint32_t acc_it = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
@@ -285,7 +293,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
       const bool row_ok = m < p.M;
       // L2 prefetch of the token rows by the TMA unit, one M tile ahead of their use in the epilogue (the very
       // first tile is requested here, before its A operand is built)
-      if (V3D_MLP_PREFETCH && threadIdx.x == 128 && p.tokens != nullptr) {
+      if (V3D_MLP_PREFETCH && threadIdx.x == 128 && p.tokens != nullptr) {  // (off by default)
         for (int t = (mt == (int)blockIdx.x ? mt : mt + (int)gridDim.x); t <= mt + (int)gridDim.x && t < m_tiles; t += gridDim.x) {
           const size_t rows = (size_t)min(kBlockM, p.M - t * kBlockM);
           const unsigned char* src = reinterpret_cast<const unsigned char*>(p.tokens + (size_t)t * kBlockM * p.E);
@@ -310,7 +318,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
       const float nmr = -mean * rstd;
       const uint32_t ta_row = tmem_base + ((uint32_t)(q * 32) << 16) + kTmemColsA;
 #pragma unroll 1
-      for (int kb = 0; kb < kNumKBlocks; ++kb) {  // 64 features = 32 TMEM columns per store
+      for (int kb = half * (kNumKBlocks / 2); kb < (half + 1) * (kNumKBlocks / 2); ++kb) {  // 64 features = 32 TMEM columns per store
         uint32_t packed[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -338,10 +346,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
       // conflict-free both ways) turns that into the row-per-thread order of the TMEM accumulator and back.
       // The token segment of the NEXT N tile is requested before the current accumulator is touched, so
       // its latency hides behind this tile's TMEM loads, math and stores.
-      constexpr int kChunks = BLOCK_N / 8;            // 16-byte chunks per row per N tile
+      constexpr int kHalfN = BLOCK_N / 2;             // columns of an N tile this warp owns
+      constexpr int kChunks = kHalfN / 8;             // 16-byte chunks per row
       constexpr int kRowsPerInst = 32 / kChunks;      // rows covered by one warp instruction
       constexpr int kInst = 32 / kRowsPerInst;        // warp instructions per N tile (= kChunks)
-      unsigned char* stage = smem + S::kOffStage + q * S::kStageBytesPerWarp;
+      unsigned char* stage = smem + S::kOffStage + (warp - 4) * S::kStageBytesPerWarp;
+      const int col0 = half * kHalfN;                // first column (inside the N tile) of this warp
       const int my_chunk = lane % kChunks, my_rsub = lane / kChunks;
       const int row0 = mt * kBlockM + q * 32;        // first global row of this warp
       const bool add = p.tokens != nullptr;
@@ -351,12 +361,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
 #pragma unroll
           for (int i = 0; i < kInst; ++i) {
             const int gr = row0 + i * kRowsPerInst + my_rsub;
-            if (gr < p.M) t[i] = ld_stream_v4(p.tokens + (size_t)gr * p.E + (size_t)nt * BLOCK_N + my_chunk * 8);
+            if (gr < p.M) t[i] = ld_stream_v4(p.tokens + (size_t)gr * p.E + (size_t)nt * BLOCK_N + col0 + my_chunk * 8);
           }
         }
       };
       auto stage_addr = [&](int row, int chunk) -> unsigned char* {
-        return stage + row * (BLOCK_N * 2) + ((chunk ^ (row & (kChunks - 1))) << 4);
+        return stage + row * (kHalfN * 2) + ((chunk ^ (row & (kChunks - 1))) << 4);
       };
       auto epilogue_tile = [&](const uint4 (&t)[kInst], int nt) {
         const uint32_t acc = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
@@ -367,13 +377,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
         }
         mbar_wait(t_full + acc, acc_phase);
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + col0;
 #pragma unroll
-        for (int cc = 0; cc < BLOCK_N / 32; ++cc) {
+        for (int cc = 0; cc < kHalfN / 32; ++cc) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + cc * 32, v);
           tmem_ld_wait();
-          const float* bias = p.b2 + nt * BLOCK_N + cc * 32;
+          const float* bias = s_bias + nt * BLOCK_N + col0 + cc * 32;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint32_t o[4];
@@ -384,7 +394,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
             for (int j = 0; j < 4; ++j) {
               const int e = i * 8 + 2 * j;
               // Linear output in bf16 (fp32 accumulate + bias, one rounding), then the bf16 add of llava_arch.py:515
-              __nv_bfloat162 pe = __floats2bfloat162_rn(__uint_as_float(v[e]) + __ldg(bias + e), __uint_as_float(v[e + 1]) + __ldg(bias + e + 1));
+              const float2 bb = *reinterpret_cast<const float2*>(bias + e);  // same address for the whole warp: broadcast
+              __nv_bfloat162 pe = __floats2bfloat162_rn(__uint_as_float(v[e]) + bb.x, __uint_as_float(v[e + 1]) + bb.y);
               if (add) {
                 const uint32_t tw = (j == 0) ? tk.x : (j == 1) ? tk.y : (j == 2) ? tk.z : tk.w;
                 pe = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&tw), pe);
@@ -395,13 +406,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
           }
         }
         tcgen05_fence_before();
-        mbar_arrive(t_empty + acc);  // 128 arrivals release the accumulator
+        mbar_arrive(t_empty + acc);  // 256 arrivals release the accumulator
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < kInst; ++i) {
           const int gr = row0 + i * kRowsPerInst + my_rsub;
           const uint4 val = *reinterpret_cast<const uint4*>(stage_addr(i * kRowsPerInst + my_rsub, my_chunk));
-          if (gr < p.M) st_stream_v4(p.out + (size_t)gr * p.E + (size_t)nt * BLOCK_N + my_chunk * 8, val);
+          if (gr < p.M) st_stream_v4(p.out + (size_t)gr * p.E + (size_t)nt * BLOCK_N + col0 + my_chunk * 8, val);
         }
         __syncwarp();
         ++acc_it;
@@ -475,6 +486,7 @@ extern "C" int v3d_pe_mlp(const float* coords, int M, int E, const float* w1, co
   V3D_REQUIRE(coords && w1 && b1 && gamma && beta && w2_bf16 && b2 && out, V3D_E_ARG, "v3d_pe_mlp: null pointer");
   V3D_REQUIRE(M >= 0 && E > 0, V3D_E_ARG, "v3d_pe_mlp: bad shape M=%d E=%d", M, E);
   V3D_REQUIRE(E % 64 == 0, V3D_E_UNSUPPORTED, "v3d_pe_mlp: embedding size %d is not a multiple of 64", E);
+  V3D_REQUIRE(E <= kMaxE, V3D_E_UNSUPPORTED, "v3d_pe_mlp: embedding size %d exceeds %d", E, kMaxE);
   V3D_REQUIRE(((reinterpret_cast<uintptr_t>(w2_bf16) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(tokens_in)) & 15) == 0,
               V3D_E_ALIGN, "v3d_pe_mlp: w2/out/tokens must be 16-byte aligned");
   if (M == 0) return V3D_OK;
