@@ -173,7 +173,7 @@ typedef struct v3d_mc_scene {
   uint64_t seed;            /* random.seed(seed) right before the greedy loop */
   /* workspace, caller-owned */
   int32_t* hash_table;      /* 4*hash_slots int32, 16-byte aligned: {i,j,k,index} per slot */
-  int hash_slots;           /* v3d_mc_hash_slots(n_pc): power of two >= 2*n_pc */
+  int hash_slots;           /* v3d_mc_hash_slots(n_pc): power of two >= 4*n_pc */
   int pad_;
   uint32_t* bitsets;        /* (n_frames, words), words = ceil(n_pc/32): frame coverage over pc order */
   /* output */

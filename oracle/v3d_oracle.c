@@ -299,60 +299,61 @@ void v3d_oracle_mc_voxel_ids(const float* world, size_t n_points, float voxel_si
   }
 }
 
-static inline uint64_t pack_key(int32_t i, int32_t j, int32_t k) {
-  /* 21 bits per axis, biased; callers range-check first */
-  return ((uint64_t)(uint32_t)(i + (1 << 20)) << 42) | ((uint64_t)(uint32_t)(j + (1 << 20)) << 21) |
-         (uint64_t)(uint32_t)(k + (1 << 20));
-}
-static inline int key_in_range(int32_t v) { return v >= -(1 << 20) && v < (1 << 20); }
-
+/* voxel triples are compared as Python compares tuples of ints: no range limit (a non-finite coordinate
+ * becomes INT32_MIN at :45 and is a set element like any other) */
 typedef struct {
-  uint64_t key;
+  int32_t v[3];
   int32_t idx;
 } kv_t;
+static int key_cmp(const int32_t* x, const int32_t* y) {
+  for (int a = 0; a < 3; ++a)
+    if (x[a] != y[a]) return x[a] < y[a] ? -1 : 1;
+  return 0;
+}
 static int kv_cmp(const void* a, const void* b) {
-  uint64_t x = ((const kv_t*)a)->key, y = ((const kv_t*)b)->key;
-  return x < y ? -1 : (x > y ? 1 : 0);
+  int c = key_cmp(((const kv_t*)a)->v, ((const kv_t*)b)->v);
+  if (c) return c;
+  /* duplicates of a voxel: the first index of the list comes first (set semantics keep one element) */
+  return ((const kv_t*)a)->idx < ((const kv_t*)b)->idx ? -1 : (((const kv_t*)a)->idx > ((const kv_t*)b)->idx);
 }
 
-/* Per-frame coverage bitsets over the mesh universe `pc` (n_pc unique int triples,
+/* Per-frame coverage bitsets over the mesh universe `pc` (n_pc int triples,
  * scripts/3d/preprocessing/convert_pcd_to_voxel.py:69-82): bit b of frame f is set iff voxel
- * pc[b] occurs among frame f's voxel ids, i.e. set(frame) & pc_voxel (:47-50, :75).
+ * pc[b] occurs among frame f's voxel ids, i.e. set(frame) & pc_voxel (:47-50, :75); a voxel listed twice
+ * in pc is one set element, represented by its first index.
  * ids: (F, n_px, 3) int32.  bitsets: (F, words) uint32, words = ceil(n_pc/32). */
 int v3d_oracle_mc_bitsets(const int32_t* ids, int F, size_t n_px, const int32_t* pc, int n_pc,
                           uint32_t* bitsets) {
   const int words = (n_pc + 31) / 32;
   kv_t* tab = (kv_t*)malloc(sizeof(kv_t) * (size_t)(n_pc > 0 ? n_pc : 1));
   if (!tab) return -1;
-  int n_tab = 0;
   for (int b = 0; b < n_pc; ++b) {
-    if (!(key_in_range(pc[3 * b]) && key_in_range(pc[3 * b + 1]) && key_in_range(pc[3 * b + 2]))) continue;
-    tab[n_tab].key = pack_key(pc[3 * b], pc[3 * b + 1], pc[3 * b + 2]);
-    tab[n_tab].idx = b;
-    ++n_tab;
+    memcpy(tab[b].v, pc + 3 * b, sizeof(int32_t) * 3);
+    tab[b].idx = b;
   }
-  qsort(tab, (size_t)n_tab, sizeof(kv_t), kv_cmp);
+  qsort(tab, (size_t)n_pc, sizeof(kv_t), kv_cmp);
   memset(bitsets, 0, sizeof(uint32_t) * (size_t)F * words);
 #pragma omp parallel for schedule(dynamic, 1)
   for (int f = 0; f < F; ++f) {
     uint32_t* bs = bitsets + (size_t)f * words;
-    uint64_t last = ~(uint64_t)0;
+    const int32_t* last = NULL;
     for (size_t i = 0; i < n_px; ++i) {
       const int32_t* v = ids + 3 * ((size_t)f * n_px + i);
-      if (!(key_in_range(v[0]) && key_in_range(v[1]) && key_in_range(v[2]))) continue;
-      uint64_t key = pack_key(v[0], v[1], v[2]);
-      if (key == last) continue;
-      last = key;
-      int lo = 0, hi = n_tab - 1;
-      while (lo <= hi) {
+      if (last && key_cmp(v, last) == 0) continue;
+      last = v;
+      int lo = 0, hi = n_pc - 1, hit = -1;
+      while (lo <= hi) { /* leftmost match = smallest index among duplicates */
         int mid = (lo + hi) >> 1;
-        if (tab[mid].key < key) lo = mid + 1;
-        else if (tab[mid].key > key) hi = mid - 1;
+        int c = key_cmp(tab[mid].v, v);
+        if (c < 0) lo = mid + 1;
         else {
-          int b = tab[mid].idx;
-          bs[b >> 5] |= 1u << (b & 31);
-          break;
+          if (c == 0) hit = mid;
+          hi = mid - 1;
         }
+      }
+      if (hit >= 0) {
+        int b = tab[hit].idx;
+        bs[b >> 5] |= 1u << (b & 31);
       }
     }
   }

@@ -416,6 +416,42 @@ def test_mc_sampler_bit_exact_vs_oracle(seed, n_frames, H, W):
     assert (res["n_all"], res["n_sel"]) == (n_all, n_sel)
 
 
+@pytest.mark.parametrize("case", ["half_voxel_shift", "odd_width", "int32_depth", "mixed_pose_kinds", "reciprocal", "huge_translation"])
+def test_mc_voxelize_guard_band_and_generic_paths(case):
+    """The voxeliser accepts an FMA estimate of the voxel id only outside a guard band around the half-integers
+    and runs the reference operator sequence otherwise (and for every frame that is not uint16 / rigid / 8-pixel
+    aligned).  Walls shifted onto half-voxel planes put 2-5 % of the pixels into the band."""
+    H, W = (60, 84) if case == "odd_width" else (240, 320)
+    sc = synthetic.make_scene(41, 6, n_total=6, H=H, W=W, device="cpu")
+    poses = sc.poses.clone()
+    depth = sc.depth
+    div_o, div_c = O.DIV_IEEE, cabi.DIV_IEEE
+    if case == "half_voxel_shift":
+        poses[:, :3, 3] += torch.tensor([0.05, 0.05, 0.05])
+    if case == "huge_translation":  # |t| beyond the range of the rounding trick: whole frames take the exact path
+        poses[3:, :3, 3] += torch.tensor([3.0e5, 0.0, 0.0])
+        poses[:3, :3, 3] += torch.tensor([1.0e4, 0.05, 0.0])
+    if case == "mixed_pose_kinds":
+        poses[1, 3, :] = torch.tensor([0.0, 0.0, 1e-3, 1.0])  # projective bottom row
+        poses[4, 0, 0] = float("nan")
+    if case == "int32_depth":
+        depth = torch.from_numpy(sc.depth_u16().astype(np.int32))
+    if case == "reciprocal":
+        div_o, div_c = O.DIV_RECIPROCAL, cabi.DIV_RECIPROCAL
+        poses[:, :3, 3] += torch.tensor([0.05, -0.05, 0.25])
+    d_np = sc.depth_u16() if case != "int32_depth" else depth.numpy()
+    world = O.unproject(sc.intrinsics.numpy(), poses.numpy(), d_np)
+    ids = O.mc_voxel_ids(world, 0.1, div_o)
+    uni = np.unique(ids[:, ::3, ::3].reshape(-1, 3), axis=0)
+    rng = np.random.default_rng(7)
+    pc = np.ascontiguousarray(uni[rng.permutation(len(uni))][: max(1, int(0.9 * len(uni)))]).astype(np.int32)
+    sampler = mc_sampling.MCSampler(device=DEV, div_mode=div_c)
+    plan = sampler.plan([{"depth": depth.to(DEV), "poses": poses.to(DEV), "intrinsics": sc.intrinsics.to(DEV),
+                          "pc_voxels": torch.from_numpy(pc).to(DEV), "seed": 5}])
+    sampler.run(plan, "voxelize")
+    np.testing.assert_array_equal(sampler.bitsets(plan, 0), O.mc_bitsets(ids, pc))
+
+
 def test_mc_sampler_batch_ragged_and_edge_cases():
     specs = [(31, 33, 120, 160), (32, 5, 120, 160), (33, 1, 120, 160), (34, 48, 120, 160)]
     scenes, refs = [], []

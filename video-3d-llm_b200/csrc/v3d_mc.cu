@@ -77,139 +77,329 @@ __device__ __forceinline__ int voxel_id(float w, const Divisor& voxel, float rcp
 }
 
 static constexpr int kPxPerThread = 8;
-
-// rint(RN(w / voxel)) without the division when it provably does not matter: t = w * r approximates the
-// IEEE quotient q within |t| * 2^-22 (r is within an ulp of 1/voxel, one more rounding for the product),
-// so if t is farther than that (with a 2x safety factor) from every half-integer, rint(q) == rint(t).
-// About one coordinate in 10^4 lands in the guard band and takes the exact division.
-__device__ __forceinline__ int voxel_id_fast(float w, const Divisor& voxel) {
-  const float t = __fmul_rn(w, voxel.r);
-  const float n = rintf(t);
-  const float margin = __fmaf_rn(fabsf(t), -0x1p-21f, 0.5f);
-  if (fabsf(__fsub_rn(t, n)) < margin && fabsf(t) < 1.0e9f) return (int)n;
-  return voxel_id(w, voxel, 0.f, V3D_DIV_IEEE);
-}
+#ifndef V3D_MC_MIN_BLOCKS
+#define V3D_MC_MIN_BLOCKS 4
+#endif
 
 struct Vox {
   int i, j, k;
 };
 __device__ __forceinline__ bool vox_eq(const Vox& a, const Vox& b) { return a.i == b.i && a.j == b.j && a.k == b.k; }
 
-// Candidate voxels of one block iteration are queued in shared memory so that the hash probes run with
-// dense lanes (a probe is a dependent chain of L2 loads; run inline, 2-4 of 32 lanes would be active).
+// Candidate voxels are queued in shared memory so that the hash probes run with dense lanes (a probe is a
+// dependent chain of L2 loads; run inline, 2-4 of 32 lanes would be active).
 __device__ __forceinline__ void mc_push(int3* s_q, int* s_qn, const Vox& v) {
   const int pos = atomicAdd(s_qn, 1);
   s_q[pos] = make_int3(v.i, v.j, v.k);
 }
 
+__device__ __forceinline__ void mc_probe(const int4* __restrict__ tab, uint32_t mask, uint32_t* __restrict__ bits, int i, int j, int k) {
+  const int b = hash_find(tab, mask, i, j, k);
+  if (b >= 0) {
+    const uint32_t m = 1u << (b & 31);
+    if (!(bits[b >> 5] & m)) atomicOr(bits + (b >> 5), m);
+  }
+}
+
+// ---- approximate-then-verify voxel ids ------------------------------------------------------------------
+// For a rigid pose the voxel coordinate of a pixel is, in real arithmetic,
+//     t_i = d * (A_i*um + B_i*vm + C_i) + D_i,   A_i = P_i0/(fx*scale*voxel), B_i = P_i1/(fy*scale*voxel),
+//                                                 C_i = P_i2/(scale*voxel),    D_i = P_i3/voxel,
+// six FMAs per pixel instead of the reference's 3 divisions + 12 pose operations + 3 divisions.  The reference
+// result q_i (every operation rounded to fp32, video_utils.py:57-65 then max_coverage_sampling.py:44) deviates
+// from t_i by at most u*(9*S + 3*|D_i|), u = 2^-24, S = d*(|A_i||um| + |B_i||vm| + |C_i|) (three roundings
+// per camera-space coordinate, four pose operations, the final division); the FMA evaluation with coefficients
+// rounded from fp64 deviates by at most u*(8*S + 2*|D_i|).  With k1 = 40u*max_i(|A_i|um_max + |B_i|vm_max +
+// |C_i|) and k0 = 12u*max_i|D_i| + 2^-20 (2.3x the sum of the two bounds) a pixel whose three t_i are farther than
+// k1*d + k0 from every half-integer has rint(q_i) == rint(t_i); the others (2-3 of 10^4 on ScanNet-shaped
+// scenes, tools/check_mc_guard_band.py) run the exact operator sequence.  rint is the 1.5*2^23 add/subtract
+// (round-half-even for |t| < 2^22, which the frame test guarantees for every uint16 depth).
+struct McSetup {
+  float coef[12];  // A_i, B_i, C_i, D_i for i = x, y, z
+  float k1, half_minus_k0;
+  int fast;
+  Camera cam;  // for the exact path
+  Divisor ds, dv;
+  float rcp;
+  int div_mode;
+};
+
+static constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+static constexpr int kWarpQueue = 32 + 32 * kPxPerThread;  // leftovers of the previous iteration + one iteration
+
+__device__ __noinline__ void mc_setup_frame(McSetup* s, const v3d_mc_scene& sc, int f, int H, int W, float depth_scale, float voxel, int div_mode,
+                               bool layout_ok) {
+  const Camera cam = load_camera(sc.poses, sc.intr, f);
+  s->cam = cam;
+  s->ds = make_divisor(depth_scale);
+  s->dv = make_divisor(voxel);
+  s->rcp = 1.0f / voxel;
+  s->div_mode = div_mode;
+  const double sv = (double)depth_scale * (double)voxel;
+  const double den[4] = {(double)cam.fx.b * sv, (double)cam.fy.b * sv, sv, (double)voxel};
+  const double um_max = fmax(fabs(0.0 - (double)cam.cx), fabs((double)(W - 1) - (double)cam.cx));
+  const double vm_max = fmax(fabs(0.0 - (double)cam.cy), fabs((double)(H - 1) - (double)cam.cy));
+  double r_max = 0.0, d_max = 0.0;
+  bool finite = true;
+  for (int i = 0; i < 3; ++i) {
+    double c[4];
+    for (int j = 0; j < 4; ++j) {
+      c[j] = (double)cam.P[4 * i + j] / den[j];
+      s->coef[4 * i + j] = (float)c[j];
+      finite = finite && (fabs(c[j]) < 1.0e30);
+    }
+    r_max = fmax(r_max, fabs(c[0]) * um_max + fabs(c[1]) * vm_max + fabs(c[2]));
+    d_max = fmax(d_max, fabs(c[3]));
+  }
+  const double u = 1.0 / 16777216.0;
+  const double k1 = 40.0 * u * r_max, k0 = 12.0 * u * d_max + 1.0 / 1048576.0;
+  s->k1 = (float)(k1 * 1.000001);
+  s->half_minus_k0 = (float)(0.5 - k0 * 1.000001);
+  // every |t| stays below 2^21 for any uint16 depth; divisors far inside the normal range (no overflow or
+  // underflow inside the reference sequence that the bound would not see)
+  s->fast = layout_ok && finite && cam.rigid && s->ds.ok && cam.fx.ok && cam.fy.ok && s->dv.ok && (65535.0 * r_max + d_max < 2097152.0) &&
+            (um_max < 1.0e6) && (vm_max < 1.0e6);
+}
+
+// exact operator sequence of one pixel (the guard-band pixels), probed right away
+__device__ __noinline__ void mc_exact_probe(const McSetup* s, const v3d_mc_scene* __restrict__ scp, int f, uint32_t raw, int col, int row) {
+  const Camera cam = s->cam;
+  float x, y, z;
+  unproject_px(cam, (float)raw, __fsub_rn((float)col, cam.cx), __fsub_rn((float)row, cam.cy), s->ds, x, y, z);
+  const int i = voxel_id(x, s->dv, s->rcp, s->div_mode), j = voxel_id(y, s->dv, s->rcp, s->div_mode), k = voxel_id(z, s->dv, s->rcp, s->div_mode);
+  mc_probe(reinterpret_cast<const int4*>(scp->hash_table), (uint32_t)scp->hash_slots - 1u,
+           scp->bitsets + (size_t)f * ((scp->n_pc + 31) / 32), i, j, k);
+}
+
+// Append (x,y,z) to the warp's queue if it differs from (px,py,pz): predicated, no branch (some lane of the warp
+// appends on 99 % of the steps).
+__device__ __forceinline__ void mc_push_if_changed(uint32_t q_addr, uint32_t cnt_addr, float x, float y, float z, float px, float py,
+                                                   float pz) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 pos, a;\n\t"
+      "mov.u32 pos, 0;\n\t"
+      "setp.neu.f32 p, %2, %5;\n\t"
+      "setp.neu.or.f32 p, %3, %6, p;\n\t"
+      "setp.neu.or.f32 p, %4, %7, p;\n\t"
+      "@p atom.shared.add.u32 pos, [%1], 1;\n\t"
+      "mad.lo.u32 a, pos, 12, %0;\n\t"
+      "@p st.shared.f32 [a], %2;\n\t"
+      "@p st.shared.f32 [a+4], %3;\n\t"
+      "@p st.shared.f32 [a+8], %4;\n\t"
+      "}" ::"r"(q_addr),
+      "r"(cnt_addr), "f"(x), "f"(y), "f"(z), "f"(px), "f"(py), "f"(pz)
+      : "memory");
+}
+
+struct McPixel {
+  float n[3];
+  bool ok;
+};
+// voxel estimate of one pixel: n = rint(t), ok = every t is outside the guard band
+__device__ __forceinline__ McPixel mc_estimate(float df, const float (&ray)[3], const float (&D)[3], float k1n, float hmk0) {
+  McPixel r;
+  const float m = __fmaf_rn(df, k1n, hmk0);
+  r.ok = true;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float t = __fmaf_rn(df, ray[i], D[i]);
+    r.n[i] = __fsub_rn(__fadd_rn(t, kMagic), kMagic);
+    r.ok = r.ok && (fabsf(__fsub_rn(t, r.n[i])) < m);
+  }
+  return r;
+}
+
+// One warp voxelises rows [rw0, rw1) of frame f: 8 pixels per lane from one 128-bit load, run-length dedup
+// against the previous pixel (for the first pixel of a group: the left lane's last pixel, re-estimated from its
+// shuffled depth), candidates appended to the warp's own shared-memory queue (no block barriers) and probed
+// 32 at a time from the top of the queue.  A guard-band pixel is entered as NaN (never equal to a neighbour, skipped
+// by the probes) and evaluated exactly after the eight steps.
+__device__ __forceinline__ void mc_rows_fast(const McSetup* __restrict__ s, const v3d_mc_scene* __restrict__ scp, int f, int H, int W,
+                                             int rw0, int rw1, float* __restrict__ q, int* __restrict__ q_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int gpr = W / kPxPerThread;
+  const int n_groups = (rw1 - rw0) * gpr;
+  if (n_groups <= 0) return;
+  const uint32_t gpr_magic = 0xffffffffu / (uint32_t)gpr + 1u;  // g / gpr == umulhi(g, magic) for g < 2^16
+  float A[3], B[3], Cc[3], D[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    A[i] = s->coef[4 * i];
+    B[i] = s->coef[4 * i + 1];
+    Cc[i] = s->coef[4 * i + 2];
+    D[i] = s->coef[4 * i + 3];
+  }
+  const float k1n = -s->k1, hmk0 = s->half_minus_k0, cx = s->cam.cx, cy = s->cam.cy;
+  uint32_t q_addr = smem_u32(q), cnt_addr = smem_u32(q_cnt);
+  // opaque to the compiler: keep these in registers instead of re-deriving them from %tid at every use
+  asm volatile("" : "+r"(q_addr), "+r"(cnt_addr));
+  const uint16_t* frame = reinterpret_cast<const uint16_t*>(scp->depth) + ((size_t)f * H + rw0) * W;
+  // lanes past the end of a ragged last iteration redo the last group (duplicate candidates are harmless)
+  int g = min(lane, n_groups - 1);
+  int r = (int)__umulhi((uint32_t)g, gpr_magic);
+  int c0 = (g - r * gpr) * kPxPerThread;
+  uint4 w = ld_stream_v4(frame + (size_t)r * W + c0);
+  for (int g0 = 0; g0 < n_groups; g0 += 32) {
+    const uint32_t w4[4] = {w.x, w.y, w.z, w.w};
+    const float vm = __fsub_rn((float)(rw0 + r), cy), um0 = __fsub_rn((float)c0, cx);
+    float ray0[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ray0[i] = __fmaf_rn(A[i], um0, __fmaf_rn(B[i], vm, Cc[i]));
+    // previous pixel of the group's first pixel: the left lane's last pixel (same row when c0 > 0)
+    float px, py, pz;
+    {
+      const uint32_t left = __shfl_up_sync(0xffffffffu, w4[3], 1);
+      const float df = (float)(left >> 16);
+      float ray[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ray[i] = __fsub_rn(ray0[i], A[i]);
+      const McPixel p = mc_estimate(df, ray, D, k1n, hmk0);
+      const bool usable = p.ok && lane != 0 && c0 != 0;
+      px = usable ? p.n[0] : __int_as_float(0x7fc00000);
+      py = p.n[1];
+      pz = p.n[2];
+    }
+    uint32_t slow = 0;
+#pragma unroll
+    for (int e = 0; e < kPxPerThread; ++e) {
+      const float df = (float)((e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xffffu));  // I2F.U16 reads either half
+      float ray[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ray[i] = __fmaf_rn(A[i], (float)e, ray0[i]);
+      const McPixel p = mc_estimate(df, ray, D, k1n, hmk0);
+      const float nx = p.ok ? p.n[0] : __int_as_float(0x7fc00000);
+      slow |= p.ok ? 0u : (1u << e);
+      mc_push_if_changed(q_addr, cnt_addr, nx, p.n[1], p.n[2], px, py, pz);
+      px = nx;
+      py = p.n[1];
+      pz = p.n[2];
+    }
+    if (slow) {  // 2-3 pixels in 10^4: exact operator sequence, probed directly
+#pragma unroll 1
+      for (uint32_t rest = slow; rest; rest &= rest - 1) {
+        const int e = __ffs(rest) - 1;
+        const uint32_t lo = (e & 4) ? w4[2] : w4[0], hi = (e & 4) ? w4[3] : w4[1];
+        const uint32_t word = (e & 2) ? hi : lo;
+        mc_exact_probe(s, scp, f, (e & 1) ? (word >> 16) : (word & 0xffffu), c0 + e, rw0 + r);
+      }
+    }
+    // next iteration's position; its load is in flight during the probes below
+    const bool last = g0 + 32 >= n_groups;
+    if (!last) {
+      g = min(g0 + 32 + lane, n_groups - 1);
+      r = (int)__umulhi((uint32_t)g, gpr_magic);
+      c0 = (g - r * gpr) * kPxPerThread;
+      w = ld_stream_v4(frame + (size_t)r * W + c0);
+    }
+    __syncwarp();
+    // probe whole batches of 32 from the top of the queue; fewer than 32 candidates stay for the next iteration
+    const int qn = *q_cnt;
+    const int keep = last ? 0 : (qn & 31);
+    if (qn > keep) {
+      const int4* tab = reinterpret_cast<const int4*>(scp->hash_table);
+      const uint32_t mask = (uint32_t)scp->hash_slots - 1u;
+      uint32_t* bits = scp->bitsets + (size_t)f * ((scp->n_pc + 31) / 32);
+      for (int i = keep + lane; i < qn; i += 32) {
+        const float* v = q + 3 * i;
+        const float vx = v[0];
+        if (vx == vx) mc_probe(tab, mask, bits, (int)vx, (int)v[1], (int)v[2]);
+      }
+      __syncwarp();
+      if (lane == 0) *q_cnt = keep;
+    }
+    __syncwarp();
+  }
+}
+
 template <int DT>
-__global__ void __launch_bounds__(kMcThreads) k_mc_voxelize(const v3d_mc_scene* __restrict__ scenes, int H, int W,
+__device__ __forceinline__ void mc_slab_generic(const v3d_mc_scene& sc, const McSetup* __restrict__ s, int f, int H, int W, int r0, int r1,
+                                                int3* s_q, int* s_qn, int& phase, const int4* __restrict__ tab, uint32_t mask,
+                                                uint32_t* __restrict__ bits) {
+  const Camera cam = s->cam;
+  const Divisor ds = s->ds, dv = s->dv;
+  const float rcp = s->rcp;
+  const int div_mode = s->div_mode;
+  const int groups_per_row = (W + kPxPerThread - 1) / kPxPerThread;
+  const int lane = threadIdx.x & 31;
+  const int n_groups = (r1 - r0) * groups_per_row;
+  // all threads of the block iterate together (barriers and shuffles below); whole warps past the end idle
+  // two queue counters used alternately: the idle one is cleared between the barriers of an iteration
+  for (int g0 = 0; g0 < n_groups; g0 += kMcThreads, phase ^= 1) {
+    int* cnt = s_qn + phase;
+    const int g = g0 + threadIdx.x;
+    const bool valid = g < n_groups;
+    Vox first = {0x7fffffff, 0x7fffffff, 0x7fffffff}, prev = first;
+    int n_px = 0, c0 = 0;
+    if (valid) {
+      const int gr = g / groups_per_row;
+      const int r = r0 + gr;
+      c0 = (g - gr * groups_per_row) * kPxPerThread;
+      n_px = min(kPxPerThread, W - c0);
+      const float vm = __fsub_rn((float)r, cam.cy);
+      const size_t base = ((size_t)f * H + r) * W + c0;
+#pragma unroll 1
+      for (int e = 0; e < n_px; ++e) {
+        float x, y, z;
+        unproject_px(cam, load_depth<DT>(sc.depth, base + e), __fsub_rn((float)(c0 + e), cam.cx), vm, ds, x, y, z);
+        const Vox v = {voxel_id(x, dv, rcp, div_mode), voxel_id(y, dv, rcp, div_mode), voxel_id(z, dv, rcp, div_mode)};
+        if (e == 0) first = v;
+        else if (!vox_eq(v, prev)) mc_push(s_q, cnt, v);
+        prev = v;
+      }
+    }
+    Vox left;
+    left.i = __shfl_up_sync(0xffffffffu, prev.i, 1);
+    left.j = __shfl_up_sync(0xffffffffu, prev.j, 1);
+    left.k = __shfl_up_sync(0xffffffffu, prev.k, 1);
+    const int left_px = __shfl_up_sync(0xffffffffu, n_px, 1);
+    if (n_px > 0 && (lane == 0 || left_px != kPxPerThread || c0 == 0 || !vox_eq(first, left))) mc_push(s_q, cnt, first);
+    __syncthreads();
+    const int qn = *cnt;
+    if (threadIdx.x == 0) s_qn[phase ^ 1] = 0;
+    for (int i = threadIdx.x; i < qn; i += kMcThreads) {
+      const int3 v = s_q[i];
+      mc_probe(tab, mask, bits, v.x, v.y, v.z);
+    }
+    __syncthreads();
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kMcThreads, V3D_MC_MIN_BLOCKS) k_mc_voxelize(const v3d_mc_scene* __restrict__ scenes, int H, int W,
                                                             float depth_scale, float voxel, int div_mode, int slabs_per_frame,
                                                             int rows_per_slab) {
   const v3d_mc_scene sc = scenes[blockIdx.y];
   const int words = (sc.n_pc + 31) / 32;
   const uint32_t mask = (uint32_t)sc.hash_slots - 1u;
   const int4* tab = reinterpret_cast<const int4*>(sc.hash_table);
-  const float rcp = 1.0f / voxel;
-  const Divisor ds = make_divisor(depth_scale);
-  const Divisor dv = make_divisor(voxel);
-  const int groups_per_row = (W + kPxPerThread - 1) / kPxPerThread;
-  const int lane = threadIdx.x & 31;
-  __shared__ int3 s_q[kMcThreads * kPxPerThread];  // 24 KB
-  __shared__ int s_qn;
-  if (threadIdx.x == 0) s_qn = 0;
-  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  __shared__ __align__(16) float s_q[(kMcThreads / 32) * kWarpQueue * 3];  // 27 KB; the generic path uses it as one int3 queue
+  __shared__ McSetup s_set;
+  __shared__ int s_qn[2];
+  __shared__ int s_wqn[kMcThreads / 32];
+  int phase = 0;
+  static_assert(sizeof(float) * (kMcThreads / 32) * kWarpQueue * 3 >= sizeof(int3) * kMcThreads * kPxPerThread, "queue size");
+  // 8 pixels per 128-bit load: rows must be whole groups and 16-byte aligned
+  const bool layout_ok = DT == V3D_DEPTH_U16 && (W % kPxPerThread) == 0 && (reinterpret_cast<uintptr_t>(sc.depth) & 15) == 0;
+  const int rows_per_warp = (rows_per_slab + kMcThreads / 32 - 1) / (kMcThreads / 32);
+  if (threadIdx.x == 0) s_qn[0] = s_qn[1] = 0;
+  if (threadIdx.x < kMcThreads / 32) s_wqn[threadIdx.x] = 0;
   for (int item = blockIdx.x; item < sc.n_frames * slabs_per_frame; item += gridDim.x) {
     const int f = item / slabs_per_frame, r0 = (item - f * slabs_per_frame) * rows_per_slab;
     const int r1 = min(r0 + rows_per_slab, H);
-    const Camera cam = load_camera(sc.poses, sc.intr, f);
-    // uint16 depth + rigid pose + divisors well inside the normal range: branch-free unprojection (see
-    // pool_rows_fast in v3d_frontend.cu) and division-free voxel ids
-    const bool frame_fast = DT == V3D_DEPTH_U16 && div_mode == V3D_DIV_IEEE && cam.rigid && ds.ok && cam.fx.ok && cam.fy.ok &&
-                            ds.b > 0.f && dv.ok;
+    __syncthreads();  // the previous item's readers of s_set are done
+    if (threadIdx.x == 0) mc_setup_frame(&s_set, sc, f, H, W, depth_scale, voxel, div_mode, layout_ok);
+    __syncthreads();
     uint32_t* bits = sc.bitsets + (size_t)f * words;
-    const int n_groups = (r1 - r0) * groups_per_row;
-    // all threads of the block iterate together (barriers and shuffles below); whole warps past the end idle
-    for (int g0 = 0; g0 < n_groups; g0 += kMcThreads) {
-      const int g = g0 + threadIdx.x;
-      const bool valid = g < n_groups;
-      Vox first = {0x7fffffff, 0x7fffffff, 0x7fffffff}, prev = first;
-      int n_px = 0, c0 = 0;
-      if (valid) {
-        const int gr = g / groups_per_row;
-        const int r = r0 + gr;
-        c0 = (g - gr * groups_per_row) * kPxPerThread;
-        n_px = min(kPxPerThread, W - c0);
-        const float vm = __fsub_rn((float)r, cam.cy);
-        const size_t base = ((size_t)f * H + r) * W + c0;
-        bool fast = false;
-        if constexpr (DT == V3D_DEPTH_U16) {
-          const float um0 = __fsub_rn((float)c0, cam.cx), um7 = __fsub_rn((float)(c0 + kPxPerThread - 1), cam.cx);
-          // (u - cx) of the 8 columns lies between um0 and um7: all are in the fast range unless that
-          // interval comes within 2^-20 of zero
-          fast = frame_fast && n_px == kPxPerThread && ((base * 2 + reinterpret_cast<uintptr_t>(sc.depth)) & 15) == 0 &&
-                 fabsf(vm) >= 0x1p-20f && fabsf(vm) <= 0x1p20f && fabsf(um0) <= 0x1p20f && fabsf(um7) <= 0x1p20f &&
-                 (um0 > 0x1p-20f || um7 < -0x1p-20f);
-        }
-        if (fast) {
-          const uint4 q = ld_stream_v4(reinterpret_cast<const uint16_t*>(sc.depth) + base);
-          const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-          for (int e = 0; e < kPxPerThread; ++e) {
-            const uint32_t raw = (e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xffffu);
-            const float df = (float)raw;
-            const bool nz = raw != 0;
-            const float um = __fsub_rn((float)(c0 + e), cam.cx);
-            float q0 = __fmul_rn(df, ds.r);
-            float q1 = __fmaf_rn(ds.r, __fmaf_rn(-ds.b, q0, df), q0);
-            const float cz = nz ? q1 : q0;
-            const float ax = __fmul_rn(um, cz);
-            q0 = __fmul_rn(ax, cam.fx.r);
-            q1 = __fmaf_rn(cam.fx.r, __fmaf_rn(-cam.fx.b, q0, ax), q0);
-            const float cx_ = nz ? q1 : q0;
-            const float ay = __fmul_rn(vm, cz);
-            q0 = __fmul_rn(ay, cam.fy.r);
-            q1 = __fmaf_rn(cam.fy.r, __fmaf_rn(-cam.fy.b, q0, ay), q0);
-            const float cy_ = nz ? q1 : q0;
-            const float x = __fadd_rn(__fmaf_rn(cam.P[2], cz, __fmaf_rn(cam.P[1], cy_, __fmul_rn(cam.P[0], cx_))), cam.P[3]);
-            const float y = __fadd_rn(__fmaf_rn(cam.P[6], cz, __fmaf_rn(cam.P[5], cy_, __fmul_rn(cam.P[4], cx_))), cam.P[7]);
-            const float z = __fadd_rn(__fmaf_rn(cam.P[10], cz, __fmaf_rn(cam.P[9], cy_, __fmul_rn(cam.P[8], cx_))), cam.P[11]);
-            const Vox v = {voxel_id_fast(x, dv), voxel_id_fast(y, dv), voxel_id_fast(z, dv)};
-            if (e == 0) first = v;
-            else if (!vox_eq(v, prev)) mc_push(s_q, &s_qn, v);
-            prev = v;
-          }
-        } else {
-#pragma unroll 1
-          for (int e = 0; e < n_px; ++e) {
-            float x, y, z;
-            unproject_px(cam, load_depth<DT>(sc.depth, base + e), __fsub_rn((float)(c0 + e), cam.cx), vm, ds, x, y, z);
-            const Vox v = {voxel_id(x, dv, rcp, div_mode), voxel_id(y, dv, rcp, div_mode), voxel_id(z, dv, rcp, div_mode)};
-            if (e == 0) first = v;
-            else if (!vox_eq(v, prev)) mc_push(s_q, &s_qn, v);
-            prev = v;
-          }
-        }
+    if (s_set.fast) {
+      if constexpr (DT == V3D_DEPTH_U16) {
+        const int rw0 = r0 + warp * rows_per_warp;
+        mc_rows_fast(&s_set, scenes + blockIdx.y, f, H, W, rw0, min(rw0 + rows_per_warp, r1), s_q + warp * kWarpQueue * 3, s_wqn + warp);
       }
-      // the first pixel of a group is a duplicate if it equals the last pixel of the left neighbour lane
-      Vox left;
-      left.i = __shfl_up_sync(0xffffffffu, prev.i, 1);
-      left.j = __shfl_up_sync(0xffffffffu, prev.j, 1);
-      left.k = __shfl_up_sync(0xffffffffu, prev.k, 1);
-      const int left_px = __shfl_up_sync(0xffffffffu, n_px, 1);
-      if (n_px > 0 && (lane == 0 || left_px != kPxPerThread || c0 == 0 || !vox_eq(first, left))) mc_push(s_q, &s_qn, first);
-      __syncthreads();
-      const int qn = s_qn;
-      for (int i = threadIdx.x; i < qn; i += kMcThreads) {
-        const int3 v = s_q[i];
-        const int b = hash_find(tab, mask, v.x, v.y, v.z);
-        if (b >= 0) {
-          const uint32_t m = 1u << (b & 31);
-          if (!(bits[b >> 5] & m)) atomicOr(bits + (b >> 5), m);
-        }
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) s_qn = 0;
+    } else {
+      mc_slab_generic<DT>(sc, &s_set, f, H, W, r0, r1, reinterpret_cast<int3*>(s_q), s_qn, phase, tab, mask, bits);
     }
   }
 }
@@ -423,8 +613,8 @@ static int launch_voxelize(const v3d_mc_scene* dev_scenes, int n_scenes, int max
     bx = bx < 1 ? 1 : (bx > 1024 ? 1024 : bx);
     k_mc_build<<<dim3(bx, n_scenes), kMcThreads, 0, s>>>(dev_scenes);
   }
-  // 16 rows x (640/8) groups = 1280 = 5 full block iterations for ScanNet-shaped depth
-  const int rows_per_slab = 16;
+  // 48 rows = 6 per warp; 6 x (640/8) groups = 15 full warp iterations for ScanNet-shaped depth
+  const int rows_per_slab = 48;
   const int slabs = (H + rows_per_slab - 1) / rows_per_slab;
   // enough CTAs per scene to fill the machine a few times over, grid.y = scene
   long want = ((long)num_sms() * 16 + n_scenes - 1) / n_scenes;
@@ -460,7 +650,7 @@ extern "C" {
 
 int v3d_mc_hash_slots(int n_pc) {
   int s = 64;
-  while (s < 2 * n_pc) s <<= 1;
+  while (s < 4 * (long long)n_pc && s < (1 << 30)) s <<= 1;  // load factor <= 0.25: probe chains of 1-2 slots
   return s;
 }
 
