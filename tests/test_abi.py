@@ -34,7 +34,7 @@ def test_version_and_pure_host_helpers():
     assert lib.v3d_version() == 100
     assert [lib.v3d_pool_points(m) for m in range(5)] == [1, 2, 9, 5, 1]
     assert lib.v3d_pool_points(99) == -1
-    assert lib.v3d_mc_hash_slots(0) == 64 and lib.v3d_mc_hash_slots(1000) == 2048
+    assert lib.v3d_mc_hash_slots(0) == 64 and lib.v3d_mc_hash_slots(1000) == 4096
     assert lib.v3d_pe_table_bytes(3584, 1, 301, cabi.BF16) == (3 * 302 + 1) * 1208 * 2
     assert lib.v3d_pe_table_bytes(12, 1, 301, cabi.BF16) == 0  # nf < 8 is unsupported, reported as 0 bytes
 
