@@ -8,6 +8,7 @@
 //   k_mc_greedy   : one CTA per scene; each round = popcount(bits & ~used) per remaining frame,
 //                   argmax with the ascending-order tie list (:72-82), CPython-compatible
 //                   MT19937 random.choice (:84), used |= bits (:86) -- bit-exact selection.
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
 #include "v3d_common.cuh"
@@ -16,6 +17,7 @@ namespace v3d {
 
 static constexpr int kMcThreads = 256;
 static constexpr int kGreedyThreads = 512;
+static constexpr int kGreedyCluster = 8;  // CTAs per scene (portable cluster size)
 static constexpr int kMaxWordsSmem = 16384;  // `used` bitset lives in shared memory (64 KB)
 
 __device__ __forceinline__ uint32_t hash3(int i, int j, int k) {
@@ -471,52 +473,84 @@ __device__ uint32_t mt_randbelow(Mt* s, uint32_t n) {
   return r;
 }
 
-__global__ void __launch_bounds__(kGreedyThreads) k_mc_greedy(const v3d_mc_scene* __restrict__ scenes, int max_pick) {
+// One cluster of kGreedyCluster CTAs per scene.  CTA `rank` owns a contiguous block of frames whose coverage
+// bitsets it keeps in shared memory for all rounds (when they fit); every CTA keeps its own copy of `used` and of
+// the MT19937 state, so a round needs one exchange only: the owners' gains, read through distributed shared
+// memory after one cluster barrier (double-buffered by round parity), after which every CTA derives the same
+// pick (max gain, ascending tie list, random.choice).
+__global__ void __launch_bounds__(kGreedyThreads) k_mc_greedy(const v3d_mc_scene* __restrict__ scenes, int max_pick, int per_max,
+                                                              int bits_in_smem) {
+  namespace cg = cooperative_groups;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const v3d_mc_scene sc = scenes[blockIdx.x];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const v3d_mc_scene sc = scenes[blockIdx.x / kGreedyCluster];
   const int F = sc.n_frames, words = (sc.n_pc + 31) / 32;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, n_warps = kGreedyThreads / 32;
-  uint32_t* s_used = reinterpret_cast<uint32_t*>(smem_raw);
-  int* s_gain = reinterpret_cast<int*>(s_used + words);  // -2 = already taken
-  Mt* s_mt = reinterpret_cast<Mt*>(s_gain + F);
+  const int per = max((F + kGreedyCluster - 1) / kGreedyCluster, 1);
+  const int f_lo = min(F, rank * per), nf = min(F, f_lo + per) - f_lo;
+  // layout (identical in every CTA of the cluster: remote addresses are computed from the local ones)
+  int* s_gain_own = reinterpret_cast<int*>(smem_raw);              // [2][per_max], -2 = already taken
+  int* s_part = s_gain_own + 2 * per_max;                            // [1] partial popcount of the union
+  int* s_taken = s_part + 1;                                         // [per_max]
+  int* s_gain = s_taken + per_max;                                   // [F] gathered gains
+  uint32_t* s_used = reinterpret_cast<uint32_t*>(s_gain + kGreedyCluster * per_max);
+  Mt* s_mt = reinterpret_cast<Mt*>(s_used + words);
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_mt + 1);          // [nf][words] when bits_in_smem
   __shared__ int s_red[kGreedyThreads / 32];
-  __shared__ int s_pick, s_max, s_n_all;
+  __shared__ int s_pick, s_max;
 
   for (int w = t; w < words; w += kGreedyThreads) s_used[w] = 0u;
-  for (int f = t; f < F; f += kGreedyThreads) s_gain[f] = 0;
-  for (int i = t; i < V3D_MC_RECORD_INTS; i += kGreedyThreads) sc.record[i] = (i < 2 * V3D_MC_MAX_PICK) ? -1 : 0;
-  if (t == 0) mt_seed(s_mt, sc.seed);  // overlaps with the union popcount below on the other warps
-
-  // n_all = |(union of frames) & pc| (:102): popcount of the OR over frames
-  int cnt = 0;
-  if (t >= 32 || F == 0) {
-    for (int w = t - (F ? 32 : 0); w < words; w += kGreedyThreads - (F ? 32 : 0)) {
+  for (int f = t; f < per_max; f += kGreedyThreads) s_taken[f] = 0;
+  if (rank == 0)
+    for (int i = t; i < V3D_MC_RECORD_INTS; i += kGreedyThreads) sc.record[i] = (i < 2 * V3D_MC_MAX_PICK) ? -1 : 0;
+  if (t == 0) mt_seed(s_mt, sc.seed);  // overlaps with the loads below on the other warps
+  const uint32_t* g_bits = sc.bitsets + (size_t)f_lo * words;
+  const uint32_t* my_bits = g_bits;
+  if (bits_in_smem) {
+    for (int i = t; i < nf * words; i += kGreedyThreads) s_bits[i] = g_bits[i];
+    my_bits = s_bits;
+  }
+  // n_all = |(union of frames) & pc| (:102): this CTA counts its slice of the words of the OR over all frames
+  {
+    const int wper = (words + kGreedyCluster - 1) / kGreedyCluster;
+    const int w_hi = min(words, (rank + 1) * wper);
+    int cnt = 0;
+    for (int w = rank * wper + t; w < w_hi; w += kGreedyThreads) {
       uint32_t u = 0u;
       for (int f = 0; f < F; ++f) u |= sc.bitsets[(size_t)f * words + w];
       cnt += __popc(u);
     }
-  }
-  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0) s_red[warp] = cnt;
-  __syncthreads();
-  if (t == 0) {
-    int tot = 0;
-    for (int i = 0; i < n_warps; ++i) tot += s_red[i];
-    s_n_all = tot;
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_red[warp] = cnt;
+    __syncthreads();
+    if (t == 0) {
+      int tot = 0;
+      for (int i = 0; i < n_warps; ++i) tot += s_red[i];
+      *s_part = tot;
+    }
   }
   __syncthreads();
 
   int n_picked = 0;
   const int rounds = min(F, max_pick);
   for (int round = 0; round < rounds; ++round) {
-    // gains of the remaining frames: one warp per frame, lanes stride the words
-    for (int f = warp; f < F; f += n_warps) {
-      if (s_gain[f] == -2) continue;
-      const uint32_t* bs = sc.bitsets + (size_t)f * words;
-      int g = 0;
-      for (int w = lane; w < words; w += 32) g += __popc(bs[w] & ~s_used[w]);
-      for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-      if (lane == 0) s_gain[f] = g;
+    int* own = s_gain_own + (round & 1) * per_max;
+    // gains of this CTA's remaining frames: one warp per frame, lanes stride the words
+    for (int fl = warp; fl < nf; fl += n_warps) {
+      int g = -2;
+      if (!s_taken[fl]) {
+        const uint32_t* bs = my_bits + (size_t)fl * words;
+        g = 0;
+        for (int w = lane; w < words; w += 32) g += __popc(bs[w] & ~s_used[w]);
+        for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+      }
+      if (lane == 0) own[fl] = g;
+    }
+    cluster.sync();
+    for (int f = t; f < F; f += kGreedyThreads) {
+      const int c = f / per;
+      s_gain[f] = cluster.map_shared_rank(own, c)[f - c * per];
     }
     __syncthreads();
     if (warp == 0) {
@@ -551,30 +585,37 @@ __global__ void __launch_bounds__(kGreedyThreads) k_mc_greedy(const v3d_mc_scene
     }
     __syncthreads();
     const int pick = s_pick;
-    const uint32_t* bs = sc.bitsets + (size_t)pick * words;
+    const uint32_t* bs = (bits_in_smem && pick >= f_lo && pick < f_lo + nf) ? s_bits + (size_t)(pick - f_lo) * words
+                                                                            : sc.bitsets + (size_t)pick * words;
     for (int w = t; w < words; w += kGreedyThreads) s_used[w] |= bs[w];
     if (t == 0) {
-      sc.record[n_picked] = pick;
-      sc.record[V3D_MC_MAX_PICK + n_picked] = s_max;
-      s_gain[pick] = -2;
+      if (pick >= f_lo && pick < f_lo + nf) s_taken[pick - f_lo] = 1;
+      if (rank == 0) {
+        sc.record[n_picked] = pick;
+        sc.record[V3D_MC_MAX_PICK + n_picked] = s_max;
+      }
     }
     ++n_picked;
     __syncthreads();
   }
-  // n_sel = |used & pc| (:103)
-  cnt = 0;
-  for (int w = t; w < words; w += kGreedyThreads) cnt += __popc(s_used[w]);
-  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  __syncthreads();
-  if (lane == 0) s_red[warp] = cnt;
-  __syncthreads();
-  if (t == 0) {
-    int tot = 0;
-    for (int i = 0; i < n_warps; ++i) tot += s_red[i];
-    sc.record[2 * V3D_MC_MAX_PICK + 0] = n_picked;
-    sc.record[2 * V3D_MC_MAX_PICK + 1] = s_n_all;
-    sc.record[2 * V3D_MC_MAX_PICK + 2] = tot;
+  cluster.sync();  // every CTA's s_part is written; nobody reads remote gains any more
+  if (rank == 0) {
+    // n_sel = |used & pc| (:103)
+    int cnt = 0;
+    for (int w = t; w < words; w += kGreedyThreads) cnt += __popc(s_used[w]);
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_red[warp] = cnt;
+    __syncthreads();
+    if (t == 0) {
+      int tot = 0, n_all = 0;
+      for (int i = 0; i < n_warps; ++i) tot += s_red[i];
+      for (int c = 0; c < kGreedyCluster; ++c) n_all += *cluster.map_shared_rank(s_part, c);
+      sc.record[2 * V3D_MC_MAX_PICK + 0] = n_picked;
+      sc.record[2 * V3D_MC_MAX_PICK + 1] = n_all;
+      sc.record[2 * V3D_MC_MAX_PICK + 2] = tot;
+    }
   }
+  cluster.sync();  // shared memory of a CTA must outlive the remote reads of it
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -635,10 +676,27 @@ static int launch_greedy(const v3d_mc_scene* dev_scenes, int n_scenes, int max_f
   V3D_REQUIRE(max_pick > 0 && max_pick <= V3D_MC_MAX_PICK, V3D_E_ARG, "mc: max_pick=%d must be in [1,%d]", max_pick, V3D_MC_MAX_PICK);
   const int words = (max_pc + 31) / 32;
   V3D_REQUIRE(words <= kMaxWordsSmem, V3D_E_UNSUPPORTED, "mc: universe of %d voxels exceeds the %d supported", max_pc, kMaxWordsSmem * 32);
-  const size_t smem = (size_t)words * 4 + (size_t)max_frames * 4 + sizeof(Mt) + 16;
-  V3D_REQUIRE(smem <= 200 * 1024, V3D_E_UNSUPPORTED, "mc: greedy needs %zu bytes of shared memory", smem);
-  if (smem > 48 * 1024) V3D_CUDA(cudaFuncSetAttribute(k_mc_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_mc_greedy<<<n_scenes, kGreedyThreads, smem, s>>>(dev_scenes, max_pick);
+  int per_max = (max_frames + kGreedyCluster - 1) / kGreedyCluster;
+  if (per_max < 1) per_max = 1;
+  const size_t fixed = (size_t)(3 * per_max + 1 + kGreedyCluster * per_max) * 4 + (size_t)words * 4 + sizeof(Mt) + 16;
+  V3D_REQUIRE(fixed <= 200 * 1024, V3D_E_UNSUPPORTED, "mc: greedy needs %zu bytes of shared memory", fixed);
+  const size_t with_bits = fixed + (size_t)per_max * words * 4;
+  const int bits_in_smem = with_bits <= 200 * 1024;
+  const size_t smem = bits_in_smem ? with_bits : fixed;
+  V3D_CUDA(cudaFuncSetAttribute(k_mc_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)n_scenes * kGreedyCluster);
+  cfg.blockDim = dim3(kGreedyThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kGreedyCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  V3D_CUDA(cudaLaunchKernelEx(&cfg, k_mc_greedy, dev_scenes, max_pick, per_max, bits_in_smem));
   return check_launch("k_mc_greedy");
 }
 
