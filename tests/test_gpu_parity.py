@@ -533,6 +533,38 @@ def test_video_processor_matches_reference(dataset, D, strategy, lazy, monkeypat
     assert d["objects"].tolist() == gold["objects"] and d["video_size"] == gold["video_size"]
 
 
+def test_online_mc_sampling_equals_the_offline_json(dataset, D, monkeypatch, tmp_path):
+    """frame_sampling_strategy 'mc-online-ratio95' computes the max-coverage order inside
+    VideoProcessor (device voxelise + greedy) and must give what the reference's offline script wrote to
+    scannet_select_frames.json under the same tie-break seeds -- and the same sampled frames as 'mc-ratio95'.
+    Also through the packed scene binaries (f3)."""
+    from video_3d_llm_b200 import scene_pack
+
+    monkeypatch.chdir(dataset)
+    seeds = {f"scannet/{name}": m["seed"] for name, m in D["scenes"].items()}
+    vp_off = _vp(dataset, "mc-ratio95")
+    vp_on = _vp(dataset, "mc-online-ratio95", mc_seeds=seeds)
+    packs = str(tmp_path)
+    for video_id in vp_off.scene:
+        scene_pack.pack_scene(vp_off, video_id, scene_pack.pack_path(packs, video_id))
+    vp_on_pack = _vp(dataset, "mc-online-ratio95", mc_seeds=seeds, pack_dir=packs)
+    for gold in D["select_frames"]:
+        vid = gold["video_id"]
+        for vp in (vp_on, vp_on_pack):
+            rec = vp.mc_sample_online(vid)
+            assert [os.path.normpath(f) for f in rec["frame_files"]] == [os.path.normpath(f) for f in gold["frame_files"]]
+            assert rec["voxel_nums"] == gold["voxel_nums"]
+            assert (rec["num_all_voxels"], rec["num_select_voxels"]) == (gold["num_all_voxels"], gold["num_select_voxels"])
+            for ub in (3, 8, 32):
+                assert [os.path.normpath(f) for f in vp.sample_frame_files_mc(vid, frames_upbound=ub)] == \
+                       [os.path.normpath(f) for f in vp_off.sample_frame_files_mc(vid, frames_upbound=ub)]
+    ip = fixtures.FakeImageProcessor(384)
+    a = vp_off.process_3d_video("scannet/scene0003_00", ip, force_sample=True, frames_upbound=3)
+    b = vp_on_pack.process_3d_video("scannet/scene0003_00", ip, force_sample=True, frames_upbound=3)
+    assert torch.equal(a["world_coords"].materialize(), b["world_coords"].materialize())
+    assert torch.equal(a["images"], b["images"])
+
+
 def test_lazy_handle_through_the_reference_call_structure(dataset, D, monkeypatch):
     monkeypatch.chdir(dataset)
     """What prepare_inputs_labels_for_multimodal does with video_dict (llava_arch.py:386-420, 506-517), on a

@@ -1,0 +1,90 @@
+"""Packed per-scene binary: byte-identical inputs to the PNG/txt path of the reference
+(llava/video_utils.py:212-230), format checks, error behaviour.  CPU only."""
+import os
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from video_3d_llm_b200 import scene_pack
+from video_3d_llm_b200 import video_utils as VU
+
+
+def _vp(root, **kw):
+    return VU.VideoProcessor(video_folder=os.path.join(root, "data"), annotation_dir=os.path.join(root, "data", "embodiedscan"),
+                             voxel_size=0.1, min_xyz_range=[-15, -15, -5], max_xyz_range=[15, 15, 5],
+                             frame_sampling_strategy="uniform", metadata_dir=os.path.join(root, "data", "metadata"), **kw)
+
+
+@pytest.fixture(scope="module")
+def packed(dataset, tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("packs"))
+    vp = _vp(dataset)
+    for video_id in vp.scene:
+        scene_pack.pack_scene(vp, video_id, scene_pack.pack_path(out, video_id))
+    return out
+
+
+def test_pack_equals_png_txt_path(dataset, packed):
+    vp_files, vp_pack = _vp(dataset), _vp(dataset, pack_dir=packed)
+    for video_id, info in vp_files.scene.items():
+        files = [os.path.join(vp_files.video_folder, img["img_path"]) for img in info["images"]]
+        for pick in (files, files[::3], files[::-2][:5], files[:1]):
+            a = vp_files.load_frames(video_id, pick)
+            b = vp_pack.load_frames(video_id, pick)
+            for x, y in zip(a, b):
+                assert x.dtype == y.dtype and x.shape == y.shape
+                assert torch.equal(x, y)
+        assert vp_pack._pack(video_id) is not None
+
+
+def test_pack_layout_and_header(dataset, packed):
+    vp = _vp(dataset)
+    video_id = sorted(vp.scene)[0]
+    path = scene_pack.pack_path(packed, video_id)
+    raw = open(path, "rb").read()
+    magic, ver, n, H, W, code, _, off_ids, off_poses, off_intr, off_depth, total = struct.unpack_from("<8sIIIIIIQQQQQ", raw)
+    assert magic == b"V3DPACK1" and ver == 1 and code == 0 and total == len(raw)
+    assert n == len(vp.scene[video_id]["images"]) and off_depth % 4096 == 0 and off_ids == 4096
+    assert total == off_depth + n * H * W * 2
+    pk = scene_pack.ScenePack(path)
+    assert pk.ids.tolist() == [scene_pack.frame_number(i["img_path"]) for i in vp.scene[video_id]["images"]]
+    d, p, k = pk.load(pk.ids[:2], pin=False)
+    assert d.dtype == torch.int16 and tuple(d.shape) == (2, H, W) and tuple(p.shape) == (2, 4, 4) and tuple(k.shape) == (2, 4, 4)
+
+
+def test_pack_errors(dataset, packed, tmp_path):
+    vp = _vp(dataset)
+    video_id = sorted(vp.scene)[0]
+    pk = scene_pack.ScenePack(scene_pack.pack_path(packed, video_id))
+    with pytest.raises(KeyError):
+        pk.load([123457])
+    bad = tmp_path / "bad.v3dpack"
+    bad.write_bytes(b"NOTAPACK" + bytes(4096))
+    with pytest.raises(ValueError):
+        scene_pack.ScenePack(str(bad))
+    raw = open(scene_pack.pack_path(packed, video_id), "rb").read()
+    trunc = tmp_path / "trunc.v3dpack"
+    trunc.write_bytes(raw[:-10])
+    with pytest.raises(ValueError):
+        scene_pack.ScenePack(str(trunc))
+    with pytest.raises(ValueError):
+        scene_pack.write_pack(str(tmp_path / "x.v3dpack"), [0], np.eye(4, dtype=np.float32)[None], np.eye(4, dtype=np.float32),
+                              np.zeros((1, 4, 4), np.float32))
+    # a scene without a pack falls back to the files
+    vp2 = _vp(dataset, pack_dir=str(tmp_path))
+    files = [os.path.join(vp2.video_folder, img["img_path"]) for img in vp2.scene[video_id]["images"]][:2]
+    assert torch.equal(vp2.load_frames(video_id, files)[0], vp.load_frames(video_id, files)[0])
+
+
+def test_int32_depth_pack_round_trip(tmp_path):
+    rng = np.random.default_rng(0)
+    depth = rng.integers(0, 70000, (3, 6, 8)).astype(np.int32)
+    poses = rng.normal(size=(3, 4, 4)).astype(np.float32)
+    intr = rng.normal(size=(4, 4)).astype(np.float32)
+    path = str(tmp_path / "s.v3dpack")
+    scene_pack.write_pack(path, [30, 10, 20], poses, intr, depth)
+    d, p, k = scene_pack.ScenePack(path).load([10, 30])
+    assert d.dtype == torch.int32 and np.array_equal(d.numpy(), depth[[1, 0]])
+    assert np.array_equal(p.numpy(), poses[[1, 0]]) and np.array_equal(k.numpy(), np.repeat(intr[None], 2, 0))

@@ -1,0 +1,156 @@
+"""Packed per-scene binary of the geometry inputs.
+
+The reference reads, per sampled frame, one 16-bit PNG (`Image.open` + `np.array`, llava/video_utils.py:215-218)
+and one `%f` text pose (`np.loadtxt`, :221-223) and multiplies by the axis-align matrix in float64 (:205,227).
+With the device side at microseconds per frame that host work is the end-to-end bound, so a scene is converted
+once into one file that holds exactly what `VideoProcessor.load_frames` produces:
+
+    offset 0     header, 4096 bytes, little endian:
+                   magic "V3DPACK1", u32 version, u32 n_frames, u32 H, u32 W, u32 depth_code (0 = uint16,
+                   1 = int32), u32 reserved, u64 off_ids, u64 off_poses, u64 off_intr, u64 off_depth, u64 file_bytes
+    off_ids      int32[n_frames]        frame number (file stem, e.g. 00120.png -> 120)
+    off_poses    float32[n_frames][16]  float32(axis_align(f64) @ loadtxt(pose)(f64)), the tensor of :230
+    off_intr     float32[16]            depth_cam2img as float32 (:206,228)
+    off_depth    depth[n_frames][H][W]  4096-byte aligned; frame i is one contiguous H*W*itemsize block
+
+Reading a set of frames is one contiguous copy per frame from the page cache (np.memmap) into a pinned staging
+buffer, then a single async H2D copy.  Bit-identical to the PNG/txt path (tests/test_scene_pack.py).
+
+    python -m video_3d_llm_b200.scene_pack --video_dir data/scannet/posed_images --out_dir data/scannet/packed
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import struct
+
+import numpy as np
+import torch
+
+MAGIC = b"V3DPACK1"
+VERSION = 1
+HEADER_BYTES = 4096
+_HDR = struct.Struct("<8sIIIIIIQQQQQ")
+
+
+def _align(n: int, a: int = 4096) -> int:
+    return (n + a - 1) // a * a
+
+
+def frame_number(path: str) -> int:
+    return int(os.path.basename(path).split(".")[0])
+
+
+def write_pack(path: str, frame_ids, poses32: np.ndarray, intr32: np.ndarray, depth: np.ndarray) -> None:
+    """poses32 (n,4,4) float32, intr32 (4,4) float32, depth (n,H,W) uint16 or int32."""
+    n, H, W = depth.shape
+    if depth.dtype == np.uint16:
+        code = 0
+    elif depth.dtype == np.int32:
+        code = 1
+    else:
+        raise ValueError(f"depth must be uint16 or int32, got {depth.dtype}")
+    ids = np.asarray(frame_ids, np.int32)
+    poses32 = np.ascontiguousarray(poses32, np.float32).reshape(n, 16)
+    intr32 = np.ascontiguousarray(intr32, np.float32).reshape(16)
+    if ids.shape != (n,):
+        raise ValueError("one frame id per depth frame")
+    off_ids = HEADER_BYTES
+    off_poses = off_ids + _align(4 * n, 64)
+    off_intr = off_poses + 64 * n
+    off_depth = _align(off_intr + 64)
+    total = off_depth + depth.nbytes
+    tmp = path + ".tmp"
+    with open(tmp, "wb") as f:
+        f.write(_HDR.pack(MAGIC, VERSION, n, H, W, code, 0, off_ids, off_poses, off_intr, off_depth, total).ljust(HEADER_BYTES, b"\0"))
+        f.write(ids.tobytes().ljust(off_poses - off_ids, b"\0"))
+        f.write(poses32.tobytes())
+        f.write(intr32.tobytes().ljust(off_depth - off_intr, b"\0"))
+        f.write(np.ascontiguousarray(depth).tobytes())
+    os.replace(tmp, path)
+
+
+class ScenePack:
+    """Read side: memory-mapped views, frames addressed by frame number."""
+
+    def __init__(self, path: str):
+        self.path = path
+        with open(path, "rb") as f:
+            hdr = f.read(_HDR.size)
+        if len(hdr) < _HDR.size:
+            raise ValueError(f"{path}: truncated header")
+        magic, ver, n, H, W, code, _, off_ids, off_poses, off_intr, off_depth, total = _HDR.unpack(hdr)
+        if magic != MAGIC or ver != VERSION:
+            raise ValueError(f"{path}: not a V3DPACK1 file (magic {magic!r}, version {ver})")
+        if code not in (0, 1):
+            raise ValueError(f"{path}: unknown depth code {code}")
+        if os.path.getsize(path) != total:
+            raise ValueError(f"{path}: size {os.path.getsize(path)} != {total} recorded in the header")
+        self.n_frames, self.H, self.W = n, H, W
+        self.depth_dtype = np.uint16 if code == 0 else np.int32
+        mm = np.memmap(path, dtype=np.uint8, mode="r")
+        self.ids = np.frombuffer(mm, np.int32, n, off_ids)
+        self.poses = np.frombuffer(mm, np.float32, 16 * n, off_poses).reshape(n, 4, 4)
+        self.intr = np.frombuffer(mm, np.float32, 16, off_intr).reshape(4, 4)
+        self.depth = np.frombuffer(mm, self.depth_dtype, n * H * W, off_depth).reshape(n, H, W)
+        self._index = {int(v): i for i, v in enumerate(self.ids)}
+
+    def rows(self, frame_numbers) -> np.ndarray:
+        try:
+            return np.fromiter((self._index[int(k)] for k in frame_numbers), np.int64)
+        except KeyError as e:
+            raise KeyError(f"{self.path}: frame {e.args[0]} is not in the pack") from None
+
+    def load(self, frame_numbers, pin: bool = False):
+        """(depth, poses, intrinsics) tensors for the given frame numbers, like VideoProcessor.load_frames:
+        depth (V,H,W) int16 storage of uint16 (or int32), poses (V,4,4) f32, intrinsics (V,4,4) f32."""
+        rows = self.rows(frame_numbers)
+        V = len(rows)
+        store = torch.int16 if self.depth_dtype == np.uint16 else torch.int32
+        depth_t = torch.empty((V, self.H, self.W), dtype=store, pin_memory=pin)
+        dst = depth_t.numpy().view(self.depth_dtype)
+        for o, r in enumerate(rows):  # one contiguous H*W block per frame
+            dst[o] = self.depth[r]
+        poses_t = torch.from_numpy(np.array(self.poses[rows]))
+        intr_t = torch.from_numpy(np.array(self.intr)).unsqueeze(0).repeat(V, 1, 1)
+        if pin:
+            poses_t, intr_t = poses_t.pin_memory(), intr_t.pin_memory()
+        return depth_t, poses_t, intr_t
+
+
+def pack_path(pack_dir: str, video_id: str) -> str:
+    return os.path.join(pack_dir, video_id.split("/")[-1] + ".v3dpack")
+
+
+def pack_scene(vp, video_id: str, out_path: str) -> str:
+    """Convert one scene of a VideoProcessor's dataset (all frames of its info entry) from PNG/txt."""
+    files = [os.path.join(vp.video_folder, img["img_path"]) for img in vp.scene[video_id]["images"]]
+    depth_t, poses_t, intr_t = vp.load_frames_from_files(video_id, files)
+    depth = depth_t.numpy()
+    depth = depth.view(np.uint16) if depth.dtype == np.int16 else depth
+    write_pack(out_path, [frame_number(f) for f in files], poses_t.numpy(), intr_t[0].numpy(), depth)
+    return out_path
+
+
+def main(args) -> None:
+    from .video_utils import VideoProcessor
+
+    vp = VideoProcessor(video_folder=args.video_folder, annotation_dir=args.annotation_dir, voxel_size=0.1, lazy=True,
+                        metadata_dir=args.metadata_dir)
+    os.makedirs(args.out_dir, exist_ok=True)
+    for scene_id in sorted(os.listdir(args.video_dir)):
+        video_id = f"scannet/{scene_id}"
+        if video_id not in vp.scene:
+            continue
+        out = pack_scene(vp, video_id, pack_path(args.out_dir, video_id))
+        print(f"[{scene_id}] {os.path.getsize(out) / 1e6:.1f} MB -> {out}")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--video_dir", default="data/scannet/posed_images")
+    ap.add_argument("--video_folder", default="data")
+    ap.add_argument("--annotation_dir", default="data/embodiedscan/")
+    ap.add_argument("--metadata_dir", default=None)
+    ap.add_argument("--out_dir", default="data/scannet/packed")
+    main(ap.parse_args())

@@ -27,6 +27,7 @@ DEPTH_SCALE = 1000.0
 
 
 def _device_for(*tensors):
+    """The CUDA device of the first CUDA tensor, else the current device; raises without CUDA."""
     for t in tensors:
         if isinstance(t, torch.Tensor) and t.is_cuda:
             return t.device
@@ -271,13 +272,20 @@ class VideoProcessor:
     only) selects what `world_coords` is: a LazyWorldCoords handle (default) or a real tensor."""
 
     def __init__(self, video_folder="data", annotation_dir="data/embodiedscan/", voxel_size=None, min_xyz_range=None,
-                 max_xyz_range=None, frame_sampling_strategy="uniform", val_box_type="pred", *, lazy=True, metadata_dir=None):
+                 max_xyz_range=None, frame_sampling_strategy="uniform", val_box_type="pred", *, lazy=True, metadata_dir=None,
+                 pack_dir=None, mc_seeds=None):
         self.video_folder = video_folder
         self.voxel_size = voxel_size
         self.min_xyz_range = torch.tensor(min_xyz_range) if min_xyz_range is not None else None
         self.max_xyz_range = torch.tensor(max_xyz_range) if max_xyz_range is not None else None
         self.frame_sampling_strategy = frame_sampling_strategy
         self.lazy = lazy
+        # extras (keyword only): packed per-scene binaries (scene_pack.py) replace the PNG/txt reads when present;
+        # mc_seeds {video_id: int} fixes the tie-break seed of the online MC sampler (default crc32(video_id))
+        self.pack_dir = pack_dir
+        self.mc_seeds = dict(mc_seeds or {})
+        self._packs = {}
+        self._mc_sampler = None
         self.scene = {}
         print("============frame sampling strategy: {}=============".format(self.frame_sampling_strategy))
         # the reference hard-codes data/metadata relative to the working directory (:102,109,116)
@@ -296,10 +304,15 @@ class VideoProcessor:
                 self.scan2obj.update(json.load(f))
 
         if "mc" in self.frame_sampling_strategy:
-            with open(os.path.join(meta, "scannet_select_frames.json")) as f:
-                self.mc_sampling_files = {dd["video_id"]: dd for dd in json.load(f)}
+            # "online" in the strategy (e.g. mc-online-ratio95): the order is computed here by the CUDA sampler
+            # instead of being read from the offline script's JSON
+            self.mc_sampling_files = {}
+            if "online" not in self.frame_sampling_strategy:
+                with open(os.path.join(meta, "scannet_select_frames.json")) as f:
+                    self.mc_sampling_files = {dd["video_id"]: dd for dd in json.load(f)}
             with open(os.path.join(meta, "pcd_discrete_0.1.pkl"), "rb") as f:
                 pc_data = pickle.load(f)
+            self.pc_data = pc_data
             self.pc_min, self.pc_max = {}, {}
             for scene_id, pts in pc_data.items():
                 arr = np.asarray(pts, dtype=np.int64).reshape(-1, 3)
@@ -312,6 +325,8 @@ class VideoProcessor:
     # ---- frame selection (host, integer work) ------------------------------------------------
     def sample_frame_files_mc(self, video_id: str, frames_upbound: int = 32, do_shift=False):
         """:131-159 -- prefix of the offline MC order, cut at the coverage ratio, sorted by frame id."""
+        if video_id not in self.mc_sampling_files and "online" in self.frame_sampling_strategy:
+            self.mc_sampling_files[video_id] = self.mc_sample_online(video_id)
         mc = self.mc_sampling_files[video_id]
         frame_files = mc["frame_files"][:frames_upbound]
         voxel_nums = mc["voxel_nums"][:frames_upbound]
@@ -339,9 +354,54 @@ class VideoProcessor:
         picks = np.linspace(0, len(frame_files) - 1, n, dtype=int)
         return [frame_files[i] for i in picks]
 
+    def mc_sample_online(self, video_id: str, max_pick: int = 32):
+        """scripts/3d/preprocessing/max_coverage_sampling.py:24-104 for one scene, at run time: candidates =
+        every second frame (all if that leaves < 32), voxelise + greedy on the device, the record of :98-104.
+        The reference caps the order at 32 picks (:93); so does the kernel's record."""
+        from . import mc_sampling
+
+        info = self.scene[video_id]
+        files = [os.path.join(self.video_folder, img["img_path"]) for img in info["images"]][::2]
+        if len(files) < 32:
+            files = [os.path.join(self.video_folder, img["img_path"]) for img in info["images"]]
+        dev = _device_for()
+        if self._mc_sampler is None:
+            self._mc_sampler = mc_sampling.MCSampler(self.voxel_size if self.voxel_size is not None else 0.1, device=dev)
+        depth, poses, intr = self.load_frames(video_id, files)
+        scene_id = video_id.split("/")[-1]
+        pc = torch.tensor(np.asarray(self.pc_data[scene_id], dtype=np.int32).reshape(-1, 3), device=dev)
+        import zlib
+
+        seed = self.mc_seeds.get(video_id, zlib.crc32(video_id.encode()))
+        res = self._mc_sampler.sample([{"depth": depth.to(dev), "poses": poses.to(dev), "intrinsics": intr.to(dev), "pc_voxels": pc,
+                                        "seed": seed}])[0]
+        return {"video_id": video_id, "frame_files": [files[i] for i in res["order"][:max_pick]],
+                "voxel_nums": res["gains"][:max_pick], "num_all_voxels": res["n_all"], "num_select_voxels": res["n_sel"]}
+
     # ---- geometry --------------------------------------------------------------------------------
+    def _pack(self, video_id: str):
+        """The scene's packed binary (scene_pack.py) if pack_dir holds one, else None."""
+        if self.pack_dir is None:
+            return None
+        if video_id not in self._packs:
+            from . import scene_pack
+
+            path = scene_pack.pack_path(self.pack_dir, video_id)
+            self._packs[video_id] = scene_pack.ScenePack(path) if os.path.isfile(path) else None
+        return self._packs[video_id]
+
     def load_frames(self, video_id: str, frame_files):
-        """Raw inputs of :196-230: uint16 depth stack, float32(axis_align @ pose), float32 intrinsics."""
+        """Raw inputs of :196-230: uint16 depth stack, float32(axis_align @ pose), float32 intrinsics -- from the
+        scene's packed binary when there is one (one contiguous read per frame), else from the PNG/txt files."""
+        pack = self._pack(video_id)
+        if pack is not None:
+            from . import scene_pack
+
+            return pack.load([scene_pack.frame_number(f) for f in frame_files])
+        return self.load_frames_from_files(video_id, frame_files)
+
+    def load_frames_from_files(self, video_id: str, frame_files):
+        """:212-230 as written: Image.open of the depth PNG, np.loadtxt of the pose, axis_align(f64) @ pose."""
         meta_info = self.scene[video_id]
         axis_align = np.array(meta_info["axis_align_matrix"], dtype=np.float64)
         intr = np.array(meta_info["depth_cam2img"], dtype=np.float64)
