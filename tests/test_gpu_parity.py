@@ -552,12 +552,13 @@ def test_online_mc_sampling_equals_the_offline_json(dataset, D, monkeypatch, tmp
         vid = gold["video_id"]
         for vp in (vp_on, vp_on_pack):
             rec = vp.mc_sample_online(vid)
-            assert [os.path.normpath(f) for f in rec["frame_files"]] == [os.path.normpath(f) for f in gold["frame_files"]]
+            # the offline JSON holds paths relative to the working directory (video_folder "data"), as upstream
+            assert [os.path.abspath(f) for f in rec["frame_files"]] == [os.path.abspath(f) for f in gold["frame_files"]]
             assert rec["voxel_nums"] == gold["voxel_nums"]
             assert (rec["num_all_voxels"], rec["num_select_voxels"]) == (gold["num_all_voxels"], gold["num_select_voxels"])
             for ub in (3, 8, 32):
-                assert [os.path.normpath(f) for f in vp.sample_frame_files_mc(vid, frames_upbound=ub)] == \
-                       [os.path.normpath(f) for f in vp_off.sample_frame_files_mc(vid, frames_upbound=ub)]
+                assert [os.path.abspath(f) for f in vp.sample_frame_files_mc(vid, frames_upbound=ub)] == \
+                       [os.path.abspath(f) for f in vp_off.sample_frame_files_mc(vid, frames_upbound=ub)]
     ip = fixtures.FakeImageProcessor(384)
     a = vp_off.process_3d_video("scannet/scene0003_00", ip, force_sample=True, frames_upbound=3)
     b = vp_on_pack.process_3d_video("scannet/scene0003_00", ip, force_sample=True, frames_upbound=3)
