@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define V3D_VERSION 100 /* 0.1.0 */
+#define V3D_VERSION 101 /* 0.1.1 */
 
 enum v3d_status { V3D_OK = 0, V3D_E_ARG = -1, V3D_E_ALIGN = -2, V3D_E_UNSUPPORTED = -3, V3D_E_CUDA = -4 };
 
@@ -196,6 +196,35 @@ int v3d_mc_voxelize(const v3d_mc_scene* scenes_host, int n_scenes, int H, int W,
 int v3d_mc_greedy(const v3d_mc_scene* scenes_host, int n_scenes, int max_pick, void* scratch, v3d_stream_t stream);
 /* voxel ids of materialised world coordinates: int(round(w / voxel)) (max_coverage_sampling.py:44-45) */
 int v3d_mc_voxel_ids(const float* world, size_t n_points, float voxel_size, int div_mode, int32_t* ids, v3d_stream_t stream);
+
+/* ---- projector tail ------------------------------------------------------
+ * One kernel for llava/model/llava_arch.py:191-210 `get_2dPool` (the 2x2 spatial pooling of the projected video
+ * tokens: bilinear interpolate to ceil(G/stride), or avg/max pooling to floor(G/stride)), :506-517 (the add of
+ * world_position_embedding(coords)) and :307-328 `add_token_per_grid` (image_newline after every grid row).
+ *   tokens (n_frames, src_grid*src_grid, E) of `dtype`, row-major grid like the vision tower emits it;
+ *   coords NULL (no PE) or (n_frames, out_grid*out_grid, n_points, 3) fp32 -- what the PE is evaluated on
+ *     (discretised or not), e.g. the pe_coords_out of v3d_frontend_pe; dim_t/table/table_rows as for v3d_pe_sine3d;
+ *   newline NULL or E elements: out is (n_frames, out_grid, out_grid + (newline != NULL), E).
+ * The pooled value is rounded to `dtype` before the PE is added (the reference materialises it), so the result has
+ * the reference's two roundings. */
+/* NONE keeps the grid (stride ignored): PE add and/or newline insertion only */
+enum v3d_token_pool_mode { V3D_TOKEN_POOL_BILINEAR = 0, V3D_TOKEN_POOL_AVERAGE = 1, V3D_TOKEN_POOL_MAX = 2, V3D_TOKEN_POOL_NONE = 3 };
+typedef struct v3d_pool_desc {
+  const void* tokens;
+  int n_frames, src_grid, E, dtype;
+  int pool_mode; /* v3d_token_pool_mode (config.mm_spatial_pool_mode) */
+  int stride;    /* config.mm_spatial_pool_stride */
+  const float* coords;
+  int n_points;
+  const float* dim_t;
+  const void* table;
+  int table_rows;
+  const void* newline;
+  void* out;
+} v3d_pool_desc;
+/* tokens per side after pooling, -1 for bad arguments */
+int v3d_token_pool_out_grid(int src_grid, int stride, int pool_mode);
+int v3d_pool_pe_grid(const v3d_pool_desc* desc, v3d_stream_t stream);
 
 /* ---- object proposals -------------------------------------------------------
  * v3d_object_patch_masks replaces the per-object loop of llava/model/llava_arch.py:351-378: for each of K

@@ -345,6 +345,40 @@ def golden_objects():
     print("objects.npz written")
 
 
+def golden_tail():
+    """Projector tail: the reference's own get_2dPool / PositionEmbeddingSine3D / add_token_per_grid
+    (llava_arch.py:191-210, :506-517, :307-328) on random bf16 tokens, chained as :469 -> :515 -> :536."""
+    arch = ref_import.llava_arch()
+    pe_mod = ref_import.position_encoding()
+    cls = arch.LlavaMetaForCausalLM
+    g = {}
+    for tag, (V, side, E, mode) in {"bilinear_1152": (2, 27, 1152, "bilinear"), "bilinear_3584": (1, 27, 3584, "bilinear"),
+                                    "average_1152": (2, 27, 1152, "average"), "max_1152": (2, 27, 1152, "max"),
+                                    "bilinear_16_264": (1, 16, 264, "bilinear")}.items():
+        tokens = synthetic.make_tokens(70, V, side * side, E)
+        gen = torch.Generator().manual_seed(71)
+        newline = torch.randn(E, generator=gen).to(torch.bfloat16)
+        shim = types.SimpleNamespace(
+            config=types.SimpleNamespace(mm_spatial_pool_mode=mode, add_faster_video=False),
+            model=types.SimpleNamespace(image_newline=newline),
+            get_vision_tower=lambda side=side: types.SimpleNamespace(num_patches_per_side=side))
+        pooled = cls.get_2dPool(shim, tokens, 2)
+        Go = int(round(pooled.shape[1] ** 0.5))
+        coords = torch.randint(0, 301, (V, Go * Go, 3), generator=gen).to(torch.bfloat16)
+        coords[..., 2] = torch.randint(0, 101, (V, Go * Go), generator=gen).to(torch.bfloat16)
+        with_pe = pooled + pe_mod.PositionEmbeddingSine3D(E)(coords.detach())
+        out = cls.add_token_per_grid(shim, with_pe)
+        assert out.shape == (V * Go * (Go + 1), E) and out.dtype == torch.bfloat16
+        g[f"{tag}_coords"] = coords.float().numpy()
+        g[f"{tag}_newline"] = newline.view(torch.int16).numpy()
+        g[f"{tag}_pooled_sha"] = np.frombuffer(bytes.fromhex(sha(pooled.contiguous().view(torch.int16).numpy())), np.uint8)
+        g[f"{tag}_out_sha"] = np.frombuffer(bytes.fromhex(sha(out.contiguous().view(torch.int16).numpy())), np.uint8)
+        g[f"{tag}_out_sample"] = out.contiguous().view(torch.int16).numpy()[::7, ::5].copy()
+        g[f"{tag}_meta"] = np.array([V, side, E, Go])
+    np.savez_compressed(os.path.join(GOLDEN, "tail.npz"), **g)
+    print("tail.npz written")
+
+
 def golden_mt():
     """CPython `random` known answers for the in-kernel MT19937 (tie-break protocol)."""
     out = {}
@@ -371,5 +405,7 @@ if __name__ == "__main__":
         golden_frontend()
     if a.only in ("", "objects"):
         golden_objects()
+    if a.only in ("", "tail"):
+        golden_tail()
     if a.only in ("", "dataset"):
         golden_dataset()

@@ -97,3 +97,46 @@ def frontend(depths: torch.Tensor, poses: torch.Tensor, intrinsics: torch.Tensor
     if tokens is not None:
         return tokens + pe.to(tokens.dtype), pooled, disc
     return pe.to(torch.bfloat16), pooled, disc
+
+
+# ---- projector tail ---------------------------------------------------------------------------
+def get_2dpool(image_feature: torch.Tensor, stride: int = 2, mode: str = "bilinear") -> torch.Tensor:
+    """llava/model/llava_arch.py:191-210 with num_patches_per_side = sqrt(tokens)."""
+    import math
+
+    num_frames, num_tokens, num_dim = image_feature.shape
+    side = int(math.isqrt(num_tokens))
+    x = image_feature.view(num_frames, side, side, -1).permute(0, 3, 1, 2).contiguous()
+    if mode == "average":
+        x = torch.nn.functional.avg_pool2d(x, stride)
+    elif mode == "max":
+        x = torch.nn.functional.max_pool2d(x, stride)
+    elif mode == "bilinear":
+        h, w = x.shape[2:]
+        x = torch.nn.functional.interpolate(x, size=[math.ceil(h / stride), math.ceil(w / stride)], mode="bilinear")
+    else:
+        raise ValueError(f"Unexpected mm_spatial_pool_mode: {mode}")
+    return x.permute(0, 2, 3, 1).reshape(num_frames, -1, num_dim)
+
+
+def add_token_per_grid(image_feature: torch.Tensor, image_newline: torch.Tensor) -> torch.Tensor:
+    """llava_arch.py:307-328 (add_faster_video off)."""
+    import math
+
+    resize_h = int(math.sqrt(image_feature.shape[1]))
+    num_frames = image_feature.shape[0]
+    x = image_feature.view(num_frames, 1, resize_h, resize_h, -1).permute(4, 0, 2, 1, 3).contiguous()
+    x = x.flatten(1, 2).flatten(2, 3)
+    x = torch.cat((x, image_newline[:, None, None].expand(*x.shape[:-1], 1)), dim=-1)
+    return x.flatten(1, 2).transpose(0, 1)
+
+
+def projector_tail(image_feature: torch.Tensor, coords, embedding_size: int, image_newline, stride: int = 2, mode: str = "bilinear") -> torch.Tensor:
+    """get_2dPool (:469) -> + PE(coords) (:506-517) -> add_token_per_grid (:536).  coords: None or (V, Go*Go, 3) in the
+    token dtype (the module returns the PE in the dtype of its input, position_encoding.py:48)."""
+    x = get_2dpool(image_feature, stride, mode)
+    if coords is not None:
+        x = x + pe_sine3d(coords.detach(), embedding_size)
+    if image_newline is not None:
+        x = add_token_per_grid(x, image_newline)
+    return x

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_pure_host_helpers():
     lib = cabi.load()
-    assert lib.v3d_version() == 100
+    assert lib.v3d_version() == 101
     assert [lib.v3d_pool_points(m) for m in range(5)] == [1, 2, 9, 5, 1]
     assert lib.v3d_pool_points(99) == -1
     assert lib.v3d_mc_hash_slots(0) == 64 and lib.v3d_mc_hash_slots(1000) == 4096

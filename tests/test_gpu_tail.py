@@ -1,0 +1,107 @@
+"""GPU: the projector-tail kernel (get_2dPool -> PE add -> add_token_per_grid) through the
+host mirror -> ctypes -> C ABI, against the CPU restatement of the reference's operator sequence
+(oracle/torch_port.py, pinned on the reference's own methods in tests/test_oracle_golden.py) and the golden vectors.
+
+Bar: newline rows, max pooling and the grid layout bit-exact; pooled / PE-added bf16 values equal except for a small
+fraction of elements that differ by one bf16 ulp (fp32 evaluation order of the bilinear taps, CUDA vs SLEEF sin/cos)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from oracle import torch_port as TP  # noqa: E402
+from test_gpu_parity import assert_bf16_close, bf16_bits  # noqa: E402
+from video_3d_llm_b200 import cabi, projector_tail as PT, synthetic  # noqa: E402
+from video_3d_llm_b200.position_encoding import PositionEmbeddingSine3D  # noqa: E402
+
+DEV = torch.device("cuda:0")
+TAIL_CASES = ["bilinear_1152", "bilinear_3584", "average_1152", "max_1152", "bilinear_16_264"]
+
+
+def _case(golden_dir, tag):
+    G = np.load(os.path.join(golden_dir, "tail.npz"))
+    V, side, E, Go = (int(v) for v in G[f"{tag}_meta"])
+    tokens = synthetic.make_tokens(70, V, side * side, E)
+    coords = torch.from_numpy(G[f"{tag}_coords"]).to(torch.bfloat16)
+    newline = torch.from_numpy(G[f"{tag}_newline"]).view(torch.bfloat16)
+    return G, V, side, E, Go, tokens, coords, newline, tag.split("_")[0]
+
+
+@pytest.mark.parametrize("tag", TAIL_CASES)
+def test_pool_pe_newline_matches_reference(golden_dir, tag):
+    G, V, side, E, Go, tokens, coords, newline, mode = _case(golden_dir, tag)
+    ref_pooled = TP.get_2dpool(tokens, 2, mode)
+    ref = TP.projector_tail(tokens, coords, E, newline, 2, mode)
+    # pooling alone, under the reference's name
+    got_pooled = PT.get_2dPool(tokens.to(DEV), 2, mode)
+    assert got_pooled.shape == ref_pooled.shape and got_pooled.dtype == torch.bfloat16
+    if mode == "max":
+        assert torch.equal(got_pooled.cpu(), ref_pooled)
+    else:
+        assert_bf16_close(bf16_bits(got_pooled), bf16_bits(ref_pooled), max_frac=5e-4)
+    # the fused tail
+    pe = PositionEmbeddingSine3D(E)
+    got = PT.pool_pe_newline(tokens.to(DEV), stride=2, mode=mode, coords=coords.to(DEV), position_embedding=pe, image_newline=newline.to(DEV))
+    assert got.shape == (V * Go * (Go + 1), E) and got.dtype == torch.bfloat16
+    assert_bf16_close(bf16_bits(got), bf16_bits(ref), max_frac=1e-3)
+    g4 = got.view(V, Go, Go + 1, E)
+    assert torch.equal(g4[:, :, Go, :].cpu(), newline.expand(V, Go, E))  # add_token_per_grid: newline closes every row
+    # against the vectors written by the reference itself
+    assert_bf16_close(bf16_bits(got)[::7, ::5], G[f"{tag}_out_sample"].view(np.uint16), max_frac=2e-3)
+    # the two-step composition (pool kernel, then the PE module's fused add, then the newline kernel) agrees exactly
+    two_step = PT.add_token_per_grid(pe(coords.to(DEV), add_to=got_pooled), newline.to(DEV))
+    assert torch.equal(two_step, got)
+
+
+def test_tail_other_dtypes_layouts_and_continuous_coords():
+    V, side, E = 2, 12, 192
+    tokens = synthetic.make_tokens(5, V, side * side, E)
+    gen = torch.Generator().manual_seed(3)
+    coords = torch.rand(V, 36, 3, generator=gen) * 20  # non-integer: the PE is evaluated directly, no table rows
+    coords[0, :5] = torch.tensor([3.0, 7.0, 250.0])  # integer-valued: served from the table
+    newline = torch.randn(E, generator=gen)
+    for dt, frac in ((torch.float32, None), (torch.float16, 2e-3), (torch.bfloat16, 2e-3)):
+        t, c, nl = tokens.to(dt), coords.to(dt), newline.to(dt)
+        ref = TP.projector_tail(t, c, E, nl, 2, "bilinear")
+        got = PT.pool_pe_newline(t.to(DEV), coords=c.to(DEV), position_embedding=PositionEmbeddingSine3D(E), image_newline=nl.to(DEV))
+        assert got.dtype == dt and got.shape == ref.shape
+        if dt == torch.float32:
+            torch.testing.assert_close(got.cpu(), ref, rtol=0, atol=2e-6)
+        else:
+            d = (got.cpu().float() - ref.float()).abs()
+            ulp = torch.maximum(ref.float().abs(), torch.tensor(1e-3)) * (2.0 ** -7 if dt == torch.bfloat16 else 2.0 ** -10)
+            assert bool((d <= ulp).all()) and float((d > 0).float().mean()) < frac
+    # no newline, no PE, not flattened: (V, Go*Go, E)
+    out = PT.pool_pe_newline(tokens.to(DEV), stride=3, mode="bilinear")
+    assert out.shape == (V, 16, E)
+    ref = TP.get_2dpool(tokens, 3, "bilinear")
+    assert_bf16_close(bf16_bits(out), bf16_bits(ref), max_frac=5e-4)
+    # newline only (add_token_per_grid on its own) is a pure copy
+    nl = newline.to(torch.bfloat16)
+    assert torch.equal(PT.add_token_per_grid(tokens.to(DEV), nl.to(DEV)).cpu(), TP.add_token_per_grid(tokens, nl))
+    # NaN propagation of max pooling (a later NaN replaces the maximum, like ATen)
+    tn = tokens.clone()
+    tn[0, 13, 7] = float("nan")
+    a, b = PT.get_2dPool(tn.to(DEV), 2, "max").cpu(), TP.get_2dpool(tn, 2, "max")
+    assert torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+
+
+def test_tail_errors_and_empty():
+    tokens = synthetic.make_tokens(1, 1, 36, 64).to(DEV)
+    with pytest.raises(ValueError):
+        PT.pool_pe_newline(tokens, mode="median")
+    with pytest.raises(ValueError):
+        PT.pool_pe_newline(tokens[:, :35])
+    with pytest.raises(ValueError):
+        PT.pool_pe_newline(tokens, coords=torch.zeros(1, 9, 3, device=DEV))
+    with pytest.raises(NotImplementedError):
+        PT.pool_pe_newline(tokens, stride=3, mode="average")
+    with pytest.raises(RuntimeError):
+        PT.pool_pe_newline(tokens.cpu())
+    assert PT.pool_pe_newline(tokens[:0]).shape == (0, 9, 64)

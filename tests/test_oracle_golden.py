@@ -270,3 +270,33 @@ def test_object_patch_masks_and_features(golden_dir, stages):
     tokens = synthetic.make_tokens(0, 2, 196, 256).view(torch.int16).numpy().view(np.uint16).reshape(-1, 256)
     feat = O.object_features(tokens, O.object_patch_masks(stages["coords"], GO["boxes"], "patch27"))
     np.testing.assert_allclose(O.bf16_bits_to_f32(feat), GO["objfeat_patch27"], rtol=0, atol=2.0 ** -7)
+
+
+# ---------------------------------------------------------------------------------------------
+# projector tail: the torch port == the reference's get_2dPool / PE / add_token_per_grid
+# ---------------------------------------------------------------------------------------------
+TAIL_CASES = ["bilinear_1152", "bilinear_3584", "average_1152", "max_1152", "bilinear_16_264"]
+
+
+@pytest.mark.parametrize("tag", TAIL_CASES)
+def test_torch_port_projector_tail_matches_reference(golden_dir, tag):
+    import hashlib
+
+    import torch
+
+    from oracle import torch_port as TP
+    from video_3d_llm_b200 import synthetic
+
+    G = np.load(os.path.join(golden_dir, "tail.npz"))
+    V, side, E, Go = (int(v) for v in G[f"{tag}_meta"])
+    tokens = synthetic.make_tokens(70, V, side * side, E)
+    coords = torch.from_numpy(G[f"{tag}_coords"]).to(torch.bfloat16)
+    newline = torch.from_numpy(G[f"{tag}_newline"]).view(torch.bfloat16)
+    mode = tag.split("_")[0]
+    pooled = TP.get_2dpool(tokens, 2, mode)
+    out = TP.projector_tail(tokens, coords, E, newline, 2, mode)
+    assert out.shape == (V * Go * (Go + 1), E)
+    sha = lambda t: hashlib.sha256(np.ascontiguousarray(t.contiguous().view(torch.int16).numpy()).tobytes()).digest()
+    assert sha(pooled) == G[f"{tag}_pooled_sha"].tobytes()
+    assert sha(out) == G[f"{tag}_out_sha"].tobytes()
+    np.testing.assert_array_equal(out.contiguous().view(torch.int16).numpy()[::7, ::5], G[f"{tag}_out_sample"])

@@ -20,6 +20,7 @@ BF16, F16, F32 = 0, 1, 2
 DIV_IEEE, DIV_RECIPROCAL = 0, 1
 POOL_AVG, POOL_MINMAX, POOL_SAMPLE9, POOL_SAMPLE5, POOL_SAMPLE1 = 0, 1, 2, 3, 4
 PE_NONE, PE_SINE3D = 0, 1
+TOKEN_POOL_BILINEAR, TOKEN_POOL_AVERAGE, TOKEN_POOL_MAX, TOKEN_POOL_NONE = 0, 1, 2, 3
 MC_MAX_PICK = 32
 MC_RECORD_INTS = 2 * MC_MAX_PICK + 4
 
@@ -29,6 +30,7 @@ SYMBOLS = (
     "v3d_boundary", "v3d_pool_coords",
     "v3d_discretize", "v3d_pe_table_bytes", "v3d_pe_table_build", "v3d_pe_sine3d", "v3d_frontend_pe",
     "v3d_mc_hash_slots", "v3d_mc_sample", "v3d_mc_voxelize", "v3d_mc_greedy", "v3d_mc_voxel_ids", "v3d_pe_mlp", "v3d_object_patch_masks", "v3d_masked_token_mean",
+    "v3d_token_pool_out_grid", "v3d_pool_pe_grid",
 )
 
 
@@ -46,6 +48,16 @@ class FrontendDesc(C.Structure):
         ("pe_mode", C.c_int), ("E", C.c_int), ("dim_t", C.c_void_p), ("table", C.c_void_p), ("table_rows", C.c_int),
         ("dtype", C.c_int), ("tokens_in", C.c_void_p), ("pe_out", C.c_void_p),
         ("pooled_out", C.c_void_p), ("pe_coords_out", C.c_void_p),
+    ]
+
+
+class PoolDesc(C.Structure):
+    """struct v3d_pool_desc"""
+
+    _fields_ = [
+        ("tokens", C.c_void_p), ("n_frames", C.c_int), ("src_grid", C.c_int), ("E", C.c_int), ("dtype", C.c_int),
+        ("pool_mode", C.c_int), ("stride", C.c_int), ("coords", C.c_void_p), ("n_points", C.c_int), ("dim_t", C.c_void_p),
+        ("table", C.c_void_p), ("table_rows", C.c_int), ("newline", C.c_void_p), ("out", C.c_void_p),
     ]
 
 
@@ -100,6 +112,8 @@ def load():
     lib.v3d_pe_mlp.argtypes = [vp, i, i, vp, vp, vp, vp, f, vp, vp, vp, vp, vp]
     lib.v3d_object_patch_masks.argtypes = [vp, i, i, i, i, vp, i, i, vp, vp]
     lib.v3d_masked_token_mean.argtypes = [vp, i, i, vp, i, vp, vp]
+    lib.v3d_token_pool_out_grid.argtypes = [i, i, i]
+    lib.v3d_pool_pe_grid.argtypes = [C.POINTER(PoolDesc), vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("v3d_version", "v3d_last_error", "v3d_selftest_division", "v3d_pool_points", "v3d_pe_table_bytes", "v3d_mc_hash_slots"):
