@@ -21,6 +21,20 @@ from video_3d_llm_b200 import cabi, projector_tail as PT, synthetic  # noqa: E40
 from video_3d_llm_b200.position_encoding import PositionEmbeddingSine3D  # noqa: E402
 
 DEV = torch.device("cuda:0")
+
+
+def assert_pooled_close(got: torch.Tensor, ref: torch.Tensor, max_frac=5e-4):
+    """Pooled tokens: equal except for a small fraction of elements that differ by at most one bf16/fp16 ulp of the
+    reference value -- or, where the four taps cancel, by the fp32 rounding error of the weighted sum (taps are
+    N(0,1): 4 operations x 2^-24 x |tap| < 2^-19)."""
+    g, r = got.cpu().float(), ref.float()
+    d = (g - r).abs()
+    rel = 2.0 ** -7 if ref.dtype == torch.bfloat16 else 2.0 ** -10
+    tol = torch.maximum(r.abs() * rel, torch.tensor(2.0 ** -19))
+    assert bool((d <= tol).all()), f"max error {float((d / tol).max()):.2f} x tolerance"
+    assert float((d > 0).float().mean()) <= max_frac, f"{float((d > 0).float().mean()):.3e} of the elements differ"
+
+
 TAIL_CASES = ["bilinear_1152", "bilinear_3584", "average_1152", "max_1152", "bilinear_16_264"]
 
 
@@ -44,16 +58,24 @@ def test_pool_pe_newline_matches_reference(golden_dir, tag):
     if mode == "max":
         assert torch.equal(got_pooled.cpu(), ref_pooled)
     else:
-        assert_bf16_close(bf16_bits(got_pooled), bf16_bits(ref_pooled), max_frac=5e-4)
+        assert_pooled_close(got_pooled, ref_pooled)
     # the fused tail
     pe = PositionEmbeddingSine3D(E)
     got = PT.pool_pe_newline(tokens.to(DEV), stride=2, mode=mode, coords=coords.to(DEV), position_embedding=pe, image_newline=newline.to(DEV))
     assert got.shape == (V * Go * (Go + 1), E) and got.dtype == torch.bfloat16
-    assert_bf16_close(bf16_bits(got), bf16_bits(ref), max_frac=1e-3)
+    # a pooled value on the other side of a bf16 tie moves the sum by one ulp OF THE POOLED VALUE (the PE is <= 1 in
+    # magnitude); where the two nearly cancel that is several ulps of the small result
     g4 = got.view(V, Go, Go + 1, E)
+    r4 = ref.view(V, Go, Go + 1, E)
+    d = (g4[:, :, :Go].cpu().float() - r4[:, :, :Go].float()).abs().reshape(V, Go * Go, E)
+    ulp = torch.maximum(ref_pooled.float().abs(), torch.tensor(1.0)) * 2.0 ** -7
+    assert bool((d <= ulp).all()), f"max error {float((d / ulp).max()):.2f} ulp of the pooled value"
+    assert float((d > 0).float().mean()) <= 1e-3
     assert torch.equal(g4[:, :, Go, :].cpu(), newline.expand(V, Go, E))  # add_token_per_grid: newline closes every row
     # against the vectors written by the reference itself
-    assert_bf16_close(bf16_bits(got)[::7, ::5], G[f"{tag}_out_sample"].view(np.uint16), max_frac=2e-3)
+    gold = torch.from_numpy(G[f"{tag}_out_sample"].copy()).view(torch.bfloat16).float()
+    dg = (got.cpu()[::7, ::5].float() - gold).abs()
+    assert float((dg > 0).float().mean()) <= 2e-3 and float(dg.max()) <= 2.0 ** -7 * 8
     # the two-step composition (pool kernel, then the PE module's fused add, then the newline kernel) agrees exactly
     two_step = PT.add_token_per_grid(pe(coords.to(DEV), add_to=got_pooled), newline.to(DEV))
     assert torch.equal(two_step, got)
@@ -81,7 +103,7 @@ def test_tail_other_dtypes_layouts_and_continuous_coords():
     out = PT.pool_pe_newline(tokens.to(DEV), stride=3, mode="bilinear")
     assert out.shape == (V, 16, E)
     ref = TP.get_2dpool(tokens, 3, "bilinear")
-    assert_bf16_close(bf16_bits(out), bf16_bits(ref), max_frac=5e-4)
+    assert_pooled_close(out, ref)
     # newline only (add_token_per_grid on its own) is a pure copy
     nl = newline.to(torch.bfloat16)
     assert torch.equal(PT.add_token_per_grid(tokens.to(DEV), nl.to(DEV)).cpu(), TP.add_token_per_grid(tokens, nl))
