@@ -11,6 +11,8 @@
       LlavaMetaModel.__init__, llava_arch.py:49)
   LlavaMetaForCausalLM.{average_coordinate_in_patch, minmax_coordinate_in_patch, sample_n_points,
       discrete_coords}                                                      (called at llava_arch.py:396-420)
+  LlavaMetaForCausalLM.{get_2dPool, add_token_per_grid}                     (called at :469 and :536; the slow-fast
+      variant `add_faster_video`, which this package does not implement, keeps the reference's own method)
 The 500-line prepare_inputs_labels_for_multimodal itself is left alone: with VideoProcessor(lazy=True) the
 `world_coords` it receives is a handle over raw depth/pose/intrinsics, so the first patched helper it
 calls runs the fused kernel and the (V,384,384,3) tensor is never built (video_utils.LazyWorldCoords).
@@ -26,7 +28,7 @@ def install(lazy: bool | None = None) -> dict:
     """Patch the reference modules in place; returns {dotted name: replacement} for inspection."""
     import importlib
 
-    from . import coords, position_encoding, video_utils
+    from . import coords, position_encoding, projector_tail, video_utils
 
     if lazy is None:
         lazy = os.environ.get("V3D_LAZY", "1") != "0"
@@ -65,7 +67,20 @@ def install(lazy: bool | None = None) -> dict:
         return coords.discrete_coords(world_coords, xyz_min, voxel_size=self.config.voxel_size,
                                       min_xyz_range=self.config.min_xyz_range, max_xyz_range=self.config.max_xyz_range)
 
-    for fn in (average_coordinate_in_patch, minmax_coordinate_in_patch, sample_n_points, discrete_coords):
+    ref_get_2dpool, ref_add_token_per_grid = cls.get_2dPool, cls.add_token_per_grid
+
+    def get_2dPool(self, image_feature, stride=2):
+        side = self.get_vision_tower().num_patches_per_side
+        if side * side != image_feature.shape[1]:
+            return ref_get_2dpool(self, image_feature, stride)
+        return projector_tail.get_2dPool(image_feature, stride, self.config.mm_spatial_pool_mode)
+
+    def add_token_per_grid(self, image_feature):
+        if getattr(self.config, "add_faster_video", False):
+            return ref_add_token_per_grid(self, image_feature)
+        return projector_tail.add_token_per_grid(image_feature, self.model.image_newline)
+
+    for fn in (average_coordinate_in_patch, minmax_coordinate_in_patch, sample_n_points, discrete_coords, get_2dPool, add_token_per_grid):
         setattr(cls, fn.__name__, fn)
         done[f"llava.model.llava_arch.LlavaMetaForCausalLM.{fn.__name__}"] = fn
     return done
