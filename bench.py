@@ -256,7 +256,7 @@ def mc_leg(rank: int, world: int, dev, steps: int, warmup: int):
     }
 
 
-def tail_leg(dev, n_frames: int = 256, steps: int = 10):
+def tail_leg(dev, n_frames: int = 512, steps: int = 10):
     """Secondary: the projector tail on the default recipe -- (V,27*27,3584) bf16 projector output ->
     bilinear 2x2 pool -> + sin-3D PE of the discretised patch coordinates -> newline per grid row, one kernel
     (k_pool_pe_grid), against the same operator sequence of the reference run by torch on the same GPU."""

@@ -59,6 +59,52 @@ __device__ __forceinline__ float pool_taps(int mode, float a, float b, float c, 
   return m;
 }
 
+// one 8-channel chunk of one output token: taps -> pooled value (rounded to OutT) -> + PE -> store
+template <typename OutT>
+__device__ __forceinline__ void pool_chunk(const PoolParams& p, const PeGeom& g, const OutT* __restrict__ table, const int* off,
+                                           const ChunkDesc* s_desc, const float* pts, int c8, const Chunk<OutT>& ca, const Chunk<OutT>& cb,
+                                           const Chunk<OutT>& cc, const Chunk<OutT>& cd, float wy0, float wy1, float wx0, float wx1,
+                                           OutT* po) {
+  const int ch = c8 * 8;
+  const int mode = p.mode;
+  Chunk<OutT> pe;
+  bool direct = false;
+  if (p.has_pe) {
+    const ChunkDesc d = s_desc[c8];
+    const int oa = off[d.a >> 16], ob = off[d.b >> 16];
+    direct = (oa < 0) || (ob < 0);
+    if (!direct) {
+      pe = chunk_ldg(table + (uint32_t)oa + (d.a & 0xffffu));
+      if ((g.nf & 7) != 0) chunk_or(pe, chunk_ldg(table + (uint32_t)ob + (d.b & 0xffffu)));
+    }
+  }
+  float fa[8], fb[8], fc[8], fd[8];
+  chunk_to_float(ca, fa);
+  chunk_to_float(cb, fb);
+  chunk_to_float(cc, fc);
+  chunk_to_float(cd, fd);
+  Chunk<OutT> pooled;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) pooled.v[e] = Elem<OutT>::from(pool_taps(mode, fa[e], fb[e], fc[e], fd[e], wy0, wy1, wx0, wx1));
+  if (p.has_pe) {
+    if (direct) {  // non-integer / out-of-range coordinates: evaluate the slot(s) of this chunk directly
+#pragma unroll 1
+      for (int e = 0; e < 8; ++e) {
+        const int s = (ch + e) / g.nf;
+        float val = 0.0f;
+        if (s < g.n_slots) {
+          const int j = ch + e - s * g.nf;
+          const int o = off[s];
+          val = (o >= 0) ? Elem<OutT>::to(table[o + (s * g.nf - ((s * g.nf) & ~7)) + j]) : pe_value(pts[s], j, p.dim_t);
+        }
+        pe.v[e] = Elem<OutT>::from(val);
+      }
+    }
+    pooled = chunk_add(pooled, pe);
+  }
+  chunk_st_stream(po + ch, pooled);
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(kPoolThreads) k_pool_pe_grid(const PoolParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -92,54 +138,23 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool_pe_grid(const PoolParams 
   const float wy0 = p.w0[oy], wy1 = p.w1[oy];
   const OutT* r0 = src + (size_t)y0 * Gs * E;
   const OutT* r1 = src + (size_t)y1 * Gs * E;
-  const int mode = p.mode;
-
   for (int ox = warp; ox < Go; ox += kWarps) {
     const int x0 = p.i0[ox], x1 = p.i1[ox];
     const float wx0 = p.w0[ox], wx1 = p.w1[ox];
     const OutT *pa = r0 + (size_t)x0 * E, *pb = r0 + (size_t)x1 * E, *pc = r1 + (size_t)x0 * E, *pd = r1 + (size_t)x1 * E;
     OutT* po = orow + (size_t)ox * E;
     const int* off = s_off + ox * n_off;
-    for (int c8 = lane; c8 < cpt; c8 += 32) {
-      const int ch = c8 * 8;
-      const Chunk<OutT> ca = chunk_ld_stream(pa + ch), cb = chunk_ld_stream(pb + ch), cc = chunk_ld_stream(pc + ch),
-                        cd = chunk_ld_stream(pd + ch);
-      Chunk<OutT> pe;
-      bool direct = false;
-      if (p.has_pe) {
-        const ChunkDesc d = s_desc[c8];
-        const int oa = off[d.a >> 16], ob = off[d.b >> 16];
-        direct = (oa < 0) || (ob < 0);
-        if (!direct) {
-          pe = chunk_ldg(table + (uint32_t)oa + (d.a & 0xffffu));
-          if ((g.nf & 7) != 0) chunk_or(pe, chunk_ldg(table + (uint32_t)ob + (d.b & 0xffffu)));
-        }
-      }
-      float fa[8], fb[8], fc[8], fd[8];
-      chunk_to_float(ca, fa);
-      chunk_to_float(cb, fb);
-      chunk_to_float(cc, fc);
-      chunk_to_float(cd, fd);
-      Chunk<OutT> pooled;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) pooled.v[e] = Elem<OutT>::from(pool_taps(mode, fa[e], fb[e], fc[e], fd[e], wy0, wy1, wx0, wx1));
-      if (p.has_pe) {
-        if (direct) {  // non-integer / out-of-range coordinates: evaluate the slot(s) of this chunk directly
-#pragma unroll 1
-          for (int e = 0; e < 8; ++e) {
-            const int s = (ch + e) / g.nf;
-            float val = 0.0f;
-            if (s < g.n_slots) {
-              const int j = ch + e - s * g.nf;
-              const int o = off[s];
-              val = (o >= 0) ? Elem<OutT>::to(table[o + (s * g.nf - ((s * g.nf) & ~7)) + j]) : pe_value(s_pts[ox * g.n_slots + s], j, p.dim_t);
-            }
-            pe.v[e] = Elem<OutT>::from(val);
-          }
-        }
-        pooled = chunk_add(pooled, pe);
-      }
-      chunk_st_stream(po + ch, pooled);
+    // two chunks per lane and iteration: eight 128-bit token loads in flight before the first use
+    for (int c8a = lane; c8a < cpt; c8a += 64) {
+      const int c8b = c8a + 32;
+      const bool has_b = c8b < cpt;
+      const int cha = c8a * 8, chb = (has_b ? c8b : c8a) * 8;
+      const Chunk<OutT> a0 = chunk_ld_stream(pa + cha), b0 = chunk_ld_stream(pb + cha), c0 = chunk_ld_stream(pc + cha),
+                        d0 = chunk_ld_stream(pd + cha);
+      const Chunk<OutT> a1 = chunk_ld_stream(pa + chb), b1 = chunk_ld_stream(pb + chb), c1 = chunk_ld_stream(pc + chb),
+                        d1 = chunk_ld_stream(pd + chb);
+      pool_chunk<OutT>(p, g, table, off, s_desc, s_pts + ox * g.n_slots, c8a, a0, b0, c0, d0, wy0, wy1, wx0, wx1, po);
+      if (has_b) pool_chunk<OutT>(p, g, table, off, s_desc, s_pts + ox * g.n_slots, c8b, a1, b1, c1, d1, wy0, wy1, wx0, wx1, po);
     }
   }
   if (nl) {  // add_token_per_grid: image_newline closes the grid row
