@@ -39,6 +39,8 @@ def install(lazy: bool | None = None) -> dict:
     class VideoProcessor(video_utils.VideoProcessor):
         def __init__(self, *a, **kw):
             kw.setdefault("lazy", lazy)
+            if os.environ.get("V3D_PACK_DIR"):
+                kw.setdefault("pack_dir", os.environ["V3D_PACK_DIR"])
             super().__init__(*a, **kw)
 
     for name, obj in (("unproject", video_utils.unproject), ("VideoProcessor", VideoProcessor),
