@@ -470,6 +470,41 @@ def test_mc_sampler_batch_ragged_and_edge_cases():
         assert r["order"] == list(order) and r["gains"] == list(gains) and (r["n_all"], r["n_sel"]) == (n_all, n_sel)
 
 
+def test_mc_full_size_properties():
+    """BASELINE config 3 size (300-frame scenes -> 150 candidates of 480x640, 0.1 m voxels): properties that do not need
+    the oracle at full size.  The same scenes as int32 depth take the exact operator sequence for every pixel (no FMA
+    estimate, no guard band): coverage bitsets and picks must be identical to the uint16 fast path."""
+    scenes16, scenes32 = [], []
+    for s in range(4):
+        seed = 700 + s
+        sc = synthetic.make_scene(seed, 150, n_total=300, frame_indices=np.arange(0, 300, 2), device=DEV)
+        pc = torch.from_numpy(synthetic.mesh_voxels(sc.room, sc.boxes, seed)).to(DEV)
+        base = {"poses": sc.poses, "intrinsics": sc.intrinsics, "pc_voxels": pc, "seed": seed}
+        scenes16.append(dict(base, depth=sc.depth))
+        scenes32.append(dict(base, depth=(sc.depth.to(torch.int32) & 0xFFFF)))
+    sampler = mc_sampling.MCSampler(device=DEV)
+    plan16, plan32 = sampler.plan(scenes16), sampler.plan(scenes32)
+    res16 = sampler.decode(sampler.run(plan16))
+    res32 = sampler.decode(sampler.run(plan32))
+    again = sampler.decode(sampler.run(plan16))
+    assert res16 == again  # deterministic, and re-running a plan clears its workspace
+    for i, (a, b) in enumerate(zip(res16, res32)):
+        np.testing.assert_array_equal(sampler.bitsets(plan16, i), sampler.bitsets(plan32, i))
+        assert a == b
+        bits = sampler.bitsets(plan16, i)
+        union = np.bitwise_or.reduce(bits, axis=0)
+        popc = lambda w: int(np.unpackbits(w.view(np.uint8)).sum())
+        assert a["n_all"] == popc(union)  # |union of frames & pc| (max_coverage_sampling.py:102)
+        assert len(a["order"]) == 32 and len(set(a["order"])) == 32 and all(0 <= f < 150 for f in a["order"])
+        assert all(x >= y for x, y in zip(a["gains"], a["gains"][1:]))  # greedy gains of a coverage function never grow
+        assert sum(a["gains"]) == a["n_sel"] <= a["n_all"]
+        used = np.zeros_like(union)
+        for f, g in zip(a["order"], a["gains"]):  # replay: every recorded gain is the marginal coverage of its pick
+            assert g == popc(bits[f] & ~used)
+            assert g == max(popc(bits[k] & ~used) for k in range(150) if k not in a["order"][: a["order"].index(f)])
+            used |= bits[f]
+
+
 def test_mc_sampler_golden(golden_dir):
     """Against the output of the reference's own max_coverage_sampling.main (tests/golden/dataset.json)."""
     with open(os.path.join(golden_dir, "dataset.json")) as f:

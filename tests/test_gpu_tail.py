@@ -127,3 +127,31 @@ def test_tail_errors_and_empty():
     with pytest.raises(RuntimeError):
         PT.pool_pe_newline(tokens.cpu())
     assert PT.pool_pe_newline(tokens[:0]).shape == (0, 9, 64)
+
+
+def test_tail_full_size_properties():
+    """Default-recipe size (16 scenes x 32 frames, 27x27 -> 14x14, E = 3584): properties that hold without the oracle."""
+    V, side, E, Go = 512, 27, 3584, 14
+    g = torch.Generator(device=DEV).manual_seed(11)
+    tokens = torch.randn((V, side * side, E), generator=g, device=DEV, dtype=torch.float32).to(torch.bfloat16)
+    coords = torch.randint(0, 101, (V, Go * Go, 3), generator=g, device=DEV).to(torch.bfloat16)
+    newline = torch.randn(E, generator=g, device=DEV).to(torch.bfloat16)
+    pe = PositionEmbeddingSine3D(E)
+    out = PT.pool_pe_newline(tokens, coords=coords, position_embedding=pe, image_newline=newline)
+    assert out.shape == (V * Go * (Go + 1), E)
+    assert torch.equal(out, PT.pool_pe_newline(tokens, coords=coords, position_embedding=pe, image_newline=newline))  # deterministic
+    o4 = out.view(V, Go, Go + 1, E)
+    assert torch.equal(o4[:, :, Go], newline.expand(V, Go, E))
+    # the fused result is the composition of its parts: pooled tokens + the module's PE, rounded once more
+    pooled = PT.get_2dPool(tokens, 2, "bilinear")
+    assert torch.equal(o4[:, :, :Go].reshape(V, Go * Go, E), pooled + pe(coords))
+    # identity pooling + newline is a copy; a constant image pools to the same constant (weights sum to one)
+    ident = PT.pool_pe_newline(tokens[:8], mode="none", image_newline=newline).view(8, side, side + 1, E)
+    assert torch.equal(ident[:, :, :side].reshape(8, side * side, E), tokens[:8])
+    const = torch.full((4, side * side, E), 0.625, device=DEV, dtype=torch.bfloat16)
+    for mode in ("bilinear", "average", "max"):
+        assert torch.equal(PT.get_2dPool(const, 2, mode), torch.full((4, (13 if mode != "bilinear" else 14) ** 2, E), 0.625, device=DEV, dtype=torch.bfloat16))
+    # first frames against the CPU restatement of the reference
+    ref = TP.projector_tail(tokens[:2].cpu(), coords[:2].cpu(), E, newline.cpu(), 2, "bilinear").view(2, Go, Go + 1, E)
+    d = (o4[:2].cpu().float() - ref.float()).abs()
+    assert float((d > 0).float().mean()) <= 1e-3 and float(d.max()) <= 2.0 ** -7 * 8
