@@ -723,6 +723,19 @@ def test_windowed_depth_upload_feeds_the_same_result(scene):
     a = fe(d, p, k)
     b = fe(scene.depth.to(DEV), p, k)
     assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+    # packed form: one contiguous H2D copy + device-side expansion gives the same frames inside the window
+    assert fe.packed_shape(3) == (3, 384, 472)
+    packed = fe.pack_window(scene.depth)
+    assert packed.is_pinned() and torch.equal(packed.view(3, 96, 4, 472), ref[:, :, :4, 80:552])
+    poison2 = torch.full(h.shape, 23456, dtype=h.dtype, device=DEV)
+    d2 = fe.upload_packed(packed, out=poison2)
+    torch.cuda.synchronize()
+    got2 = d2.cpu().view(3, 96, 5, 640)
+    assert torch.equal(got2[:, :, :4, 80:552], ref[:, :, :4, 80:552])
+    assert bool((got2[:, :, 4, :] == 23456).all()) and bool((got2[:, :, :, 552:] == 23456).all())
+    assert torch.equal(fe(d2, p, k).view(torch.int16), b.view(torch.int16))
+    with pytest.raises(ValueError):
+        fe.upload_packed(packed[:, :100].contiguous().pin_memory())
     # the 'resize' strategy squeezes all 640 columns into 384: the window starts at column 0 (rows still 4 of 5)
     fe2 = FrontEnd(device=DEV, patch_size=27, embedding_size=3584, strategy="resize")
     x_off, width, period, keep = fe2.upload_window(2)

@@ -88,3 +88,21 @@ def test_int32_depth_pack_round_trip(tmp_path):
     d, p, k = scene_pack.ScenePack(path).load([10, 30])
     assert d.dtype == torch.int32 and np.array_equal(d.numpy(), depth[[1, 0]])
     assert np.array_equal(p.numpy(), poses[[1, 0]]) and np.array_equal(k.numpy(), np.repeat(intr[None], 2, 0))
+
+
+def test_windowed_load_keeps_exactly_the_samples_the_front_end_reads(dataset, packed):
+    vp = _vp(dataset)
+    video_id = sorted(vp.scene)[0]
+    pk = scene_pack.ScenePack(scene_pack.pack_path(packed, video_id))
+    if pk.H % 5:
+        pytest.skip("fixture frames are not a multiple of 5 rows")
+    es = 2
+    x_off, width = 16 * ((pk.W // 8) * es // 16), 16 * ((pk.W // 2) * es // 16)
+    window = (x_off, width, 5, 4)
+    full, _, _ = pk.load(pk.ids[:3])
+    win, _, _ = pk.load(pk.ids[:3], window=window)
+    assert tuple(win.shape) == (3, pk.H // 5 * 4, width // es)
+    ref = full.view(3, pk.H // 5, 5, pk.W)[:, :, :4, x_off // es:(x_off + width) // es].reshape(win.shape)
+    assert torch.equal(win, ref)
+    with pytest.raises(ValueError):
+        pk.load(pk.ids[:1], window=(0, 2 * pk.W * es, 1, 1))

@@ -1035,6 +1035,26 @@ int v3d_upload_depth_window(const void* depth_host, void* depth_dev, size_t pitc
   return V3D_OK;
 }
 
+int v3d_expand_depth_window(const void* packed_dev, void* depth_dev, size_t pitch_bytes, size_t n_rows_total, size_t x_off_bytes,
+                            size_t width_bytes, size_t row_period, size_t rows_keep, v3d_stream_t stream) {
+  V3D_REQUIRE(packed_dev && depth_dev, V3D_E_ARG, "v3d_expand_depth_window: null pointer");
+  V3D_REQUIRE(pitch_bytes > 0 && width_bytes > 0 && x_off_bytes + width_bytes <= pitch_bytes, V3D_E_ARG,
+              "v3d_expand_depth_window: window [%zu,+%zu) outside a row of %zu bytes", x_off_bytes, width_bytes, pitch_bytes);
+  V3D_REQUIRE(row_period > 0 && rows_keep > 0 && rows_keep <= row_period && n_rows_total % row_period == 0, V3D_E_ARG,
+              "v3d_expand_depth_window: %zu rows are not a whole number of groups of %zu", n_rows_total, row_period);
+  if (n_rows_total == 0) return V3D_OK;
+  cudaMemcpy3DParms prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.srcPtr = make_cudaPitchedPtr(const_cast<void*>(packed_dev), width_bytes, width_bytes, rows_keep);
+  prm.dstPtr = make_cudaPitchedPtr(depth_dev, pitch_bytes, pitch_bytes, row_period);
+  prm.srcPos = make_cudaPos(0, 0, 0);
+  prm.dstPos = make_cudaPos(x_off_bytes, 0, 0);
+  prm.extent = make_cudaExtent(width_bytes, rows_keep, n_rows_total / row_period);
+  prm.kind = cudaMemcpyDeviceToDevice;
+  V3D_CUDA(cudaMemcpy3DAsync(&prm, (cudaStream_t)stream));
+  return V3D_OK;
+}
+
 int v3d_boundary(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
                  float depth_scale, const float* clamp_lo_hi_host, float* out6, v3d_stream_t stream) {
   V3D_REQUIRE(depth && poses && intr && out6, V3D_E_ARG, "v3d_boundary: null pointer");

@@ -109,6 +109,51 @@ class FrontEnd:
                                                         cabi.stream_ptr(self.device)), "v3d_upload_depth_window")
         return out
 
+    def packed_shape(self, n_frames: int, esize: int = 2):
+        """(n_frames, rows kept per frame, window width in elements) of the packed window layout."""
+        x_off, width, period, keep = self.upload_window(esize)
+        return n_frames, self.cfg.H // period * keep, width // esize
+
+    def pack_window(self, depth_host: torch.Tensor, out: torch.Tensor | None = None, pin: bool = True) -> torch.Tensor:
+        """Host-side: keep only the depth samples the kernel reads, contiguously (what a loader that already skips the
+        rest produces, e.g. ScenePack.load(window=...)).  (V,H,W) -> (V, rows kept, window width)."""
+        V, H, W = depth_host.shape
+        es = depth_host.element_size()
+        x_off, width, period, keep = self.upload_window(es)
+        if out is None:
+            out = torch.empty(self.packed_shape(V, es), dtype=depth_host.dtype, pin_memory=pin)
+        src = depth_host.view(V, H // period, period, W)[:, :, :keep, x_off // es:(x_off + width) // es]
+        out.view(V, H // period, keep, width // es).copy_(src)
+        return out
+
+    def upload_packed(self, packed_host: torch.Tensor, staging: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Stream-ordered: ONE contiguous host -> device copy of a packed window (pinned), then a device-side strided
+        expansion into the (V,H,W) layout __call__ reads.  Samples outside the window are unspecified and never read."""
+        if packed_host.is_cuda or not packed_host.is_pinned():
+            raise ValueError("upload_packed() takes a pinned host tensor")
+        V = packed_host.shape[0]
+        es = packed_host.element_size()
+        if tuple(packed_host.shape) != self.packed_shape(V, es) or not packed_host.is_contiguous():
+            raise ValueError(f"packed depth must be contiguous {self.packed_shape(V, es)}, got {tuple(packed_host.shape)}")
+        if staging is None:
+            staging = torch.empty(packed_host.shape, dtype=packed_host.dtype, device=self.device)
+        if out is None:
+            out = torch.empty((V, self.cfg.H, self.cfg.W), dtype=packed_host.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            staging.copy_(packed_host, non_blocking=True)
+        return self.expand_packed(staging, out)
+
+    def expand_packed(self, staging: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """Device-side strided expansion of a packed window (already on the device) into the (V,H,W) layout, on the
+        current stream -- separate from the copy so that a pipeline can keep its copy stream busy with DMAs only."""
+        V = staging.shape[0]
+        es = staging.element_size()
+        x_off, width, period, keep = self.upload_window(es)
+        with torch.cuda.device(self.device):
+            cabi.check(self.lib.v3d_expand_depth_window(staging.data_ptr(), out.data_ptr(), self.cfg.W * es, V * self.cfg.H, x_off, width,
+                                                        period, keep, cabi.stream_ptr(self.device)), "v3d_expand_depth_window")
+        return out
+
     def upload_bytes(self, n_frames: int, esize: int = 2) -> int:
         x_off, width, period, keep = self.upload_window(esize)
         return n_frames * (self.cfg.H // period) * keep * width

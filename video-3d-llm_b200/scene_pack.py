@@ -101,16 +101,28 @@ class ScenePack:
         except KeyError as e:
             raise KeyError(f"{self.path}: frame {e.args[0]} is not in the pack") from None
 
-    def load(self, frame_numbers, pin: bool = False):
+    def load(self, frame_numbers, pin: bool = False, window=None):
         """(depth, poses, intrinsics) tensors for the given frame numbers, like VideoProcessor.load_frames:
-        depth (V,H,W) int16 storage of uint16 (or int32), poses (V,4,4) f32, intrinsics (V,4,4) f32."""
+        depth (V,H,W) int16 storage of uint16 (or int32), poses (V,4,4) f32, intrinsics (V,4,4) f32.
+        window = FrontEnd.upload_window(itemsize) = (x_off_bytes, width_bytes, row_period, rows_keep): copy only the
+        samples the front end reads, packed as (V, H//period*keep, width) for FrontEnd.upload_packed."""
         rows = self.rows(frame_numbers)
         V = len(rows)
         store = torch.int16 if self.depth_dtype == np.uint16 else torch.int32
-        depth_t = torch.empty((V, self.H, self.W), dtype=store, pin_memory=pin)
-        dst = depth_t.numpy().view(self.depth_dtype)
-        for o, r in enumerate(rows):  # one contiguous H*W block per frame
-            dst[o] = self.depth[r]
+        if window is not None:
+            es = np.dtype(self.depth_dtype).itemsize
+            x_off, width, period, keep = window
+            if self.H % period or x_off % es or width % es or x_off + width > self.W * es:
+                raise ValueError(f"window {window} does not fit {self.H}x{self.W} frames")
+            depth_t = torch.empty((V, self.H // period * keep, width // es), dtype=store, pin_memory=pin)
+            dst = depth_t.numpy().view(self.depth_dtype).reshape(V, self.H // period, keep, width // es)
+            for o, r in enumerate(rows):
+                dst[o] = self.depth[r].reshape(self.H // period, period, self.W)[:, :keep, x_off // es:(x_off + width) // es]
+        else:
+            depth_t = torch.empty((V, self.H, self.W), dtype=store, pin_memory=pin)
+            dst = depth_t.numpy().view(self.depth_dtype)
+            for o, r in enumerate(rows):  # one contiguous H*W block per frame
+                dst[o] = self.depth[r]
         poses_t = torch.from_numpy(np.array(self.poses[rows]))
         intr_t = torch.from_numpy(np.array(self.intr)).unsqueeze(0).repeat(V, 1, 1)
         if pin:
