@@ -343,63 +343,6 @@ __device__ __forceinline__ void stream_pairs_clean(int l0, int cpt, int E, int n
   }
 }
 
-// The same streaming loop with the work cut into (token pair, block of 32*U chunk columns) units that the warps take
-// round-robin: balanced when the CTA has fewer pairs than warps (7 pairs for the 14x14 grid) or a pair count that
-// is not a multiple of the warp count (13 for 27x27), and the token loads of the next unit are issued before the
-// current unit is added and stored (2*U 128-bit loads in flight per lane).
-template <typename OutT, int U, bool STRADDLE, bool ADD>
-__device__ __forceinline__ void stream_units_clean(int cpt, int E, int n_pairs, int n_off, const OutT* __restrict__ table,
-                                                   const int* s_off, const ChunkDesc* s_desc, const OutT* tokens, OutT* out) {
-  constexpr int kWarps = kThreads / 32;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int blocks = (2 * cpt) / (32 * U);
-  const int n_units = n_pairs * blocks;
-  const uint32_t off_base = smem_u32(s_off);
-  Chunk<OutT> nxt[U];
-  int unit = warp;
-  auto rel_of = [&](int un, int u) -> size_t {
-    const int pair = un / blocks;
-    const int L = (un - pair * blocks) * 32 * U + lane + 32 * u;
-    const int ts = L >= cpt;
-    return (size_t)(2 * pair + ts) * E + (size_t)(L - (ts ? cpt : 0)) * 8;
-  };
-  if (ADD && unit < n_units) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) nxt[u] = chunk_ld_stream(tokens + rel_of(unit, u));
-  }
-  for (; unit < n_units; unit += kWarps) {
-    const int pair = unit / blocks;
-    const int lb = (unit - pair * blocks) * 32 * U + lane;
-    Chunk<OutT> tv[U], pe[U];
-    size_t rel[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int L = lb + 32 * u;
-      const int ts = L >= cpt;
-      const int c8 = L - (ts ? cpt : 0);
-      const uint2 d = lds_u2(s_desc + c8);
-      const uint32_t off = off_base + (uint32_t)((2 * pair + ts) * n_off) * 4u;
-      rel[u] = (size_t)(2 * pair + ts) * E + (size_t)c8 * 8;
-      if (ADD) tv[u] = nxt[u];
-      int o;
-      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + (d.x >> 16) * 4u));
-      pe[u] = chunk_ldg(table + ((uint32_t)o + (d.x & 0xffffu)));
-      if (STRADDLE) {
-        if ((int)(d.y >> 16) != n_off - 1) {
-          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(off + (d.y >> 16) * 4u));
-          chunk_or(pe[u], chunk_ldg(table + ((uint32_t)o + (d.y & 0xffffu))));
-        }
-      }
-    }
-    if (ADD && unit + kWarps < n_units) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) nxt[u] = chunk_ld_stream(tokens + rel_of(unit + kWarps, u));
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) chunk_st_stream(out + rel[u], ADD ? chunk_add(tv[u], pe[u]) : pe[u]);
-  }
-}
-
 // one token row, lanes stride its chunks (the odd last token of a CTA)
 template <typename OutT, bool STRADDLE, bool ADD>
 __device__ __forceinline__ void stream_single_clean(int tok, int cpt, int E, int n_off, const OutT* __restrict__ table,
@@ -431,13 +374,6 @@ __device__ __forceinline__ void stream_rows_clean(int cpt, int E, int n_tok, int
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_pairs = n_tok >> 1;
   const int total = 2 * cpt;
-#ifdef V3D_STREAM_UNITS
-  if (total % 96 == 0 && tokens != out) {
-    stream_units_clean<OutT, 3, STRADDLE, ADD>(cpt, E, n_pairs, n_off, table, s_off, s_desc, tokens, out);
-  } else if (total % 64 == 0 && tokens != out) {
-    stream_units_clean<OutT, 2, STRADDLE, ADD>(cpt, E, n_pairs, n_off, table, s_off, s_desc, tokens, out);
-  } else
-#endif
   if (total % 96 == 0) {
     for (int l0 = 0; l0 < total; l0 += 96)
       stream_pairs_clean<OutT, 3, STRADDLE, ADD>(l0 + lane, cpt, E, n_pairs, n_off, table, s_off, s_desc, tokens, out);
