@@ -1121,9 +1121,10 @@ int v3d_pe_sine3d(const float* coords, size_t n_tokens, int n_points, int E, con
   V3D_REQUIRE(!vec || ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(tokens_in) | reinterpret_cast<uintptr_t>(table)) & 15) == 0,
               V3D_E_ALIGN, "v3d_pe_sine3d: out/tokens/table must be 16-byte aligned");
   if (n_tokens == 0) return V3D_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec) return launch_pe_flat(coords, n_tokens, g, dim_t, table, dtype, tokens_in, out, s);
   const size_t smem = (size_t)g.cpt * sizeof(ChunkDesc) + (size_t)kPeTokPerCta * ((size_t)g.n_slots * 8 + 8);
   const int grid = grid_for((n_tokens + kPeTokPerCta - 1) / kPeTokPerCta, 1, 16);
-  cudaStream_t s = (cudaStream_t)stream;
   return dispatch_out(dtype, [&](auto tag) {
     using T = decltype(tag);
     if (smem > 48 * 1024) V3D_CUDA(cudaFuncSetAttribute(k_pe_sine3d<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -160,4 +160,8 @@ inline int make_pe_geom(int E, int n_points, int rows, PeGeom* g) {
   return V3D_OK;
 }
 
+// flat streaming PE (+ add) kernel of v3d_pool.cu, for rows that are whole 16-byte chunks
+int launch_pe_flat(const float* coords, size_t n_tokens, const PeGeom& g, const float* dim_t, const void* table, int dtype,
+                   const void* tokens, void* out, cudaStream_t s);
+
 }  // namespace v3d

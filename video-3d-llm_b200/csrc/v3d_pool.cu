@@ -105,7 +105,7 @@ __device__ __forceinline__ void pool_chunk(const PoolParams& p, const PeGeom& g,
   chunk_st_stream(po + ch, pooled);
 }
 
-template <typename OutT>
+template <typename OutT, bool ONE_TAP>
 __global__ void __launch_bounds__(kPoolThreads) k_pool_pe_grid(const PoolParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PeGeom g = p.g;
@@ -149,10 +149,16 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool_pe_grid(const PoolParams 
       const int c8b = c8a + 32;
       const bool has_b = c8b < cpt;
       const int cha = c8a * 8, chb = (has_b ? c8b : c8a) * 8;
-      const Chunk<OutT> a0 = chunk_ld_stream(pa + cha), b0 = chunk_ld_stream(pb + cha), c0 = chunk_ld_stream(pc + cha),
-                        d0 = chunk_ld_stream(pd + cha);
-      const Chunk<OutT> a1 = chunk_ld_stream(pa + chb), b1 = chunk_ld_stream(pb + chb), c1 = chunk_ld_stream(pc + chb),
-                        d1 = chunk_ld_stream(pd + chb);
+      const Chunk<OutT> a0 = chunk_ld_stream(pa + cha), a1 = chunk_ld_stream(pa + chb);
+      Chunk<OutT> b0 = a0, c0 = a0, d0 = a0, b1 = a1, c1 = a1, d1 = a1;
+      if constexpr (!ONE_TAP) {  // one tap when the grid is kept (V3D_TOKEN_POOL_NONE)
+        b0 = chunk_ld_stream(pb + cha);
+        c0 = chunk_ld_stream(pc + cha);
+        d0 = chunk_ld_stream(pd + cha);
+        b1 = chunk_ld_stream(pb + chb);
+        c1 = chunk_ld_stream(pc + chb);
+        d1 = chunk_ld_stream(pd + chb);
+      }
       pool_chunk<OutT>(p, g, table, off, s_desc, s_pts + ox * g.n_slots, c8a, a0, b0, c0, d0, wy0, wy1, wx0, wx1, po);
       if (has_b) pool_chunk<OutT>(p, g, table, off, s_desc, s_pts + ox * g.n_slots, c8b, a1, b1, c1, d1, wy0, wy1, wx0, wx1, po);
     }
@@ -161,6 +167,103 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool_pe_grid(const PoolParams 
     const OutT* nlp = reinterpret_cast<const OutT*>(p.newline);
     OutT* po = orow + (size_t)Go * E;
     for (int c8 = threadIdx.x; c8 < cpt; c8 += kPoolThreads) chunk_st_stream(po + c8 * 8, chunk_ldg(nlp + c8 * 8));
+  }
+}
+
+// ---- stand-alone PE (+ add) over a flat list of tokens -----------------------------------------------------
+// position_encoding.py:17-49 (+ the add of llava_arch.py:515) with the loop structure of the kernel above: 16 tokens
+// per CTA, one warp per token, two 8-channel chunks per lane and iteration (the token loads are issued before the
+// table loads and the adds).  PE only: 2 bytes written per element; with the add 2 read + 2 written.
+static constexpr int kFlatTok = 16;
+
+template <typename OutT>
+__global__ void __launch_bounds__(kPoolThreads) k_pe_flat(const float* __restrict__ coords, size_t n_tokens, const PeGeom g,
+                                                          const float* __restrict__ dim_t, const OutT* __restrict__ table,
+                                                          const OutT* tokens, OutT* out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int cpt = g.cpt, E = g.E, n_off = g.n_slots + 1;
+  ChunkDesc* s_desc = reinterpret_cast<ChunkDesc*>(smem_raw);
+  float* s_pts = reinterpret_cast<float*>(s_desc + cpt);
+  int* s_off = reinterpret_cast<int*>(s_pts + kFlatTok * g.n_slots);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kPoolThreads / 32;
+  for (int i = threadIdx.x; i < cpt; i += kPoolThreads) s_desc[i] = make_chunk_desc(i, g);
+  for (size_t t0 = (size_t)blockIdx.x * kFlatTok; t0 < n_tokens; t0 += (size_t)gridDim.x * kFlatTok) {
+    const int n_tok = (int)min((size_t)kFlatTok, n_tokens - t0);
+    __syncthreads();  // the previous block of tokens is done with s_off / s_pts
+    for (int i = threadIdx.x; i < n_tok * g.n_slots; i += kPoolThreads) {
+      const int tk = i / g.n_slots, sl = i - tk * g.n_slots;
+      const float x = __ldg(coords + (t0 + tk) * g.n_slots + sl);
+      s_pts[i] = x;
+      s_off[tk * n_off + sl] = pe_row_offset(x, sl, g, table != nullptr);
+    }
+    for (int tk = threadIdx.x; tk < n_tok; tk += kPoolThreads) s_off[tk * n_off + g.n_slots] = pe_zero_row_offset(g);
+    __syncthreads();
+    for (int tk = warp; tk < n_tok; tk += kWarps) {
+      const int* off = s_off + tk * n_off;
+      const float* pts = s_pts + tk * g.n_slots;
+      const OutT* tp = tokens ? tokens + (t0 + tk) * E : nullptr;
+      OutT* op = out + (t0 + tk) * E;
+      for (int c8a = lane; c8a < cpt; c8a += 64) {
+        const int c8b = c8a + 32;
+        const bool has_b = c8b < cpt;
+        Chunk<OutT> ta, tb;
+        if (tp) {
+          ta = chunk_ld_stream(tp + c8a * 8);
+          if (has_b) tb = chunk_ld_stream(tp + c8b * 8);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1 && !has_b) break;
+          const int c8 = h ? c8b : c8a, ch = c8 * 8;
+          const ChunkDesc d = s_desc[c8];
+          const int oa = off[d.a >> 16], ob = off[d.b >> 16];
+          Chunk<OutT> pe;
+          if (oa >= 0 && ob >= 0) {
+            pe = chunk_ldg(table + (uint32_t)oa + (d.a & 0xffffu));
+            if ((g.nf & 7) != 0) chunk_or(pe, chunk_ldg(table + (uint32_t)ob + (d.b & 0xffffu)));
+          } else {  // non-integer / out-of-range coordinates: evaluate the slot(s) of this chunk directly
+#pragma unroll 1
+            for (int e = 0; e < 8; ++e) {
+              const int s = (ch + e) / g.nf;
+              float val = 0.0f;
+              if (s < g.n_slots) {
+                const int j = ch + e - s * g.nf;
+                const int o = off[s];
+                val = (o >= 0) ? Elem<OutT>::to(table[o + (s * g.nf - ((s * g.nf) & ~7)) + j]) : pe_value(pts[s], j, dim_t);
+              }
+              pe.v[e] = Elem<OutT>::from(val);
+            }
+          }
+          chunk_st_stream(op + ch, tp ? chunk_add(h ? tb : ta, pe) : pe);
+        }
+      }
+    }
+  }
+}
+
+template <typename OutT>
+static int launch_pe_flat_t(const float* coords, size_t n_tokens, const PeGeom& g, const float* dim_t, const void* table,
+                            const void* tokens, void* out, cudaStream_t s) {
+  const size_t smem = sizeof(ChunkDesc) * g.cpt + (size_t)kFlatTok * (g.n_slots * sizeof(float) + (g.n_slots + 1) * sizeof(int)) + 16;
+  V3D_REQUIRE(smem <= 200 * 1024, V3D_E_UNSUPPORTED, "v3d_pe_sine3d: %zu bytes of shared memory", smem);
+  if (smem > 48 * 1024) V3D_CUDA(cudaFuncSetAttribute(k_pe_flat<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  size_t blocks = (n_tokens + kFlatTok - 1) / kFlatTok;
+  const size_t cap = (size_t)num_sms() * 32;
+  if (blocks > cap) blocks = cap;
+  k_pe_flat<OutT><<<(unsigned)blocks, kPoolThreads, smem, s>>>(coords, n_tokens, g, dim_t, reinterpret_cast<const OutT*>(table),
+                                                                reinterpret_cast<const OutT*>(tokens), reinterpret_cast<OutT*>(out));
+  return check_launch("k_pe_flat");
+}
+
+// E % 8 == 0 path of v3d_pe_sine3d (v3d_frontend.cu)
+int launch_pe_flat(const float* coords, size_t n_tokens, const PeGeom& g, const float* dim_t, const void* table, int dtype,
+                   const void* tokens, void* out, cudaStream_t s) {
+  switch (dtype) {
+    case V3D_BF16: return launch_pe_flat_t<__nv_bfloat16>(coords, n_tokens, g, dim_t, table, tokens, out, s);
+    case V3D_F16: return launch_pe_flat_t<__half>(coords, n_tokens, g, dim_t, table, tokens, out, s);
+    case V3D_F32: return launch_pe_flat_t<float>(coords, n_tokens, g, dim_t, table, tokens, out, s);
+    default: set_error("v3d_pe_sine3d: unknown dtype %d", dtype); return V3D_E_ARG;
   }
 }
 
@@ -244,10 +347,20 @@ int v3d_pool_pe_grid(const v3d_pool_desc* d, v3d_stream_t stream) {
   V3D_REQUIRE(smem <= 48 * 1024, V3D_E_UNSUPPORTED, "v3d_pool_pe_grid: %zu bytes of shared memory", smem);
   const dim3 grid((unsigned)d->n_frames * Go);
   cudaStream_t s = (cudaStream_t)stream;
+  const bool one = d->pool_mode == V3D_TOKEN_POOL_NONE;
   switch (d->dtype) {
-    case V3D_BF16: k_pool_pe_grid<__nv_bfloat16><<<grid, kPoolThreads, smem, s>>>(p); break;
-    case V3D_F16: k_pool_pe_grid<__half><<<grid, kPoolThreads, smem, s>>>(p); break;
-    default: k_pool_pe_grid<float><<<grid, kPoolThreads, smem, s>>>(p); break;
+    case V3D_BF16:
+      if (one) k_pool_pe_grid<__nv_bfloat16, true><<<grid, kPoolThreads, smem, s>>>(p);
+      else k_pool_pe_grid<__nv_bfloat16, false><<<grid, kPoolThreads, smem, s>>>(p);
+      break;
+    case V3D_F16:
+      if (one) k_pool_pe_grid<__half, true><<<grid, kPoolThreads, smem, s>>>(p);
+      else k_pool_pe_grid<__half, false><<<grid, kPoolThreads, smem, s>>>(p);
+      break;
+    default:
+      if (one) k_pool_pe_grid<float, true><<<grid, kPoolThreads, smem, s>>>(p);
+      else k_pool_pe_grid<float, false><<<grid, kPoolThreads, smem, s>>>(p);
+      break;
   }
   return check_launch("k_pool_pe_grid");
 }
