@@ -374,6 +374,15 @@ __device__ __forceinline__ void stream_rows_clean(int cpt, int E, int n_tok, int
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_pairs = n_tok >> 1;
   const int total = 2 * cpt;
+#ifdef V3D_STRADDLE_SIMPLE
+  if (STRADDLE) {
+    // slots that do not start on a 16-byte boundary (nf = 1194 for E = 3584): the pair layout spends ~60 instructions
+    // per chunk on descriptor and address arithmetic; one warp per token with per-chunk descriptors from shared memory
+    for (int tok = warp; tok < n_tok; tok += kWarps)
+      stream_single_clean<OutT, STRADDLE, ADD>(tok, cpt, E, n_off, table, s_off, s_desc, tokens, out);
+    return;
+  }
+#endif
   if (total % 96 == 0) {
     for (int l0 = 0; l0 < total; l0 += 96)
       stream_pairs_clean<OutT, 3, STRADDLE, ADD>(l0 + lane, cpt, E, n_pairs, n_off, table, s_off, s_desc, tokens, out);
