@@ -367,22 +367,63 @@ __device__ __forceinline__ void stream_single_clean(int tok, int cpt, int E, int
   }
 }
 
+// A pair of token rows per warp, lanes stride the chunk columns: the column's descriptor is read once for both rows
+// and the inner loop carries no per-pair address arithmetic.  For CTAs with few pairs (7 for the 14x14 grid) whose
+// slots do not start on 16-byte boundaries (nf = 1194 for E = 3584).
 template <typename OutT, bool STRADDLE, bool ADD>
+__device__ __forceinline__ void stream_pair_rows(int pair, int cpt, int E, int n_off, const OutT* __restrict__ table, const int* s_off,
+                                                 const ChunkDesc* s_desc, const OutT* tokens, OutT* out) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t off0 = smem_u32(s_off) + (uint32_t)(2 * pair * n_off) * 4u, off1 = off0 + (uint32_t)n_off * 4u;
+  const OutT* t0 = ADD ? tokens + (size_t)(2 * pair) * E : nullptr;
+  const OutT* t1 = ADD ? t0 + E : nullptr;
+  OutT* o0 = out + (size_t)(2 * pair) * E;
+  OutT* o1 = o0 + E;
+  const uint32_t none = (uint32_t)(n_off - 1);
+#pragma unroll 2
+  for (int c8 = lane; c8 < cpt; c8 += 32) {
+    const uint2 d = lds_u2(s_desc + c8);
+    Chunk<OutT> tv0, tv1;
+    if (ADD) {
+      tv0 = chunk_ld_stream(t0 + c8 * 8);
+      tv1 = chunk_ld_stream(t1 + c8 * 8);
+    }
+    const uint32_t sa = (d.x >> 16) * 4u, ka = d.x & 0xffffu;
+    int a0, a1;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(a0) : "r"(off0 + sa));
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(a1) : "r"(off1 + sa));
+    Chunk<OutT> pe0 = chunk_ldg(table + ((uint32_t)a0 + ka));
+    Chunk<OutT> pe1 = chunk_ldg(table + ((uint32_t)a1 + ka));
+    if (STRADDLE) {
+      if ((d.y >> 16) != none) {  // only the columns at slot boundaries touch a second slot
+        const uint32_t sb = (d.y >> 16) * 4u, kb = d.y & 0xffffu;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(a0) : "r"(off0 + sb));
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(a1) : "r"(off1 + sb));
+        chunk_or(pe0, chunk_ldg(table + ((uint32_t)a0 + kb)));
+        chunk_or(pe1, chunk_ldg(table + ((uint32_t)a1 + kb)));
+      }
+    }
+    chunk_st_stream(o0 + c8 * 8, ADD ? chunk_add(tv0, pe0) : pe0);
+    chunk_st_stream(o1 + c8 * 8, ADD ? chunk_add(tv1, pe1) : pe1);
+  }
+}
+
+template <typename OutT, bool STRADDLE, bool ADD, bool PAIR_ROWS = false>
 __device__ __forceinline__ void stream_rows_clean(int cpt, int E, int n_tok, int n_off, const OutT* __restrict__ table,
                                                   const int* s_off, const ChunkDesc* s_desc, const OutT* tokens, OutT* out) {
   constexpr int kWarps = kThreads / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_pairs = n_tok >> 1;
   const int total = 2 * cpt;
-#ifdef V3D_STRADDLE_SIMPLE
-  if (STRADDLE) {
+  if (STRADDLE && PAIR_ROWS) {
     // slots that do not start on a 16-byte boundary (nf = 1194 for E = 3584): the pair layout spends ~60 instructions
     // per chunk on descriptor and address arithmetic; one warp per token with per-chunk descriptors from shared memory
-    for (int tok = warp; tok < n_tok; tok += kWarps)
-      stream_single_clean<OutT, STRADDLE, ADD>(tok, cpt, E, n_off, table, s_off, s_desc, tokens, out);
+    for (int pair = warp; pair < n_pairs; pair += kWarps)
+      stream_pair_rows<OutT, STRADDLE, ADD>(pair, cpt, E, n_off, table, s_off, s_desc, tokens, out);
+    if ((n_tok & 1) && warp == (n_pairs % kWarps))
+      stream_single_clean<OutT, STRADDLE, ADD>(n_tok - 1, cpt, E, n_off, table, s_off, s_desc, tokens, out);
     return;
   }
-#endif
   if (total % 96 == 0) {
     for (int l0 = 0; l0 < total; l0 += 96)
       stream_pairs_clean<OutT, 3, STRADDLE, ADD>(l0 + lane, cpt, E, n_pairs, n_off, table, s_off, s_desc, tokens, out);
@@ -402,7 +443,9 @@ __device__ __forceinline__ void stream_rows_clean(int cpt, int E, int n_tok, int
 //   s_off  [n_tok][n_slots+1]  element offset of each slot's table row (-1 = evaluate directly);
 //                              entry n_slots is the zero row
 //   s_flag [n_tok]             1 = some slot of the token needs direct evaluation
-template <typename OutT>
+// PAIR_ROWS selects stream_pair_rows for slots that do not start on 16-byte boundaries.  It is a separate kernel
+// instantiation so that the code generated for the aligned geometries (E = 1152) is exactly what it was tuned to be.
+template <typename OutT, bool PAIR_ROWS = false>
 __device__ __forceinline__ void stream_pe(const PeGeom& g, const float* __restrict__ dim_t, const OutT* __restrict__ table,
                                           const float* s_pts, const int* s_off, const int* s_flag, const ChunkDesc* s_desc,
                                           int n_tok, const OutT* tokens, OutT* out) {
@@ -416,10 +459,10 @@ __device__ __forceinline__ void stream_pe(const PeGeom& g, const float* __restri
     const bool straddle = (g.nf & 7) != 0;
     if (table != nullptr && !any_direct) {
       if (tokens) {
-        if (straddle) stream_rows_clean<OutT, true, true>(g.cpt, g.E, n_tok, n_off, table, s_off, s_desc, tokens, out);
+        if (straddle) stream_rows_clean<OutT, true, true, PAIR_ROWS>(g.cpt, g.E, n_tok, n_off, table, s_off, s_desc, tokens, out);
         else stream_rows_clean<OutT, false, true>(g.cpt, g.E, n_tok, n_off, table, s_off, s_desc, tokens, out);
       } else {
-        if (straddle) stream_rows_clean<OutT, true, false>(g.cpt, g.E, n_tok, n_off, table, s_off, s_desc, tokens, out);
+        if (straddle) stream_rows_clean<OutT, true, false, PAIR_ROWS>(g.cpt, g.E, n_tok, n_off, table, s_off, s_desc, tokens, out);
         else stream_rows_clean<OutT, false, false>(g.cpt, g.E, n_tok, n_off, table, s_off, s_desc, tokens, out);
       }
       return;
@@ -661,7 +704,7 @@ __device__ __forceinline__ void pool_rows_fast(const Camera& cam, const Divisor&
   }
 }
 
-template <int DT, bool FROM_DEPTH, bool USE_TMA, typename OutT>
+template <int DT, bool FROM_DEPTH, bool USE_TMA, typename OutT, bool PAIR_ROWS = false>
 __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const FusedParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kEsz = (DT == V3D_DEPTH_U16) ? 2 : 4;
@@ -880,7 +923,7 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
   // ---- stream the PE rows of this patch row (G tokens x E channels), fused token add
   const size_t row0 = ((size_t)f * G + gi) * G;
   const OutT* tokens = reinterpret_cast<const OutT*>(p.tokens_in);
-  stream_pe<OutT>(p.g, p.dim_t, reinterpret_cast<const OutT*>(p.table), s_pts, s_off, s_flag, s_desc, G,
+  stream_pe<OutT, PAIR_ROWS>(p.g, p.dim_t, reinterpret_cast<const OutT*>(p.table), s_pts, s_off, s_flag, s_desc, G,
                      tokens ? tokens + row0 * p.g.E : nullptr, reinterpret_cast<OutT*>(p.pe_out) + row0 * p.g.E);
 }
 
@@ -1146,11 +1189,11 @@ int v3d_pe_sine3d(const float* coords, size_t n_tokens, int n_points, int E, con
 }  // extern "C"
 
 // ---- fused launcher ---------------------------------------------------------------------------
-template <int DT, bool FROM_DEPTH, bool USE_TMA, typename OutT>
+template <int DT, bool FROM_DEPTH, bool USE_TMA, typename OutT, bool PAIR_ROWS = false>
 static int launch_fused(const FusedParams& p, cudaStream_t s) {
   const size_t smem = fused_smem_bytes(p, FROM_DEPTH && USE_TMA);
   V3D_REQUIRE(smem <= 227 * 1024, V3D_E_UNSUPPORTED, "fused kernel needs %zu bytes of shared memory", smem);
-  auto kern = k_fused<DT, FROM_DEPTH, USE_TMA, OutT>;
+  auto kern = k_fused<DT, FROM_DEPTH, USE_TMA, OutT, PAIR_ROWS>;
   if (smem > 48 * 1024) V3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<p.n_frames * p.grid, kThreads, smem, s>>>(p);
   return check_launch("k_fused");
@@ -1163,6 +1206,9 @@ static int launch_fused_dt(int depth_dtype, bool use_tma, const FusedParams& p, 
   } else {
     switch (depth_dtype) {
       case V3D_DEPTH_U16:
+        // the main variant comes in two instantiations: the second streams pairs of token rows per warp when the slots do
+        // not start on 16-byte boundaries (nf % 8 != 0, e.g. nf = 1194 for E = 3584)
+        if (use_tma && p.pe_mode != V3D_PE_NONE && (p.g.nf & 7) != 0) return launch_fused<V3D_DEPTH_U16, true, true, OutT, true>(p, s);
         return use_tma ? launch_fused<V3D_DEPTH_U16, true, true, OutT>(p, s) : launch_fused<V3D_DEPTH_U16, true, false, OutT>(p, s);
       // int32 / float32 depth (the reference's in-memory dtypes) are API-compatibility inputs: they take the
       // plain-load variant, which keeps the number of kernel instantiations (and the build time) down
