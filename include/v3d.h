@@ -243,6 +243,14 @@ int v3d_pool_pe_grid(const v3d_pool_desc* desc, v3d_stream_t stream);
  * (fp32 accumulation, bf16 result; zeros when no token is selected).  tokens (T,C) bf16, masks (K,T) uint8. */
 int v3d_object_patch_masks(const float* coords, int V, int S, int patch, int grid, const float* boxes, int K, int threshold,
                            uint8_t* masks_out, v3d_stream_t stream);
+/* the same masks straight from depth/pose/intrinsics (row_map/col_map as for v3d_unproject: the resize + crop; the maps must
+ * hold at least grid*patch entries; clamp_lo_hi_host: the 'norm' clamp or NULL): the (V,S,S,3) tensor is never built.
+ * coord_dtype (v3d_dtype): the dtype the reference's world_coords has when it reaches llava_arch.py:360 -- coordinates
+ * are rounded to it before the comparison, so the result equals v3d_object_patch_masks on the materialised tensor. */
+int v3d_object_patch_masks_depth(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
+                                 float depth_scale, const int32_t* row_map, const int32_t* col_map, const float* clamp_lo_hi_host,
+                                 int coord_dtype, int patch, int grid, const float* boxes, int K, int threshold, uint8_t* masks_out,
+                                 v3d_stream_t stream);
 int v3d_masked_token_mean(const void* tokens_bf16, int T, int C, const uint8_t* masks, int K, void* out_bf16, v3d_stream_t stream);
 
 /* ---- learned-projection PE (tensor cores) ----------------------------------------------------

@@ -759,9 +759,18 @@ def test_object_patch_masks_bit_exact(golden_dir, kind):
     gold = np.unpackbits(GO[f"masks_{kind}"])[: int(np.prod(shape))].reshape(shape).astype(bool)
     np.testing.assert_array_equal(got, gold)  # the reference's own masks
     np.testing.assert_array_equal(got, O.object_patch_masks(coords.cpu().numpy(), GO["boxes"], kind))
-    # a lazy handle gives the same masks (materialised on demand)
+    # a lazy handle gives the same masks straight from depth: the (V,384,384,3) tensor is never built
     lazy = VU.LazyWorldCoords(sc.depth, sc.poses, sc.intrinsics)
     assert torch.equal(C.object_patch_masks(lazy, boxes, kind), torch.from_numpy(gold).to(DEV))
+    assert lazy._full is None
+    # in the dtype the trainer / the eval scripts cast world_coords to, and with the 'norm' clamp: equal to the
+    # materialised tensor of that dtype (the comparison runs on the rounded coordinates, as in the reference)
+    for dt in (torch.bfloat16, torch.float16):
+        for clamp in (None, ([-2.0, -1.5, 0.1], [1.5, 2.0, 1.9])):
+            hz = VU.LazyWorldCoords(sc.depth.to(DEV), sc.poses.to(DEV), sc.intrinsics.to(DEV), clamp=clamp).to(dt)
+            from_depth = C.object_patch_masks(hz, boxes, kind)
+            assert hz._full is None
+            assert torch.equal(from_depth, C.object_patch_masks(hz.materialize(), boxes, kind))
 
 
 def test_object_features_match_reference(golden_dir):

@@ -87,10 +87,32 @@ def object_patch_masks(world_coords, object_boxes, object_feature_type: str = "p
             break
     else:
         raise NotImplementedError(object_feature_type)
+    lib = cabi.load()
+    if isinstance(world_coords, LazyWorldCoords) and world_coords._full is None and not world_coords.batched:
+        # straight from depth: the (V,S,S,3) tensor the reference slices at :360-373 is never built
+        from .video_utils import _device_for
+
+        h = world_coords
+        dev = _device_for(h.depth)
+        depth = h.depth.to(dev).contiguous()
+        poses, intr = h.poses.to(dev, torch.float32).contiguous(), h.intrinsics.to(dev, torch.float32).contiguous()
+        V, H, W = depth.shape
+        rm, cm = h._maps(dev)
+        if patch * grid > rm.numel():
+            raise ValueError(f"patch*grid={patch * grid} exceeds the {rm.numel()}-pixel crop")
+        boxes = object_boxes.detach().to(dev, torch.float32).contiguous()
+        K = boxes.shape[0]
+        masks = torch.zeros((K, V, grid, grid), dtype=torch.uint8, device=dev)
+        lo_hi = None if h.clamp is None else cabi.host_floats(list(h.clamp[0]) + list(h.clamp[1]))
+        with torch.cuda.device(dev):
+            cabi.check(lib.v3d_object_patch_masks_depth(depth.data_ptr(), cabi.depth_code(depth), poses.data_ptr(), intr.data_ptr(), V, H, W,
+                                                        1000.0, rm.data_ptr(), cm.data_ptr(), lo_hi, cabi.dtype_code(h.dtype), patch, grid,
+                                                        boxes.data_ptr(), K, thr, masks.data_ptr(), cabi.stream_ptr(dev)),
+                       "v3d_object_patch_masks_depth")
+        return masks.bool()
     if isinstance(world_coords, LazyWorldCoords):
         world_coords = world_coords.materialize()
     cabi.require_cuda(world_coords, "world_coords")
-    lib = cabi.load()
     V, S = world_coords.shape[0], world_coords.shape[1]
     src = world_coords.detach().to(torch.float32).contiguous()
     boxes = object_boxes.detach().to(src.device, torch.float32).contiguous()

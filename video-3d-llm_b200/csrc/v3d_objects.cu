@@ -48,6 +48,68 @@ __global__ void __launch_bounds__(kObjThreads) k_object_masks(const float* __res
   }
 }
 
+// The same masks straight from depth: the patch's pixels are unprojected in the kernel (same device function and
+// operation order as v3d_unproject, so the coordinates -- and the masks -- are bit-identical to the materialised
+// path) instead of being read from a (V,S,S,3) tensor that would have to be built first (56.6 MB per 32 frames).
+// coord_dtype: the dtype the reference's tensor would have at this point (bf16 under the HF Trainer, fp16 in the
+// eval scripts, fp32 otherwise); coordinates are rounded to it before the comparison.
+template <int DT>
+__global__ void __launch_bounds__(kObjThreads) k_object_masks_depth(const void* __restrict__ depth, const float* __restrict__ poses,
+                                                                   const float* __restrict__ intr, int V, int H, int W, float depth_scale,
+                                                                   const int32_t* __restrict__ row_map, const int32_t* __restrict__ col_map,
+                                                                   Clamp clamp, int coord_dtype, int patch, int grid,
+                                                                   const float* __restrict__ boxes, int K, int threshold,
+                                                                   uint8_t* __restrict__ masks) {
+  extern __shared__ float s_px[];  // [3][patch*patch]
+  const int n_px = patch * patch;
+  const int cell = blockIdx.x;  // (frame, gi, gj)
+  const int gj = cell % grid, gi = (cell / grid) % grid, f = cell / (grid * grid);
+  const Camera cam = load_camera(poses, intr, f);
+  const Divisor ds = make_divisor(depth_scale);
+  for (int i = threadIdx.x; i < n_px; i += kObjThreads) {
+    const int dy = i / patch, dx = i - dy * patch;
+    const int sr = __ldg(row_map + gi * patch + dy), sc = __ldg(col_map + gj * patch + dx);
+    float x, y, z;
+    unproject_px(cam, load_depth<DT>(depth, ((size_t)f * H + sr) * W + sc), __fsub_rn((float)sc, cam.cx), __fsub_rn((float)sr, cam.cy), ds,
+                 x, y, z);
+    if (clamp.on) {
+      x = apply_clamp(clamp, x, 0);
+      y = apply_clamp(clamp, y, 1);
+      z = apply_clamp(clamp, z, 2);
+    }
+    if (coord_dtype == V3D_BF16) {
+      x = __bfloat162float(__float2bfloat16_rn(x));
+      y = __bfloat162float(__float2bfloat16_rn(y));
+      z = __bfloat162float(__float2bfloat16_rn(z));
+    } else if (coord_dtype == V3D_F16) {
+      x = __half2float(__float2half_rn(x));
+      y = __half2float(__float2half_rn(y));
+      z = __half2float(__float2half_rn(z));
+    }
+    s_px[i] = x;
+    s_px[n_px + i] = y;
+    s_px[2 * n_px + i] = z;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = warp; k < K; k += kObjThreads / 32) {
+    float lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float c = __ldg(boxes + 6 * k + a), h = __fdiv_rn(__ldg(boxes + 6 * k + 3 + a), 2.0f);
+      lo[a] = __fsub_rn(c, h);
+      hi[a] = __fadd_rn(c, h);
+    }
+    int cnt = 0;
+    for (int i = lane; i < n_px; i += 32) {
+      const float x = s_px[i], y = s_px[n_px + i], z = s_px[2 * n_px + i];
+      cnt += (lo[0] <= x && x <= hi[0] && lo[1] <= y && y <= hi[1] && lo[2] <= z && z <= hi[2]) ? 1 : 0;
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) masks[((size_t)k * V + f) * grid * grid + gi * grid + gj] = cnt >= threshold ? 1 : 0;
+  }
+}
+
 // one CTA per (object, block of 256*8 channels): compact the selected tokens chunk by chunk, accumulate in fp32
 static constexpr int kMeanThreads = 256;
 static constexpr int kMeanChunk = 2048;
@@ -111,6 +173,39 @@ int v3d_object_patch_masks(const float* coords, int V, int S, int patch, int gri
   V3D_REQUIRE(smem <= 48 * 1024, V3D_E_UNSUPPORTED, "v3d_object_patch_masks: patch %d too large", patch);
   k_object_masks<<<V * grid * grid, kObjThreads, smem, (cudaStream_t)stream>>>(coords, V, S, patch, grid, boxes, K, threshold, masks_out);
   return check_launch("k_object_masks");
+}
+
+int v3d_object_patch_masks_depth(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
+                                 float depth_scale, const int32_t* row_map, const int32_t* col_map, const float* clamp_lo_hi_host,
+                                 int coord_dtype, int patch, int grid, const float* boxes, int K, int threshold, uint8_t* masks_out,
+                                 v3d_stream_t stream) {
+  if (V == 0 || K == 0) return V3D_OK;
+  V3D_REQUIRE(depth && poses && intr && row_map && col_map && boxes && masks_out, V3D_E_ARG, "v3d_object_patch_masks_depth: null pointer");
+  V3D_REQUIRE(H > 0 && W > 0 && patch > 0 && grid > 0, V3D_E_ARG, "v3d_object_patch_masks_depth: bad sizes");
+  V3D_REQUIRE(coord_dtype == V3D_BF16 || coord_dtype == V3D_F16 || coord_dtype == V3D_F32, V3D_E_ARG, "v3d_object_patch_masks_depth: bad coord dtype");
+  const size_t smem = (size_t)3 * patch * patch * sizeof(float);
+  V3D_REQUIRE(smem <= 48 * 1024, V3D_E_UNSUPPORTED, "v3d_object_patch_masks_depth: patch %d too large", patch);
+  Clamp cl;
+  cl.on = clamp_lo_hi_host != nullptr;
+  for (int a = 0; a < 3; ++a) {
+    cl.lo[a] = cl.on ? clamp_lo_hi_host[a] : 0.f;
+    cl.hi[a] = cl.on ? clamp_lo_hi_host[3 + a] : 0.f;
+  }
+  const int blocks = V * grid * grid;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (depth_dtype) {
+    case V3D_DEPTH_U16:
+      k_object_masks_depth<V3D_DEPTH_U16><<<blocks, kObjThreads, smem, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, cl, coord_dtype, patch, grid, boxes, K, threshold, masks_out);
+      break;
+    case V3D_DEPTH_I32:
+      k_object_masks_depth<V3D_DEPTH_I32><<<blocks, kObjThreads, smem, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, cl, coord_dtype, patch, grid, boxes, K, threshold, masks_out);
+      break;
+    case V3D_DEPTH_F32:
+      k_object_masks_depth<V3D_DEPTH_F32><<<blocks, kObjThreads, smem, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, cl, coord_dtype, patch, grid, boxes, K, threshold, masks_out);
+      break;
+    default: set_error("v3d_object_patch_masks_depth: unknown depth dtype %d", depth_dtype); return V3D_E_ARG;
+  }
+  return check_launch("k_object_masks_depth");
 }
 
 int v3d_masked_token_mean(const void* tokens_bf16, int T, int C, const uint8_t* masks, int K, void* out_bf16, v3d_stream_t stream) {
