@@ -104,6 +104,80 @@ __global__ void __launch_bounds__(kThreads) k_unproject(const void* __restrict__
   }
 }
 
+// Rows of whole 4-pixel groups (OW % 4 == 0, every shape of the reference): one CTA per (frame, block of rows), so the
+// camera is loaded and its divisors are prepared once per CTA instead of once per group, and the pixel index needs no
+// 64-bit division.  Same staging: a warp's 32 groups are 384 consecutive output floats.
+template <int DT>
+__global__ void __launch_bounds__(kThreads) k_unproject_rows(const void* __restrict__ depth, const float* __restrict__ poses,
+                                                             const float* __restrict__ intr, int V, int H, int W, float depth_scale,
+                                                             const int32_t* __restrict__ row_map, const int32_t* __restrict__ col_map,
+                                                             int OH, int OW, int rows_per_block, uint32_t gpr_magic, Clamp clamp,
+                                                             float* __restrict__ out) {
+  __shared__ __align__(16) float stage[kThreads / 32][4 * 32 * 3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bpf = (OH + rows_per_block - 1) / rows_per_block;
+  const int f = blockIdx.x / bpf, r0 = (blockIdx.x - f * bpf) * rows_per_block;
+  const int r1 = min(OH, r0 + rows_per_block);
+  const int gpr = OW >> 2;
+  const int n = (r1 - r0) * gpr;
+  const Camera cam = load_camera(poses, intr, f);
+  const Divisor ds = make_divisor(depth_scale);
+  float* obase = out + ((size_t)f * OH + r0) * OW * 3;
+  const size_t total_f = (size_t)n * 12;
+  // four uint16 depths with one 64-bit load when the frame is read in place
+  const bool vec = DT == V3D_DEPTH_U16 && col_map == nullptr && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(depth) & 7) == 0;
+  for (int base = 0; base < n; base += kThreads) {
+    const int idx = base + (int)threadIdx.x;
+    float vals[12];
+    if (idx < n) {
+      const int rr = (int)__umulhi((uint32_t)idx, gpr_magic);  // idx / gpr (idx < 2^16)
+      const int c = (idx - rr * gpr) << 2;
+      const int r = r0 + rr;
+      const int sr = row_map ? __ldg(row_map + r) : r;
+      const float vm = __fsub_rn((float)sr, cam.cy);
+      const size_t row_base = ((size_t)f * H + sr) * W;
+      float d[4];
+      int sc[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[e] = col_map ? __ldg(col_map + c + e) : c + e;
+      if (vec) {
+        if constexpr (DT == V3D_DEPTH_U16) {
+          const uint2 q = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(depth) + row_base + c));
+          d[0] = (float)(q.x & 0xffffu);
+          d[1] = (float)(q.x >> 16);
+          d[2] = (float)(q.y & 0xffffu);
+          d[3] = (float)(q.y >> 16);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[e] = load_depth<DT>(depth, row_base + sc[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float x, y, z;
+        unproject_px(cam, d[e], __fsub_rn((float)sc[e], cam.cx), vm, ds, x, y, z);
+        vals[3 * e + 0] = apply_clamp(clamp, x, 0);
+        vals[3 * e + 1] = apply_clamp(clamp, y, 1);
+        vals[3 * e + 2] = apply_clamp(clamp, z, 2);
+      }
+    }
+    float* st = stage[warp];
+    if (idx < n) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) st[lane * 12 + k] = vals[k];
+    }
+    __syncwarp();
+    const size_t warp_first = (size_t)(base + warp * 32) * 12;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int j = (k * 32 + lane) * 4;
+      const size_t o = warp_first + j;
+      if (o + 4 <= total_f) st_stream_v4(obase + o, *reinterpret_cast<const uint4*>(st + j));
+    }
+    __syncwarp();
+  }
+}
+
 // ============================================================================================
 // 2. scene AABB ("boundry") straight from depth
 // ============================================================================================
@@ -1051,6 +1125,27 @@ int v3d_unproject(const void* depth, int depth_dtype, const float* poses, const 
   const size_t groups = ((size_t)V * OH * OW + 3) / 4;
   const int grid = grid_for(groups, kThreads, 16);
   cudaStream_t s = (cudaStream_t)stream;
+  const long row_blocks = (long)V * ((OH + 7) / 8);
+  if ((OW & 3) == 0 && (OW >> 2) >= 2 && (OW >> 2) <= 8191 && row_blocks <= 0x7fffffffL) {
+    // rows of whole 4-pixel groups: one CTA per (frame, 8 rows); idx / gpr by multiplication (idx < 2^16)
+    const int rpb = 8;
+    const uint32_t gpr = (uint32_t)(OW >> 2);
+    const uint32_t magic = (uint32_t)(0xffffffffu / gpr + 1u);
+    const long blocks = row_blocks;
+    switch (depth_dtype) {
+      case V3D_DEPTH_U16:
+        k_unproject_rows<V3D_DEPTH_U16><<<(unsigned)blocks, kThreads, 0, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, OH, OW, rpb, magic, cl, world_out);
+        break;
+      case V3D_DEPTH_I32:
+        k_unproject_rows<V3D_DEPTH_I32><<<(unsigned)blocks, kThreads, 0, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, OH, OW, rpb, magic, cl, world_out);
+        break;
+      case V3D_DEPTH_F32:
+        k_unproject_rows<V3D_DEPTH_F32><<<(unsigned)blocks, kThreads, 0, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, OH, OW, rpb, magic, cl, world_out);
+        break;
+      default: set_error("v3d_unproject: unknown depth dtype %d", depth_dtype); return V3D_E_ARG;
+    }
+    return check_launch("k_unproject_rows");
+  }
   switch (depth_dtype) {
     case V3D_DEPTH_U16:
       k_unproject<V3D_DEPTH_U16><<<grid, kThreads, 0, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, OH, OW, cl, world_out);
