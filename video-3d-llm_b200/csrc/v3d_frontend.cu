@@ -216,16 +216,43 @@ __global__ void __launch_bounds__(kThreads) k_boundary(const void* __restrict__ 
     const int f = item / slabs, r0 = (item - f * slabs) * rows_per_cta;
     const Camera cam = load_camera(poses, intr, f);
     const int r1 = min(r0 + rows_per_cta, H);
-    for (int i = threadIdx.x; i < (r1 - r0) * W; i += kThreads) {
-      const int r = r0 + i / W, c = i - (i / W) * W;
-      float p[3];
-      unproject_px(cam, load_depth<DT>(depth, ((size_t)f * H + r) * W + c), __fsub_rn((float)c, cam.cx),
-                   __fsub_rn((float)r, cam.cy), ds, p[0], p[1], p[2]);
+    if (DT == V3D_DEPTH_U16 && (W & 7) == 0 && W <= 65528 && (reinterpret_cast<uintptr_t>(depth) & 15) == 0) {
+      // eight pixels per 128-bit load; group index -> (row, column) by multiplication (index < 2^16)
+      if constexpr (DT == V3D_DEPTH_U16) {
+        const int gpr = W >> 3;
+        const uint32_t magic = gpr > 1 ? 0xffffffffu / (uint32_t)gpr + 1u : 0u;
+        for (int i = threadIdx.x; i < (r1 - r0) * gpr; i += kThreads) {
+          const int rr = gpr > 1 ? (int)__umulhi((uint32_t)i, magic) : i;
+          const int r = r0 + rr, c0 = (i - rr * gpr) << 3;
+          const float vm = __fsub_rn((float)r, cam.cy);
+          const uint4 q = ld_stream_v4(reinterpret_cast<const uint16_t*>(depth) + ((size_t)f * H + r) * W + c0);
+          const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const float v = apply_clamp(clamp, p[a], a);
-        mn[a] = min(mn[a], fkey_min(v));
-        mx[a] = max(mx[a], fkey_max(v));
+          for (int e = 0; e < 8; ++e) {
+            const float d = (float)((e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xffffu));
+            float p[3];
+            unproject_px(cam, d, __fsub_rn((float)(c0 + e), cam.cx), vm, ds, p[0], p[1], p[2]);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              const float v = apply_clamp(clamp, p[a], a);
+              mn[a] = min(mn[a], fkey_min(v));
+              mx[a] = max(mx[a], fkey_max(v));
+            }
+          }
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < (r1 - r0) * W; i += kThreads) {
+        const int r = r0 + i / W, c = i - (i / W) * W;
+        float p[3];
+        unproject_px(cam, load_depth<DT>(depth, ((size_t)f * H + r) * W + c), __fsub_rn((float)c, cam.cx),
+                     __fsub_rn((float)r, cam.cy), ds, p[0], p[1], p[2]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float v = apply_clamp(clamp, p[a], a);
+          mn[a] = min(mn[a], fkey_min(v));
+          mx[a] = max(mx[a], fkey_max(v));
+        }
       }
     }
   }
