@@ -440,9 +440,10 @@ def run_ours(args):
     value = world * n_frames * K / (ms / 1e3)
 
     # ---- end to end: host (pinned) depth/pose/intrinsics in, per-token voxel coordinates out ---
-    # pinned host inputs as the packed-scene loader emits them (ScenePack.load(window=...)): per frame only the depth samples
-    # the kernel reads (4 of 5 rows x the column window, 58 % of the frame), contiguous
-    h_depth, h_poses, h_intr = fe.pack_window(depth.cpu()), poses.cpu().pin_memory(), intr.cpu().pin_memory()
+    # pinned host inputs as the packed-scene loader emits them (ScenePack.load(resample=...)): the nearest-neighbour resize +
+    # crop of the reference's preprocess (video_utils.py:291-308) applied to the raw uint16 depth on the host -- per frame
+    # exactly the 378 x 378 samples the kernel reads (47 % of the frame), contiguous
+    h_depth, h_poses, h_intr = fe.pack_resampled(depth.cpu()), poses.cpu().pin_memory(), intr.cpu().pin_memory()
     d_depth, d_poses, d_intr = torch.empty_like(depth), torch.empty_like(poses), torch.empty_like(intr)
     d_stage = torch.empty(h_depth.shape, dtype=h_depth.dtype, device=dev)
     h_coords = torch.empty((n_frames, GRID, GRID, 3), dtype=torch.float32).pin_memory()
@@ -467,7 +468,7 @@ def run_ours(args):
                 events.append(ev)
         for (a, b), ev in zip(bounds, events):
             cur.wait_event(ev)
-            fe.expand_packed(d_stage[a:b], d_depth[a:b])  # device-side strided expansion into the frame layout
+            fe.scatter_resampled(d_stage[a:b], d_depth[a:b])  # back to the pixels the samples were taken from
             _, _, pe_coords = fe(d_depth[a:b], d_poses[a:b], d_intr[a:b], tokens=tokens[a:b], out=out[a:b], want_coords=True)
             d_coords[a:b].copy_(pe_coords)
         h_coords.copy_(d_coords, non_blocking=True)
@@ -489,7 +490,7 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dist.barrier()
     e2e_value = world * n_frames * Ke / float(te.item())
-    h2d = fe.upload_bytes(n_frames, h_depth.element_size()) + h_poses.numel() * 4 + h_intr.numel() * 4
+    h2d = h_depth.numel() * h_depth.element_size() + h_poses.numel() * 4 + h_intr.numel() * 4
     d2h = h_coords.numel() * 4
 
     # secondary: the reference's default recipe geometry (27-pixel windows -> 14x14 grid, E = 3584)
@@ -545,7 +546,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": BYTES_PER_FRAME_FUSED_ADD * n_frames, "kernel": "k_fused",
                          "avg_launch_us": kernel_s * 1e6},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": Ke, "note": "pinned host depth (packed by the loader to the 4-of-5 rows x column window the kernel reads: one contiguous DMA per chunk + device-side expansion)/pose/intrinsics -> device each step; vision tokens are produced on the "
+                    "steps": Ke, "note": "pinned host depth as the packed-scene loader emits it (nearest resize + crop applied to the raw uint16 depth on the host: the 378x378 samples per frame the kernel reads; contiguous DMAs + device-side scatter into the frame layout)/pose/intrinsics -> device each step; vision tokens are produced on the "
                     "device by the vision tower and stay resident; per-token voxel coordinates read back"},
             "gpu_launches": K,  # timed region: K launches of k_fused (the e2e leg launches 4 per step, the mc leg 4 per step)
             "clocks": clk,

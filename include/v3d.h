@@ -87,6 +87,14 @@ int v3d_upload_depth_window(const void* depth_host, void* depth_dev, size_t pitc
 int v3d_expand_depth_window(const void* packed_dev, void* depth_dev, size_t pitch_bytes, size_t n_rows_total, size_t x_off_bytes,
                             size_t width_bytes, size_t row_period, size_t rows_keep, v3d_stream_t stream);
 
+/* Depth that the LOADER already resampled: packed_dev (V,out_h,out_w) holds depth[f, row_map[r], col_map[c]] -- the
+ * nearest-neighbour resize + centre crop of llava/video_utils.py:291-308 applied to the raw depth (48 % of a ScanNet frame;
+ * scene_pack.ScenePack.load(resample=...), FrontEnd.pack_resampled).  This scatters it back into the (V,H,W) layout
+ * (depth_dev[f, row_map[r], col_map[c]] = packed[f, r, c]); everything else in depth_dev is left untouched and is never
+ * read by v3d_frontend_pe configured with the same maps. */
+int v3d_scatter_resampled_depth(const void* packed_dev, void* depth_dev, int depth_dtype, int V, int H, int W, const int32_t* row_map,
+                                const int32_t* col_map, int out_h, int out_w, v3d_stream_t stream);
+
 /* ---- helpers on materialised coordinates (API parity with the reference's call structure) --
  * v3d_pool_coords replaces llava/model/llava_arch.py:213-223 `average_coordinate_in_patch`,
  * :225-239 `minmax_coordinate_in_patch`, :241-257 `sample_n_points`.

@@ -706,6 +706,13 @@ def test_nan_pose_propagates_like_the_reference():
     assert np.isnan(got[1, :, 1194:2388]).all() and not np.isnan(got[0]).any()
 
 
+def geometry_maps(H, W):
+    from video_3d_llm_b200 import geometry
+
+    rows, cols = geometry.resample_maps_host(H, W, 384, "center_crop")
+    return list(rows), list(cols)
+
+
 def test_windowed_depth_upload_feeds_the_same_result(scene):
     """FrontEnd.upload copies only the depth samples the kernel reads; the result equals a full upload."""
     fe = FrontEnd(device=DEV, patch_size=14, embedding_size=1152)
@@ -736,6 +743,20 @@ def test_windowed_depth_upload_feeds_the_same_result(scene):
     assert torch.equal(fe(d2, p, k).view(torch.int16), b.view(torch.int16))
     with pytest.raises(ValueError):
         fe.upload_packed(packed[:, :100].contiguous().pin_memory())
+    # resampled form: the loader applies the nearest resize + crop to the depth; scattered back on the device
+    res = fe.pack_resampled(scene.depth)
+    assert fe.resampled_shape(3) == (3, 378, 378) and tuple(res.shape) == (3, 378, 378) and res.is_pinned()
+    rows_h, cols_h = geometry_maps(480, 640)
+    assert torch.equal(res, scene.depth[:, rows_h[:378]][:, :, cols_h[:378]])
+    poison3 = torch.full(h.shape, 3456, dtype=h.dtype, device=DEV)
+    d3 = fe.scatter_resampled(res.to(DEV), poison3)
+    torch.cuda.synchronize()
+    touched = torch.zeros(h.shape, dtype=torch.bool)
+    touched[:, torch.tensor(rows_h[:378])[:, None], torch.tensor(cols_h[:378])[None, :]] = True
+    assert torch.equal(d3.cpu()[touched], scene.depth[touched]) and bool((d3.cpu()[~touched] == 3456).all())
+    out_r, pooled_r, _ = fe(d3, p, k, want_coords=True)
+    out_f, pooled_f, _ = fe(scene.depth.to(DEV), p, k, want_coords=True)
+    assert torch.equal(out_r.view(torch.int16), out_f.view(torch.int16)) and torch.equal(pooled_r, pooled_f)
     # the 'resize' strategy squeezes all 640 columns into 384: the window starts at column 0 (rows still 4 of 5)
     fe2 = FrontEnd(device=DEV, patch_size=27, embedding_size=3584, strategy="resize")
     x_off, width, period, keep = fe2.upload_window(2)

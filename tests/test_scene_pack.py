@@ -106,3 +106,19 @@ def test_windowed_load_keeps_exactly_the_samples_the_front_end_reads(dataset, pa
     assert torch.equal(win, ref)
     with pytest.raises(ValueError):
         pk.load(pk.ids[:1], window=(0, 2 * pk.W * es, 1, 1))
+
+
+def test_resampled_load_is_the_nearest_resize_and_crop_of_the_depth(dataset, packed):
+    from video_3d_llm_b200 import geometry
+
+    vp = _vp(dataset)
+    video_id = sorted(vp.scene)[0]
+    pk = scene_pack.ScenePack(scene_pack.pack_path(packed, video_id))
+    rows, cols = geometry.resample_maps_host(pk.H, pk.W, 384, "center_crop")
+    rows, cols = rows[:378], cols[:378]
+    full, _, _ = pk.load(pk.ids[:2])
+    res, _, _ = pk.load(pk.ids[:2], resample=(rows, cols))
+    assert tuple(res.shape) == (2, 378, 378)
+    assert torch.equal(res, full[:, list(rows)][:, :, list(cols)])
+    with pytest.raises(ValueError):
+        pk.load(pk.ids[:1], resample=([0, pk.H], [0]))

@@ -178,6 +178,22 @@ __global__ void __launch_bounds__(kThreads) k_unproject_rows(const void* __restr
   }
 }
 
+// Depth that the loader already resampled (nearest-neighbour resize + crop of llava/video_utils.py:291-308 applied to the
+// uint16 depth instead of the fp32 coordinates: out_h x out_w samples per frame, 48 % of a ScanNet frame) is scattered
+// back to the pixels it was taken from, so that every kernel keeps reading the (V,H,W) layout with the original pixel
+// coordinates.  Pixels that the maps do not reference are left untouched (never read by v3d_frontend_pe).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_scatter_resampled(const T* __restrict__ packed, T* __restrict__ depth, int V, int H, int W,
+                                                                const int32_t* __restrict__ row_map, const int32_t* __restrict__ col_map,
+                                                                int OH, int OW) {
+  for (long row = blockIdx.x; row < (long)V * OH; row += gridDim.x) {
+    const int f = (int)(row / OH), r = (int)(row - (long)f * OH);
+    const T* src = packed + (size_t)row * OW;
+    T* dst = depth + ((size_t)f * H + __ldg(row_map + r)) * W;
+    for (int c = threadIdx.x; c < OW; c += kThreads) dst[__ldg(col_map + c)] = src[c];
+  }
+}
+
 // ============================================================================================
 // 2. scene AABB ("boundry") straight from depth
 // ============================================================================================
@@ -1227,6 +1243,26 @@ int v3d_expand_depth_window(const void* packed_dev, void* depth_dev, size_t pitc
   prm.kind = cudaMemcpyDeviceToDevice;
   V3D_CUDA(cudaMemcpy3DAsync(&prm, (cudaStream_t)stream));
   return V3D_OK;
+}
+
+int v3d_scatter_resampled_depth(const void* packed_dev, void* depth_dev, int depth_dtype, int V, int H, int W, const int32_t* row_map,
+                                const int32_t* col_map, int out_h, int out_w, v3d_stream_t stream) {
+  if (V == 0) return V3D_OK;
+  V3D_REQUIRE(packed_dev && depth_dev && row_map && col_map, V3D_E_ARG, "v3d_scatter_resampled_depth: null pointer");
+  V3D_REQUIRE(V > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0, V3D_E_ARG, "v3d_scatter_resampled_depth: bad sizes");
+  long blocks = (long)V * out_h;
+  const long cap = (long)num_sms() * 32;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (depth_dtype == V3D_DEPTH_U16)
+    k_scatter_resampled<uint16_t><<<(unsigned)blocks, kThreads, 0, s>>>(reinterpret_cast<const uint16_t*>(packed_dev), reinterpret_cast<uint16_t*>(depth_dev), V, H, W, row_map, col_map, out_h, out_w);
+  else if (depth_dtype == V3D_DEPTH_I32 || depth_dtype == V3D_DEPTH_F32)
+    k_scatter_resampled<uint32_t><<<(unsigned)blocks, kThreads, 0, s>>>(reinterpret_cast<const uint32_t*>(packed_dev), reinterpret_cast<uint32_t*>(depth_dev), V, H, W, row_map, col_map, out_h, out_w);
+  else {
+    set_error("v3d_scatter_resampled_depth: unknown depth dtype %d", depth_dtype);
+    return V3D_E_ARG;
+  }
+  return check_launch("k_scatter_resampled");
 }
 
 int v3d_boundary(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,

@@ -154,6 +154,36 @@ class FrontEnd:
                                                         period, keep, cabi.stream_ptr(self.device)), "v3d_expand_depth_window")
         return out
 
+    # ---- resampled form: exactly the samples the kernel reads (grid*patch rows x columns: 378 x 378 for the ScanNet recipe)
+    def resampled_shape(self, n_frames: int):
+        n = self.cfg.grid * self.cfg.patch_size
+        return n_frames, n, n
+
+    def pack_resampled(self, depth_host: torch.Tensor, out: torch.Tensor | None = None, pin: bool = True) -> torch.Tensor:
+        """Host-side nearest-neighbour resize + crop of the raw depth (llava/video_utils.py:291-308 applied to depth instead
+        of coordinates): (V,H,W) -> (V,n,n) with n = grid*patch.  What a loader that resamples on the host emits
+        (ScenePack.load(resample=...)); 47 % of the bytes of a ScanNet frame."""
+        V = depth_host.shape[0]
+        n = self.cfg.grid * self.cfg.patch_size
+        rows, cols = geometry.resample_maps_host(self.cfg.H, self.cfg.W, self.cfg.crop_size, self.cfg.strategy)
+        rows_t, cols_t = torch.as_tensor(rows[:n], dtype=torch.long), torch.as_tensor(cols[:n], dtype=torch.long)
+        if out is None:
+            out = torch.empty((V, n, n), dtype=depth_host.dtype, pin_memory=pin)
+        torch.index_select(depth_host.index_select(1, rows_t), 2, cols_t, out=out)
+        return out
+
+    def scatter_resampled(self, staging: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """Device side: put resampled depth (V,n,n) (already on the device) back at the pixels it was taken from in the
+        (V,H,W) layout __call__ reads, on the current stream."""
+        V, n, n2 = staging.shape
+        if (n, n2) != self.resampled_shape(V)[1:] or tuple(out.shape) != (V, self.cfg.H, self.cfg.W) or out.dtype != staging.dtype:
+            raise ValueError(f"resampled depth must be {self.resampled_shape(V)} and out (V,{self.cfg.H},{self.cfg.W}) of the same dtype")
+        with torch.cuda.device(self.device):
+            cabi.check(self.lib.v3d_scatter_resampled_depth(staging.data_ptr(), out.data_ptr(), cabi.depth_code(staging), V, self.cfg.H,
+                                                            self.cfg.W, self.row_map.data_ptr(), self.col_map.data_ptr(), n, n,
+                                                            cabi.stream_ptr(self.device)), "v3d_scatter_resampled_depth")
+        return out
+
     def upload_bytes(self, n_frames: int, esize: int = 2) -> int:
         x_off, width, period, keep = self.upload_window(esize)
         return n_frames * (self.cfg.H // period) * keep * width

@@ -101,15 +101,25 @@ class ScenePack:
         except KeyError as e:
             raise KeyError(f"{self.path}: frame {e.args[0]} is not in the pack") from None
 
-    def load(self, frame_numbers, pin: bool = False, window=None):
+    def load(self, frame_numbers, pin: bool = False, window=None, resample=None):
         """(depth, poses, intrinsics) tensors for the given frame numbers, like VideoProcessor.load_frames:
         depth (V,H,W) int16 storage of uint16 (or int32), poses (V,4,4) f32, intrinsics (V,4,4) f32.
         window = FrontEnd.upload_window(itemsize) = (x_off_bytes, width_bytes, row_period, rows_keep): copy only the
-        samples the front end reads, packed as (V, H//period*keep, width) for FrontEnd.upload_packed."""
+        samples the front end reads, packed as (V, H//period*keep, width) for FrontEnd.upload_packed.
+        resample = (rows, cols) index sequences: the nearest-neighbour resize + crop applied here, on the host, to the raw
+        depth -- depth[rows][:, cols] per frame, for FrontEnd.scatter_resampled."""
         rows = self.rows(frame_numbers)
         V = len(rows)
         store = torch.int16 if self.depth_dtype == np.uint16 else torch.int32
-        if window is not None:
+        if resample is not None:
+            rows_i, cols_i = np.asarray(resample[0], np.int64), np.asarray(resample[1], np.int64)
+            if rows_i.min() < 0 or rows_i.max() >= self.H or cols_i.min() < 0 or cols_i.max() >= self.W:
+                raise ValueError(f"resample maps reach outside {self.H}x{self.W} frames")
+            depth_t = torch.empty((V, len(rows_i), len(cols_i)), dtype=store, pin_memory=pin)
+            dst = depth_t.numpy().view(self.depth_dtype)
+            for o, r in enumerate(rows):
+                dst[o] = self.depth[r][rows_i][:, cols_i]
+        elif window is not None:
             es = np.dtype(self.depth_dtype).itemsize
             x_off, width, period, keep = window
             if self.H % period or x_off % es or width % es or x_off + width > self.W * es:
