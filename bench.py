@@ -245,13 +245,33 @@ def mc_leg(rank: int, world: int, dev, steps: int, warmup: int):
     ms = float(t.item())
     depth_bytes = sum(s["depth"].numel() * 2 + s["depth"].shape[0] * 80 + s["pc_voxels"].numel() * 4 + 272 for s in scenes)
     res = sampler.decode(rec)
+    # the same with the candidate frames coming from pinned host memory each step (reported separately: SURVEY 8d)
+    e2e = None
+    if world == 1:
+        h_depth = [s["depth"].cpu().pin_memory() for s in scenes]
+        for _ in range(2):
+            for s, h in zip(scenes, h_depth):
+                s["depth"].copy_(h, non_blocking=True)
+            sampler.decode(sampler.run(plan))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_e2e = 3
+        for _ in range(n_e2e):
+            for s, h in zip(scenes, h_depth):
+                s["depth"].copy_(h, non_blocking=True)
+            sampler.decode(sampler.run(plan))  # records read back to the host
+        e2e_s = time.perf_counter() - t0
+        e2e = {"value": n_scenes * n_e2e / e2e_s, "unit": "scenes/s", "h2d_bytes_per_step": int(sum(h.numel() * 2 for h in h_depth)),
+               "d2h_bytes_per_step": int(rec.numel() * 4),
+               "note": "all 150 candidate frames of every scene uploaded in full each step (92 MB per scene): PCIe-bound"}
+        del h_depth
     return {
         "metric": "MC-sampled scenes/sec (voxelise + greedy max-coverage, 32 picks)", "value": world * n_scenes * steps / (ms / 1e3),
         "unit": "scenes/s", "ms_per_step": ms / steps, "scenes_per_rank": n_scenes, "candidate_frames": cand, "voxel_size": 0.1,
         "voxelize_ms": ev[0].elapsed_time(ev[1]), "greedy_ms": ev[1].elapsed_time(ev[2]),
         "algorithmic_bytes_per_step": depth_bytes,
         "hbm_gbs_achieved_voxelize": depth_bytes / (ev[0].elapsed_time(ev[1]) / 1e3) / 1e9,
-        "allgather_bytes": int(allrec.numel() * 4), "mean_picks": float(np.mean([len(r["order"]) for r in res])),
+        "e2e": e2e, "allgather_bytes": int(allrec.numel() * 4), "mean_picks": float(np.mean([len(r["order"]) for r in res])),
         "mean_coverage": float(np.mean([r["n_sel"] / max(r["n_all"], 1) for r in res])),
     }
 
