@@ -40,3 +40,17 @@ c384 = VU.unproject(intr[:128], poses[:128], depth[:128], row_map=rm, col_map=cm
 ms = timed(lambda: C.average_coordinate_in_patch(c384, 27))
 res["pool_coords_avg27_128frames"] = {"ms": ms, "GBs": 128 * 378 * 378 * 12 / ms / 1e6}
 print(res)
+
+# object proposals: 32 frames, 100 boxes
+sc = scenes[0]
+boxes = torch.rand(100, 6, device=dev) * torch.tensor([4.0, 4.0, 2.0, 1.5, 1.5, 1.5], device=dev) + torch.tensor([-2.0, -2.0, 0.0, 0.2, 0.2, 0.2], device=dev)
+c32 = VU.unproject(sc.intrinsics, sc.poses, sc.depth, row_map=rm, col_map=cm)
+lazy = VU.LazyWorldCoords(sc.depth, sc.poses, sc.intrinsics)
+obj = {}
+for kind in ("patch14", "patch27"):
+    obj[kind + "_from_coords_ms"] = timed(lambda: C.object_patch_masks(c32, boxes, kind))
+    obj[kind + "_from_depth_ms"] = timed(lambda: C.object_patch_masks(lazy, boxes, kind))
+masks = C.object_patch_masks(c32, boxes, "patch27")
+feats = torch.randn(32, 196, 3584, device=dev).to(torch.bfloat16)
+obj["masked_token_mean_ms"] = timed(lambda: C.object_features(feats, masks))
+print({"object_proposals_32_frames_100_boxes": obj})

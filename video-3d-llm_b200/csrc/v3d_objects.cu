@@ -6,17 +6,64 @@
 //              "patch27": >= int(27*27*0.25) of the 729 pixels of a 27x27 window on the 14x14 grid)
 //   :479-496  object feature = mean of the token features of its patches (zeros if it has none)
 // One launch each for all objects instead of ~6 ATen kernels per object.
+#include <math_constants.h>
+
 #include "v3d_common.cuh"
 
 namespace v3d {
 
 static constexpr int kObjThreads = 128;
 
+// the patch's pixels are in shared memory ([3][n_px]); every warp tests its share of the boxes.  The patch's own
+// bounding box (NaN coordinates ignored: they are inside no box) rejects most boxes without looking at the pixels.
+__device__ __forceinline__ void count_boxes(const float* s_px, float* s_bbox, int n_px, const float* __restrict__ boxes, int K, int threshold,
+                                            uint8_t* __restrict__ masks, size_t cell_stride, size_t cell_off) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < 3) {  // warp a reduces axis a
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    for (int i = lane; i < n_px; i += 32) {
+      const float v = s_px[warp * n_px + i];
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+    }
+    for (int o = 16; o; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) {
+      s_bbox[2 * warp] = mn;
+      s_bbox[2 * warp + 1] = mx;
+    }
+  }
+  __syncthreads();
+  for (int k = warp; k < K; k += kObjThreads / 32) {
+    // min = centre - size/2, max = centre + size/2 in fp32, as the reference computes them per object (:363-364)
+    float lo[3], hi[3];
+    bool disjoint = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float c = __ldg(boxes + 6 * k + a), h = __fdiv_rn(__ldg(boxes + 6 * k + 3 + a), 2.0f);
+      lo[a] = __fsub_rn(c, h);
+      hi[a] = __fadd_rn(c, h);
+      disjoint = disjoint || hi[a] < s_bbox[2 * a] || lo[a] > s_bbox[2 * a + 1];
+    }
+    int cnt = 0;
+    if (!disjoint) {
+      for (int i = lane; i < n_px; i += 32) {
+        const float x = s_px[i], y = s_px[n_px + i], z = s_px[2 * n_px + i];
+        cnt += (lo[0] <= x && x <= hi[0] && lo[1] <= y && y <= hi[1] && lo[2] <= z && z <= hi[2]) ? 1 : 0;
+      }
+      for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) masks[(size_t)k * cell_stride + cell_off] = cnt >= threshold ? 1 : 0;
+  }
+}
+
 // one CTA per (frame, patch): the patch's pixels are staged once, then every warp tests its share of the boxes
 __global__ void __launch_bounds__(kObjThreads) k_object_masks(const float* __restrict__ coords, int V, int S, int patch, int grid,
                                                              const float* __restrict__ boxes, int K, int threshold,
                                                              uint8_t* __restrict__ masks) {
-  extern __shared__ float s_px[];  // [3][patch*patch]
+  extern __shared__ float s_px[];  // [3][patch*patch] + the patch's bounding box [6]
   const int n_px = patch * patch;
   const int cell = blockIdx.x;  // (frame, gi, gj)
   const int gj = cell % grid, gi = (cell / grid) % grid, f = cell / (grid * grid);
@@ -28,24 +75,7 @@ __global__ void __launch_bounds__(kObjThreads) k_object_masks(const float* __res
     s_px[2 * n_px + i] = __ldg(src + 2);
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = warp; k < K; k += kObjThreads / 32) {
-    // min = centre - size/2, max = centre + size/2 in fp32, as the reference computes them per object (:363-364)
-    float lo[3], hi[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float c = __ldg(boxes + 6 * k + a), h = __fdiv_rn(__ldg(boxes + 6 * k + 3 + a), 2.0f);
-      lo[a] = __fsub_rn(c, h);
-      hi[a] = __fadd_rn(c, h);
-    }
-    int cnt = 0;
-    for (int i = lane; i < n_px; i += 32) {
-      const float x = s_px[i], y = s_px[n_px + i], z = s_px[2 * n_px + i];
-      cnt += (lo[0] <= x && x <= hi[0] && lo[1] <= y && y <= hi[1] && lo[2] <= z && z <= hi[2]) ? 1 : 0;
-    }
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) masks[((size_t)k * V + f) * grid * grid + gi * grid + gj] = cnt >= threshold ? 1 : 0;
-  }
+  count_boxes(s_px, s_px + 3 * n_px, n_px, boxes, K, threshold, masks, (size_t)V * grid * grid, (size_t)f * grid * grid + gi * grid + gj);
 }
 
 // The same masks straight from depth: the patch's pixels are unprojected in the kernel (same device function and
@@ -60,7 +90,7 @@ __global__ void __launch_bounds__(kObjThreads) k_object_masks_depth(const void* 
                                                                    Clamp clamp, int coord_dtype, int patch, int grid,
                                                                    const float* __restrict__ boxes, int K, int threshold,
                                                                    uint8_t* __restrict__ masks) {
-  extern __shared__ float s_px[];  // [3][patch*patch]
+  extern __shared__ float s_px[];  // [3][patch*patch] + the patch's bounding box [6]
   const int n_px = patch * patch;
   const int cell = blockIdx.x;  // (frame, gi, gj)
   const int gj = cell % grid, gi = (cell / grid) % grid, f = cell / (grid * grid);
@@ -91,23 +121,7 @@ __global__ void __launch_bounds__(kObjThreads) k_object_masks_depth(const void* 
     s_px[2 * n_px + i] = z;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = warp; k < K; k += kObjThreads / 32) {
-    float lo[3], hi[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float c = __ldg(boxes + 6 * k + a), h = __fdiv_rn(__ldg(boxes + 6 * k + 3 + a), 2.0f);
-      lo[a] = __fsub_rn(c, h);
-      hi[a] = __fadd_rn(c, h);
-    }
-    int cnt = 0;
-    for (int i = lane; i < n_px; i += 32) {
-      const float x = s_px[i], y = s_px[n_px + i], z = s_px[2 * n_px + i];
-      cnt += (lo[0] <= x && x <= hi[0] && lo[1] <= y && y <= hi[1] && lo[2] <= z && z <= hi[2]) ? 1 : 0;
-    }
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) masks[((size_t)k * V + f) * grid * grid + gi * grid + gj] = cnt >= threshold ? 1 : 0;
-  }
+  count_boxes(s_px, s_px + 3 * n_px, n_px, boxes, K, threshold, masks, (size_t)V * grid * grid, (size_t)f * grid * grid + gi * grid + gj);
 }
 
 // one CTA per (object, block of 256*8 channels): compact the selected tokens chunk by chunk, accumulate in fp32
@@ -169,7 +183,7 @@ int v3d_object_patch_masks(const float* coords, int V, int S, int patch, int gri
   if (V == 0 || K == 0) return V3D_OK;
   V3D_REQUIRE(coords && boxes && masks_out, V3D_E_ARG, "v3d_object_patch_masks: null pointer");
   V3D_REQUIRE(S > 0 && patch > 0 && grid > 0 && patch * grid <= S, V3D_E_ARG, "v3d_object_patch_masks: patch*grid=%d exceeds S=%d", patch * grid, S);
-  const size_t smem = (size_t)3 * patch * patch * sizeof(float);
+  const size_t smem = ((size_t)3 * patch * patch + 8) * sizeof(float);
   V3D_REQUIRE(smem <= 48 * 1024, V3D_E_UNSUPPORTED, "v3d_object_patch_masks: patch %d too large", patch);
   k_object_masks<<<V * grid * grid, kObjThreads, smem, (cudaStream_t)stream>>>(coords, V, S, patch, grid, boxes, K, threshold, masks_out);
   return check_launch("k_object_masks");
@@ -183,7 +197,7 @@ int v3d_object_patch_masks_depth(const void* depth, int depth_dtype, const float
   V3D_REQUIRE(depth && poses && intr && row_map && col_map && boxes && masks_out, V3D_E_ARG, "v3d_object_patch_masks_depth: null pointer");
   V3D_REQUIRE(H > 0 && W > 0 && patch > 0 && grid > 0, V3D_E_ARG, "v3d_object_patch_masks_depth: bad sizes");
   V3D_REQUIRE(coord_dtype == V3D_BF16 || coord_dtype == V3D_F16 || coord_dtype == V3D_F32, V3D_E_ARG, "v3d_object_patch_masks_depth: bad coord dtype");
-  const size_t smem = (size_t)3 * patch * patch * sizeof(float);
+  const size_t smem = ((size_t)3 * patch * patch + 8) * sizeof(float);
   V3D_REQUIRE(smem <= 48 * 1024, V3D_E_UNSUPPORTED, "v3d_object_patch_masks_depth: patch %d too large", patch);
   Clamp cl;
   cl.on = clamp_lo_hi_host != nullptr;
