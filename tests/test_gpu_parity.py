@@ -757,6 +757,7 @@ def test_windowed_depth_upload_feeds_the_same_result(scene):
     out_r, pooled_r, _ = fe(d3, p, k, want_coords=True)
     out_f, pooled_f, _ = fe(scene.depth.to(DEV), p, k, want_coords=True)
     assert torch.equal(out_r.view(torch.int16), out_f.view(torch.int16)) and torch.equal(pooled_r, pooled_f)
+    assert torch.equal(fe.from_resampled(res, scene.poses, scene.intrinsics).view(torch.int16), out_f.view(torch.int16))
     # the 'resize' strategy squeezes all 640 columns into 384: the window starts at column 0 (rows still 4 of 5)
     fe2 = FrontEnd(device=DEV, patch_size=27, embedding_size=3584, strategy="resize")
     x_off, width, period, keep = fe2.upload_window(2)

@@ -184,6 +184,17 @@ class FrontEnd:
                                                             cabi.stream_ptr(self.device)), "v3d_scatter_resampled_depth")
         return out
 
+    def from_resampled(self, resampled: torch.Tensor, poses, intrinsics, scratch: torch.Tensor | None = None, **kw):
+        """__call__ on depth the loader already resampled ((V,n,n), pinned host or device): upload if needed, scatter into a
+        (V,H,W) scratch buffer (allocated unless given) and run the front end on it."""
+        if not resampled.is_cuda:
+            resampled = resampled.to(self.device, non_blocking=True)
+        V = resampled.shape[0]
+        if scratch is None:
+            scratch = torch.empty((V, self.cfg.H, self.cfg.W), dtype=resampled.dtype, device=self.device)
+        self.scatter_resampled(resampled, scratch)
+        return self(scratch, poses.to(self.device), intrinsics.to(self.device), **kw)
+
     def upload_bytes(self, n_frames: int, esize: int = 2) -> int:
         x_off, width, period, keep = self.upload_window(esize)
         return n_frames * (self.cfg.H // period) * keep * width
