@@ -12,10 +12,15 @@ discretise -> sin-3D PE (E=1152) added to the bf16 vision tokens, ONE fused kern
 Printed JSON line (rank 0):
   value      frames/s of the whole job, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        the same through the public API with HOST (pinned) depth/pose/intrinsics buffers: H2D copies
-             and a D2H read of the per-token voxel coordinates inside the timed region
+             and a D2H read of the per-token voxel coordinates inside the timed region.  The pinned depth is
+             what the packed-scene loader emits (ScenePack.load(resample=...)): the reference's nearest resize +
+             crop applied on the host to the raw uint16 depth, i.e. the 378x378 samples per frame the kernel reads
   roofline   algorithmic bytes per launch / average launch time vs the measured HBM copy peak
   cpu_baseline  the reference's torch-CPU operator sequence (oracle/torch_port.py) on the host cores
-  mc         secondary metric: max-coverage sampled scenes/s (voxelise + greedy, BASELINE configs[2])
+  mc         secondary metric: max-coverage sampled scenes/s (voxelise + greedy, BASELINE configs[2]); mc.e2e: the
+             same with all candidate frames uploaded from pinned host memory every step
+  default_recipe_geometry / mlp_pe / projector_tail / host_ingest   secondary objects: the reference-default 14x14 grid
+             with E=3584, the tcgen05 learned-projection PE, the pool + PE + newline kernel, PNG/txt vs packed ingest
 `--impl reference` times the CPU port only (rank 0), on a bounded sample of the same workload.
 """
 from __future__ import annotations
