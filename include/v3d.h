@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define V3D_VERSION 101 /* 0.1.1 */
+#define V3D_VERSION 102 /* 0.1.2 */
 
 enum v3d_status { V3D_OK = 0, V3D_E_ARG = -1, V3D_E_ALIGN = -2, V3D_E_UNSUPPORTED = -3, V3D_E_CUDA = -4 };
 
@@ -106,9 +106,11 @@ int v3d_pool_coords(const float* coords, int V, int S, int patch, int grid, int 
 /* replaces llava/model/llava_arch.py:259-272 `discrete_coords` and
  * llava/video_utils.py:348-358 `VideoProcessor.discrete_point`:
  *   out = rint((min(max(c, lo), hi) - lo) / voxel), n_points*3 floats.  has_range = 0 skips
- *   the clamp and the shift (discrete_point with min/max_xyz_range None). */
+ *   the clamp and the shift (discrete_point with min/max_xyz_range None).
+ *   coord_dtype (v3d_dtype): the dtype of the reference's tensor; for bf16/fp16 the subtraction and the quotient are
+ *   each rounded to it (ATen rounds every element-wise op on 16-bit tensors); coords must hold values of that dtype. */
 int v3d_discretize(const float* coords, size_t n_points, const float* min_xyz_host, const float* max_xyz_host,
-                   int has_range, float voxel_size, int div_mode, float* out, v3d_stream_t stream);
+                   int has_range, float voxel_size, int div_mode, int coord_dtype, float* out, v3d_stream_t stream);
 
 /* ---- sinusoidal 3D position encoding ------------------------------------------------------
  * Lookup table behind the discretised PE: for slot s (= point*3 + axis) and
@@ -171,6 +173,16 @@ typedef struct v3d_frontend_desc {
   /* optional side outputs, fp32 */
   float* pooled_out;      /* (n_frames,G,G,n_points,3) pooled coordinates */
   float* pe_coords_out;   /* same shape: what the PE was evaluated on (discretised or not) */
+  /* depth that the LOADER already resampled (scene_pack.py, FrontEnd.pack_resampled): `depth` is (n_frames,H,W) with
+   * depth[f,r,c] = raw[f,row_map[r],col_map[c]] for r,c < grid*patch (H, W >= grid*patch; rows of W elements, so a
+   * 16-byte multiple keeps the TMA path: 384 columns for the ScanNet recipe).  row_map/col_map still give the SOURCE
+   * pixel coordinates u, v of every sample; src_col_min/max are ignored. */
+  int depth_resampled;
+  /* v3d_dtype of the coordinate tensor the reference would hold at llava_arch.py:396 (bf16 under the HF Trainer's
+   * cast, fp16 after the eval scripts' .half(), model_scanqa.py:164-165): every unprojected (and clamped) coordinate,
+   * every pooled mean and every step of the discretisation is rounded to it, like ATen's element-wise kernels do.
+   * V3D_F32 = the fp32 contract of the oracle.  NOTE: V3D_BF16 is 0 -- set this field explicitly. */
+  int coord_dtype;
 } v3d_frontend_desc;
 
 int v3d_frontend_pe(const v3d_frontend_desc* desc, v3d_stream_t stream);

@@ -2,8 +2,10 @@
 
 Used in the build container (where /root/reference is mounted read-only) by
 `oracle/gen_golden.py` to pin the oracle restatement and to write the golden
-vectors under tests/golden/.  /root/reference does not exist on the GPU box, so
-nothing under tests -m gpu, smoke() or bench.py may import this module.
+vectors under tests/golden/.  /root/reference does not exist on the GPU box: there the
+integration tests (tests/test_gpu_overlay.py) import the unmodified copy that
+`oracle/make_ref.py` placed under oracle/_ref/ (git-ignored); smoke() and bench.py never
+import this module.
 
 Recipe follows SURVEY.md section 8(c):
   * llava/video_utils.py and llava/model/position_encoding.py load standalone
@@ -20,7 +22,9 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("V3D_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the mounted reference in the build container; on the GPU box the unmodified copy made by oracle/make_ref.py
+REF_ROOT = os.environ.get("V3D_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/llava") else os.path.join(_HERE, "_ref"))
 
 
 def available() -> bool:

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_pure_host_helpers():
     lib = cabi.load()
-    assert lib.v3d_version() == 101
+    assert lib.v3d_version() == 102
     assert [lib.v3d_pool_points(m) for m in range(5)] == [1, 2, 9, 5, 1]
     assert lib.v3d_pool_points(99) == -1
     assert lib.v3d_mc_hash_slots(0) == 64 and lib.v3d_mc_hash_slots(1000) == 4096
@@ -41,8 +41,8 @@ def test_version_and_pure_host_helpers():
 
 def test_argument_errors_are_reported_without_a_gpu():
     lib = cabi.load()
-    assert lib.v3d_discretize(None, 0, None, None, 0, 0.1, 0, None, None) == cabi.V3D_OK  # empty input: nothing to do
-    rc = lib.v3d_discretize(None, 4, None, None, 0, 0.1, 0, None, None)
+    assert lib.v3d_discretize(None, 0, None, None, 0, 0.1, 0, cabi.F32, None, None) == cabi.V3D_OK  # empty input: nothing to do
+    rc = lib.v3d_discretize(None, 4, None, None, 0, 0.1, 0, cabi.F32, None, None)
     assert rc == cabi.V3D_E_ARG and b"null pointer" in lib.v3d_last_error()
     with pytest.raises(ValueError):
         cabi.check(rc, "v3d_discretize")
@@ -65,7 +65,7 @@ int main(void) {
   F(v3d_frontend_desc, max_xyz); F(v3d_frontend_desc, voxel_size); F(v3d_frontend_desc, div_mode); F(v3d_frontend_desc, pe_mode);
   F(v3d_frontend_desc, E); F(v3d_frontend_desc, dim_t); F(v3d_frontend_desc, table); F(v3d_frontend_desc, table_rows);
   F(v3d_frontend_desc, dtype); F(v3d_frontend_desc, tokens_in); F(v3d_frontend_desc, pe_out); F(v3d_frontend_desc, pooled_out);
-  F(v3d_frontend_desc, pe_coords_out);
+  F(v3d_frontend_desc, pe_coords_out); F(v3d_frontend_desc, depth_resampled); F(v3d_frontend_desc, coord_dtype);
   printf("sizeof.v3d_mc_scene %zu\n", sizeof(v3d_mc_scene));
   F(v3d_mc_scene, depth); F(v3d_mc_scene, poses); F(v3d_mc_scene, intr); F(v3d_mc_scene, pc_voxels); F(v3d_mc_scene, n_frames);
   F(v3d_mc_scene, n_pc); F(v3d_mc_scene, seed); F(v3d_mc_scene, hash_table); F(v3d_mc_scene, hash_slots); F(v3d_mc_scene, bitsets);

@@ -745,19 +745,34 @@ def test_windowed_depth_upload_feeds_the_same_result(scene):
         fe.upload_packed(packed[:, :100].contiguous().pin_memory())
     # resampled form: the loader applies the nearest resize + crop to the depth; scattered back on the device
     res = fe.pack_resampled(scene.depth)
-    assert fe.resampled_shape(3) == (3, 378, 378) and tuple(res.shape) == (3, 378, 378) and res.is_pinned()
+    assert fe.resampled_shape(3) == (3, 384, 384) and tuple(res.shape) == (3, 384, 384) and res.is_pinned()
     rows_h, cols_h = geometry_maps(480, 640)
-    assert torch.equal(res, scene.depth[:, rows_h[:378]][:, :, cols_h[:378]])
+    assert torch.equal(res, scene.depth[:, rows_h][:, :, cols_h])
     poison3 = torch.full(h.shape, 3456, dtype=h.dtype, device=DEV)
     d3 = fe.scatter_resampled(res.to(DEV), poison3)
     torch.cuda.synchronize()
     touched = torch.zeros(h.shape, dtype=torch.bool)
-    touched[:, torch.tensor(rows_h[:378])[:, None], torch.tensor(cols_h[:378])[None, :]] = True
+    touched[:, torch.tensor(rows_h)[:, None], torch.tensor(cols_h)[None, :]] = True
     assert torch.equal(d3.cpu()[touched], scene.depth[touched]) and bool((d3.cpu()[~touched] == 3456).all())
     out_r, pooled_r, _ = fe(d3, p, k, want_coords=True)
     out_f, pooled_f, _ = fe(scene.depth.to(DEV), p, k, want_coords=True)
     assert torch.equal(out_r.view(torch.int16), out_f.view(torch.int16)) and torch.equal(pooled_r, pooled_f)
-    assert torch.equal(fe.from_resampled(res, scene.poses, scene.intrinsics).view(torch.int16), out_f.view(torch.int16))
+    # the fused kernel reads the resampled form in place (v3d_frontend_desc.depth_resampled): 768-byte rows staged by TMA ...
+    out_i, pooled_i, disc_i = fe.from_resampled(res, scene.poses, scene.intrinsics, want_coords=True)
+    assert torch.equal(out_i.view(torch.int16), out_f.view(torch.int16)) and torch.equal(pooled_i, pooled_f)
+    # ... a 378 x 378 stack (756-byte rows: plain loads), both geometries, and the sample modes
+    res378 = res[:, :378, :378].contiguous().to(DEV)
+    assert torch.equal(fe(res378, p, k, resampled=True).view(torch.int16), out_f.view(torch.int16))
+    for kw in (dict(patch_size=14, embedding_size=1152), dict(patch_size=27, embedding_size=1152, world_position_embedding_type="sample9-discrete-sin3d"),
+               dict(patch_size=27, embedding_size=1152, world_position_embedding_type="minmax-sin3d")):
+        fe_k = FrontEnd(device=DEV, **kw)
+        full = fe_k(scene.depth.to(DEV), p, k, want_coords=True, clamp=((-2, -2, 0), (2, 2, 2)))
+        for stack in (res.to(DEV), res378):
+            got = fe_k(stack, p, k, want_coords=True, clamp=((-2, -2, 0), (2, 2, 2)), resampled=True)
+            for x, y in zip(got, full):
+                assert torch.equal(x.view(torch.int16) if x.dtype == torch.bfloat16 else x.view(torch.int32), y.view(torch.int16) if y.dtype == torch.bfloat16 else y.view(torch.int32))
+    with pytest.raises(ValueError):
+        fe(res[:, :300].contiguous().to(DEV), p, k, resampled=True)
     # the 'resize' strategy squeezes all 640 columns into 384: the window starts at column 0 (rows still 4 of 5)
     fe2 = FrontEnd(device=DEV, patch_size=27, embedding_size=3584, strategy="resize")
     x_off, width, period, keep = fe2.upload_window(2)

@@ -45,7 +45,8 @@ def test_pack_layout_and_header(dataset, packed):
     path = scene_pack.pack_path(packed, video_id)
     raw = open(path, "rb").read()
     magic, ver, n, H, W, code, _, off_ids, off_poses, off_intr, off_depth, total = struct.unpack_from("<8sIIIIIIQQQQQ", raw)
-    assert magic == b"V3DPACK1" and ver == 1 and code == 0 and total == len(raw)
+    assert magic == b"V3DPACK1" and ver == 2 and code == 0 and total == len(raw)
+    assert struct.unpack_from("<QII", raw, struct.calcsize("<8sIIIIIIQQQQQ")) == (0, 0, 0)  # no resampled stack in this pack
     assert n == len(vp.scene[video_id]["images"]) and off_depth % 4096 == 0 and off_ids == 4096
     assert total == off_depth + n * H * W * 2
     pk = scene_pack.ScenePack(path)
@@ -122,3 +123,48 @@ def test_resampled_load_is_the_nearest_resize_and_crop_of_the_depth(dataset, pac
     assert torch.equal(res, full[:, list(rows)][:, :, list(cols)])
     with pytest.raises(ValueError):
         pk.load(pk.ids[:1], resample=([0, pk.H], [0]))
+
+
+def test_stored_resampled_stack_and_lazy_handle(dataset, tmp_path):
+    """Version-2 packs can hold the depth already resampled for the model-side front end: VideoProcessor(pack_dir, lazy=True)
+    then hands out handles over those samples (one contiguous copy per frame), bit-identical to resampling on the fly."""
+    from video_3d_llm_b200 import geometry
+
+    vp = _vp(dataset)
+    video_id = "scannet/scene0003_00"  # 480 x 640
+    out = scene_pack.pack_scene(vp, video_id, scene_pack.pack_path(str(tmp_path), video_id), resample=(384, "center_crop"))
+    pk = scene_pack.ScenePack(out)
+    assert pk.resampled_for == (384, "center_crop") and pk.resampled.shape == (pk.n_frames, 384, 384)
+    rows, cols = geometry.resample_maps_host(pk.H, pk.W, 384, "center_crop")
+    assert np.array_equal(pk.resampled, pk.depth[:, list(rows)][:, :, list(cols)])
+    raw = open(out, "rb").read()
+    off_res, crop, strat = struct.unpack_from("<QII", raw, struct.calcsize("<8sIIIIIIQQQQQ"))
+    assert off_res % 4096 == 0 and (crop, strat) == (384, 0) and len(raw) == off_res + pk.n_frames * 384 * 384 * 2
+    d, p, k = pk.load_resampled(pk.ids[1:3])
+    assert d.dtype == torch.int16 and tuple(d.shape) == (2, 384, 384) and torch.equal(d, torch.from_numpy(np.array(pk.resampled[1:3]).view(np.int16)))
+    ring = torch.zeros((4, 384, 384), dtype=torch.int16)
+    pk.load_resampled(pk.ids[:2], out=ring[2:])
+    assert torch.equal(ring[2:], torch.from_numpy(np.array(pk.resampled[:2]).view(np.int16))) and not ring[:2].any()
+    vp_pack = _vp(dataset, pack_dir=str(tmp_path), lazy=True)
+    files = vp_pack.sample_frame_files(video_id, force_sample=True, frames_upbound=3)
+    h = vp_pack.world_coords(video_id, files)
+    assert isinstance(h, VU.LazyWorldCoords) and h.resampled and h.src_hw == (480, 640) and h.shape == (3, 384, 384, 3)
+    full, _, _ = vp_pack.load_frames(video_id, files)
+    assert torch.equal(h.depth, full[:, list(rows)][:, :, list(cols)])
+    # another crop size / strategy, or lazy=False, falls back to full frames
+    assert not vp_pack.world_coords(video_id, files, crop_size=224).resampled
+    with pytest.raises(KeyError):
+        scene_pack.ScenePack(scene_pack.pack_path(str(tmp_path), video_id)).load_resampled([123456])
+    with pytest.raises(ValueError):
+        VU.LazyWorldCoords(h.depth, h.poses, h.intrinsics, resampled=True)
+    # version-1 files (no trailer) stay readable
+    hdr = bytearray(raw[:4096])
+    struct.pack_into("<I", hdr, 8, 1)
+    hdr[struct.calcsize("<8sIIIIIIQQQQQ"):struct.calcsize("<8sIIIIIIQQQQQ") + 16] = b"\0" * 16
+    off_depth = struct.unpack_from("<Q", hdr, 8 + 24 + 24)[0]
+    body = raw[4096:off_depth + pk.n_frames * 480 * 640 * 2]
+    struct.pack_into("<Q", hdr, 8 + 24 + 32, 4096 + len(body))
+    v1 = tmp_path / "v1.v3dpack"
+    v1.write_bytes(bytes(hdr) + body)
+    pk1 = scene_pack.ScenePack(str(v1))
+    assert pk1.resampled is None and np.array_equal(pk1.depth, pk.depth)

@@ -48,7 +48,12 @@ class FrontendDesc(C.Structure):
         ("pe_mode", C.c_int), ("E", C.c_int), ("dim_t", C.c_void_p), ("table", C.c_void_p), ("table_rows", C.c_int),
         ("dtype", C.c_int), ("tokens_in", C.c_void_p), ("pe_out", C.c_void_p),
         ("pooled_out", C.c_void_p), ("pe_coords_out", C.c_void_p),
+        ("depth_resampled", C.c_int), ("coord_dtype", C.c_int),
     ]
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.coord_dtype = F32  # V3D_BF16 is 0: the zero-initialised struct would otherwise ask for bf16 rounding
 
 
 class PoolDesc(C.Structure):
@@ -101,7 +106,7 @@ def load():
     lib.v3d_expand_depth_window.argtypes = [vp, vp, sz, sz, sz, sz, sz, sz, vp]
     lib.v3d_scatter_resampled_depth.argtypes = [vp, vp, i, i, i, i, vp, vp, i, i, vp]
     lib.v3d_pool_coords.argtypes = [vp, i, i, i, i, i, vp, vp]
-    lib.v3d_discretize.argtypes = [vp, sz, vp, vp, i, f, i, vp, vp]
+    lib.v3d_discretize.argtypes = [vp, sz, vp, vp, i, f, i, i, vp, vp]
     lib.v3d_pe_table_bytes.argtypes, lib.v3d_pe_table_bytes.restype = [i, i, i, i], sz
     lib.v3d_pe_table_build.argtypes = [vp, i, i, i, i, vp, vp]
     lib.v3d_pe_sine3d.argtypes = [vp, sz, i, i, vp, vp, i, i, vp, vp, vp]
@@ -162,6 +167,17 @@ def depth_code(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return DEPTH_F32
     raise TypeError(f"unsupported depth dtype {t.dtype}; use uint16/int16 (raw PNG bits), int32 or float32")
+
+
+def div_mode_default() -> int:
+    """Division semantics of the drop-in entry points that replace code the reference runs ON CUDA (the overlay's
+    discrete_coords, llava_arch.py:269; the MC script's voxel ids, max_coverage_sampling.py:44): ATen's CUDA kernel
+    multiplies by the reciprocal of a scalar divisor, so that is the default; V3D_DIV_MODE=ieee selects torch-CPU
+    semantics (the parity target of the CPU oracle and of the golden vectors)."""
+    v = os.environ.get("V3D_DIV_MODE", "reciprocal").lower()
+    if v not in ("ieee", "reciprocal"):
+        raise ValueError(f"V3D_DIV_MODE must be 'ieee' or 'reciprocal', got {v!r}")
+    return DIV_IEEE if v == "ieee" else DIV_RECIPROCAL
 
 
 def dtype_code(dt: torch.dtype) -> int:

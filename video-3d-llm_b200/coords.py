@@ -56,7 +56,14 @@ def sample_n_points(world_coords, n_points=9):
 def discrete_coords(world_coords, xyz_min=None, *, voxel_size=0.1, min_xyz_range=(-15, -15, -5), max_xyz_range=(15, 15, 5),
                     div_mode: int = cabi.DIV_IEEE):
     """llava/model/llava_arch.py:259-272: round((clamp(c, min, max) - min) / voxel_size); the result
-    stays floating point and detached; `xyz_min` is accepted and ignored like upstream."""
+    stays floating point and detached; `xyz_min` is accepted and ignored like upstream.  On a bf16 / fp16 tensor every
+    step is rounded to that dtype like ATen's element-wise kernels do; a deferred LazyPooled stays deferred."""
+    from .lazy import LazyPooled
+
+    if isinstance(world_coords, LazyPooled) and world_coords.disc is None and min_xyz_range is not None and max_xyz_range is not None:
+        return world_coords.discretized(voxel_size, min_xyz_range, max_xyz_range, div_mode)
+    if isinstance(world_coords, LazyPooled):
+        world_coords = world_coords.materialize()
     cabi.require_cuda(world_coords, "world_coords")
     lib = cabi.load()
     if world_coords.shape[-1] != 3:
@@ -68,7 +75,7 @@ def discrete_coords(world_coords, xyz_min=None, *, voxel_size=0.1, min_xyz_range
     hi = cabi.host_floats(max_xyz_range) if has_range else None
     with torch.cuda.device(src.device):
         cabi.check(lib.v3d_discretize(src.data_ptr(), src.numel() // 3, lo, hi, int(has_range), float(voxel_size), div_mode,
-                                      out.data_ptr(), cabi.stream_ptr(src.device)), "v3d_discretize")
+                                      cabi.dtype_code(world_coords.dtype), out.data_ptr(), cabi.stream_ptr(src.device)), "v3d_discretize")
     return out.to(world_coords.dtype)
 
 

@@ -676,6 +676,12 @@ struct FusedParams {
   float* pe_coords_out;
   // TMA staging: bytes [col_lo_byte, col_lo_byte + span) of each needed depth row
   int col_lo_byte, span;
+  // depth is already resampled: sample (r, c) of the (H, W) buffer belongs to dst pixel (r, c), whose source pixel
+  // coordinates (for u - cx, v - cy) are still (row_map[r], col_map[c])
+  int resampled;
+  // dtype of the coordinate tensor the reference would hold (bf16 under the HF Trainer, fp16 in the eval scripts): each
+  // unprojected (and clamped) coordinate and each pooled mean is rounded to it; V3D_F32 = the fp32 contract
+  int coord_dtype;
 };
 
 // xyz of one resampled row live in three planes of kPlane floats (x | y | z), double buffered.  The
@@ -758,10 +764,12 @@ __device__ __forceinline__ void chain_row(ChainAcc& c, const float* src, int P, 
 // dividend of the three divisions is then either exactly zero (d == 0, where a*r is the correctly
 // signed zero) or inside div_exact's fast range, and every camera-space value is finite, so no range
 // test, no fallback and no w-division remain in the loop.
+template <bool ROUND>
 __device__ __forceinline__ void pool_rows_fast(const Camera& cam, const Divisor& ds, int P, uint32_t span, int n_px,
                                                const float um[2], const uint32_t d_addr[2], const uint32_t w_addr[2],
                                                const float2* s_vm, bool chain, const float* chain_src, int pool_mode,
-                                               const Clamp& clamp, ChainAcc& c, const unsigned char* pf_src, size_t pf_bytes) {
+                                               const Clamp& clamp, ChainAcc& c, const unsigned char* pf_src, size_t pf_bytes,
+                                               int coord_dtype) {
   // the token rows are pulled into L2 ~8 row pairs before the streaming phase needs them: early enough to hide
   // DRAM latency, late enough that the output stream of the co-resident CTAs has not evicted them again
 #ifndef V3D_PF_LEAD
@@ -805,6 +813,11 @@ __device__ __forceinline__ void pool_rows_fast(const Camera& cam, const Divisor&
               x = apply_clamp(clamp, x, 0);
               y = apply_clamp(clamp, y, 1);
               z = apply_clamp(clamp, z, 2);
+            }
+            if constexpr (ROUND) {
+              x = round_to_dtype(x, coord_dtype);
+              y = round_to_dtype(y, coord_dtype);
+              z = round_to_dtype(z, coord_dtype);
             }
             sts_xyz(w_addr[k] + bsel + (uint32_t)(rr * 3 * kPlane * 4), x, y, z);
           }
@@ -864,7 +877,7 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
       if (t == 0) mbar_arrive_expect_tx(bar, (uint32_t)(P * p.span));
       __syncwarp();
       for (int dy = t; dy < P; dy += 32) {
-        const int sr = __ldg(p.row_map + gi * P + dy);
+        const int sr = p.resampled ? gi * P + dy : __ldg(p.row_map + gi * P + dy);
         const unsigned char* src =
             reinterpret_cast<const unsigned char*>(p.depth) + ((size_t)f * p.H + sr) * p.W * kEsz + p.col_lo_byte;
         tma_bulk_g2s(s_depth + (size_t)dy * p.span, src, (uint32_t)p.span, bar);
@@ -886,7 +899,7 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
   for (int dy = t; dy < P; dy += kThreads) {
     const int sr = FROM_DEPTH ? __ldg(p.row_map + gi * P + dy) : gi * P + dy;
     const float vm = FROM_DEPTH ? __fsub_rn((float)sr, cam.cy) : 0.0f;
-    s_srow[dy] = sr;
+    s_srow[dy] = (FROM_DEPTH && p.resampled) ? gi * P + dy : sr;  // the row the sample is stored in
     s_vm[dy] = make_float2(vm, 0.0f);
     fast_ok = fast_ok && fabsf(vm) >= 0x1p-20f && fabsf(vm) <= 0x1p20f;
   }
@@ -912,7 +925,8 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
       if constexpr (FROM_DEPTH) {
         um[k] = __fsub_rn((float)sc, cam.cx);
         fast_ok = fast_ok && fabsf(um[k]) >= 0x1p-20f && fabsf(um[k]) <= 0x1p20f;
-        src_off[k] = USE_TMA ? (size_t)(sc * kEsz - p.col_lo_byte) : (size_t)sc;
+        const int stored = p.resampled ? col[k] : sc;  // the column the sample is stored in
+        src_off[k] = USE_TMA ? (size_t)(stored * kEsz - p.col_lo_byte) : (size_t)stored;
         d_addr[k] += (uint32_t)src_off[k];
       } else {
         src_off[k] = (size_t)sc * 3;
@@ -930,8 +944,12 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
     ChainAcc ca = {0.0f, -CUDART_INF_F, -CUDART_INF_F};
     const float* chain_src = s_row + a * kPlane + j * P;
     if (all_fast) {
-      pool_rows_fast(cam, ds, P, (uint32_t)p.span, col[1] >= 0 ? 2 : 1, um, d_addr, w_addr, s_vm, chain, chain_src, p.pool_mode,
-                     p.clamp, ca, pf_src, pf_bytes);
+      if (p.coord_dtype == V3D_F32)
+        pool_rows_fast<false>(cam, ds, P, (uint32_t)p.span, col[1] >= 0 ? 2 : 1, um, d_addr, w_addr, s_vm, chain, chain_src,
+                              p.pool_mode, p.clamp, ca, pf_src, pf_bytes, V3D_F32);
+      else
+        pool_rows_fast<true>(cam, ds, P, (uint32_t)p.span, col[1] >= 0 ? 2 : 1, um, d_addr, w_addr, s_vm, chain, chain_src,
+                             p.pool_mode, p.clamp, ca, pf_src, pf_bytes, p.coord_dtype);
     } else {
       if (pf_src != nullptr && t == 32) {
         for (size_t o = 0; o < pf_bytes; o += 32768) tma_prefetch_l2(pf_src + o, (uint32_t)min((size_t)32768, pf_bytes - o));
@@ -960,6 +978,11 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
               y = apply_clamp(p.clamp, y, 1);
               z = apply_clamp(p.clamp, z, 2);
             }
+            if (p.coord_dtype != V3D_F32) {
+              x = round_to_dtype(x, p.coord_dtype);
+              y = round_to_dtype(y, p.coord_dtype);
+              z = round_to_dtype(z, p.coord_dtype);
+            }
           } else {
             const float* src = p.coords_in + ((size_t)f * p.S + s_srow[dy]) * p.S * 3 + src_off[k];
             x = __ldg(src);
@@ -977,7 +1000,7 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
       const size_t tok = ((size_t)f * G + gi) * G + j;
       const bool have_table = p.table != nullptr;
       if (p.pool_mode == V3D_POOL_AVG) {
-        const float v = __fdiv_rn(acc, (float)(P * P));
+        const float v = round_to_dtype(__fdiv_rn(acc, (float)(P * P)), p.coord_dtype);
         const float pv = p.disc.on ? discretize1(p.disc, v, a) : v;
         if (p.pooled_out) p.pooled_out[tok * 3 + a] = v;
         if (p.pe_coords_out) p.pe_coords_out[tok * 3 + a] = pv;
@@ -1005,10 +1028,10 @@ __global__ void __launch_bounds__(kThreads, V3D_FUSED_MIN_BLOCKS) k_fused(const 
       float v[3];
       if constexpr (FROM_DEPTH) {
         const int sr = __ldg(p.row_map + r), sc = __ldg(p.col_map + c);
-        const float d = load_depth<DT>(p.depth, ((size_t)f * p.H + sr) * p.W + sc);
+        const float d = load_depth<DT>(p.depth, ((size_t)f * p.H + (p.resampled ? r : sr)) * p.W + (p.resampled ? c : sc));
         unproject_px(cam, d, __fsub_rn((float)sc, cam.cx), __fsub_rn((float)sr, cam.cy), ds, v[0], v[1], v[2]);
 #pragma unroll
-        for (int a = 0; a < 3; ++a) v[a] = apply_clamp(p.clamp, v[a], a);
+        for (int a = 0; a < 3; ++a) v[a] = round_to_dtype(apply_clamp(p.clamp, v[a], a), p.coord_dtype);
       } else {
         const float* src = p.coords_in + (((size_t)f * p.S + r) * p.S + c) * 3;
         v[0] = __ldg(src);
@@ -1056,7 +1079,7 @@ __global__ void __launch_bounds__(kThreads) k_discretize(const float* __restrict
       out[i] = discretize1(d, x, a);
     } else {
       x = (d.div_mode == V3D_DIV_RECIPROCAL) ? __fmul_rn(x, d.rcp_voxel) : __fdiv_rn(x, d.voxel);
-      out[i] = rintf(x);
+      out[i] = rintf(round_to_dtype(x, d.coord_dtype));
     }
   }
 }
@@ -1093,7 +1116,7 @@ static Clamp make_clamp(const float* lo_hi) {
   }
   return c;
 }
-static Discretize make_disc(int on, const float* lo, const float* hi, float voxel, int div_mode) {
+static Discretize make_disc(int on, const float* lo, const float* hi, float voxel, int div_mode, int coord_dtype = V3D_F32) {
   Discretize d;
   memset(&d, 0, sizeof(d));
   d.on = on;
@@ -1104,6 +1127,7 @@ static Discretize make_disc(int on, const float* lo, const float* hi, float voxe
   d.voxel = voxel;
   d.rcp_voxel = 1.0f / voxel;
   d.div_mode = div_mode;
+  d.coord_dtype = coord_dtype;
   return d;
 }
 
@@ -1285,13 +1309,13 @@ int v3d_boundary(const void* depth, int depth_dtype, const float* poses, const f
 }
 
 int v3d_discretize(const float* coords, size_t n_points, const float* min_xyz_host, const float* max_xyz_host,
-                   int has_range, float voxel_size, int div_mode, float* out, v3d_stream_t stream) {
+                   int has_range, float voxel_size, int div_mode, int coord_dtype, float* out, v3d_stream_t stream) {
   if (n_points == 0) return V3D_OK;
   V3D_REQUIRE(coords && out, V3D_E_ARG, "v3d_discretize: null pointer");
   V3D_REQUIRE(!has_range || (min_xyz_host && max_xyz_host), V3D_E_ARG, "v3d_discretize: range requested but not given");
   V3D_REQUIRE(voxel_size > 0.f, V3D_E_ARG, "v3d_discretize: voxel_size must be positive");
-  if (n_points == 0) return V3D_OK;
-  const Discretize d = make_disc(1, min_xyz_host, max_xyz_host, voxel_size, div_mode);
+  V3D_REQUIRE(coord_dtype == V3D_BF16 || coord_dtype == V3D_F16 || coord_dtype == V3D_F32, V3D_E_ARG, "v3d_discretize: bad coord dtype %d", coord_dtype);
+  const Discretize d = make_disc(1, min_xyz_host, max_xyz_host, voxel_size, div_mode, coord_dtype);
   const size_t n = n_points * 3;
   k_discretize<<<grid_for(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(coords, n, d, has_range, out);
   return check_launch("k_discretize");
@@ -1412,6 +1436,8 @@ int v3d_pool_coords(const float* coords, int V, int S, int patch, int grid, int 
   p.n_points = n_points;
   p.pe_mode = V3D_PE_NONE;
   p.pooled_out = out;
+  p.coord_dtype = V3D_F32;  // the caller's tensor already holds values of its dtype and rounds the result itself
+  p.disc.coord_dtype = V3D_F32;
   return launch_fused_dt<false, __nv_bfloat16>(0, false, p, (cudaStream_t)stream);
 }
 
@@ -1446,9 +1472,17 @@ int v3d_frontend_pe(const v3d_frontend_desc* d, v3d_stream_t stream) {
     float lh[6] = {d->clamp_lo[0], d->clamp_lo[1], d->clamp_lo[2], d->clamp_hi[0], d->clamp_hi[1], d->clamp_hi[2]};
     p.clamp = make_clamp(lh);
   }
+  V3D_REQUIRE(d->coord_dtype == V3D_BF16 || d->coord_dtype == V3D_F16 || d->coord_dtype == V3D_F32, V3D_E_ARG,
+              "v3d_frontend_pe: bad coord_dtype %d", d->coord_dtype);
+  p.coord_dtype = d->coord_dtype;
+  p.disc.coord_dtype = d->coord_dtype;
+  p.resampled = d->depth_resampled ? 1 : 0;
+  if (p.resampled)
+    V3D_REQUIRE(d->H >= p.Sp && d->W >= p.Sp, V3D_E_ARG, "v3d_frontend_pe: resampled depth is %dx%d, the grid needs %dx%d samples", d->H, d->W,
+                p.Sp, p.Sp);
   if (d->discrete) {
     V3D_REQUIRE(d->voxel_size > 0.f, V3D_E_ARG, "v3d_frontend_pe: voxel_size must be positive");
-    p.disc = make_disc(1, d->min_xyz, d->max_xyz, d->voxel_size, d->div_mode);
+    p.disc = make_disc(1, d->min_xyz, d->max_xyz, d->voxel_size, d->div_mode, d->coord_dtype);
   }
   p.pe_mode = d->pe_mode;
   p.pooled_out = d->pooled_out;
@@ -1476,12 +1510,13 @@ int v3d_frontend_pe(const v3d_frontend_desc* d, v3d_stream_t stream) {
 
   // TMA staging geometry: bytes [lo, hi) of a depth row that cover every column the maps use.
   const size_t esz = depth_size(d->depth_dtype);
-  V3D_REQUIRE(d->src_col_min >= 0 && d->src_col_max >= d->src_col_min && d->src_col_max < d->W, V3D_E_ARG,
+  V3D_REQUIRE(p.resampled || (d->src_col_min >= 0 && d->src_col_max >= d->src_col_min && d->src_col_max < d->W), V3D_E_ARG,
               "v3d_frontend_pe: src_col_min/max [%d,%d] outside [0,%d)", d->src_col_min, d->src_col_max, d->W);
   const bool use_tma = ((size_t)d->W * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->depth) & 15) == 0;
   if (use_tma) {
-    const int lo = (int)((d->src_col_min * esz) & ~(size_t)15);
-    const int hi = (int)(((d->src_col_max + 1) * esz + 15) & ~(size_t)15);
+    // resampled depth: the first Sp stored columns of every row, whatever the source columns were
+    const int lo = p.resampled ? 0 : (int)((d->src_col_min * esz) & ~(size_t)15);
+    const int hi = (int)((((p.resampled ? p.Sp : d->src_col_max + 1)) * esz + 15) & ~(size_t)15);
     p.col_lo_byte = lo;
     p.span = hi - lo;
   }

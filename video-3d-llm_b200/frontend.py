@@ -154,60 +154,66 @@ class FrontEnd:
                                                         period, keep, cabi.stream_ptr(self.device)), "v3d_expand_depth_window")
         return out
 
-    # ---- resampled form: exactly the samples the kernel reads (grid*patch rows x columns: 378 x 378 for the ScanNet recipe)
+    # ---- resampled form: the reference's resize + crop applied to the raw depth by the loader (crop x crop samples per
+    # frame, 384 x 384 for the ScanNet recipe: rows of 768 bytes keep the TMA path; the kernel reads the first grid*patch)
     def resampled_shape(self, n_frames: int):
-        n = self.cfg.grid * self.cfg.patch_size
-        return n_frames, n, n
+        return n_frames, self.cfg.crop_size, self.cfg.crop_size
 
     def pack_resampled(self, depth_host: torch.Tensor, out: torch.Tensor | None = None, pin: bool = True) -> torch.Tensor:
         """Host-side nearest-neighbour resize + crop of the raw depth (llava/video_utils.py:291-308 applied to depth instead
-        of coordinates): (V,H,W) -> (V,n,n) with n = grid*patch.  What a loader that resamples on the host emits
-        (ScenePack.load(resample=...)); 47 % of the bytes of a ScanNet frame."""
+        of coordinates): (V,H,W) -> (V,crop,crop).  What a loader that resamples on the host emits (ScenePack.load(
+        resample=...), or reads straight from a pack written with a resampled stack); 48 % of the bytes of a ScanNet frame."""
         V = depth_host.shape[0]
-        n = self.cfg.grid * self.cfg.patch_size
         rows, cols = geometry.resample_maps_host(self.cfg.H, self.cfg.W, self.cfg.crop_size, self.cfg.strategy)
-        rows_t, cols_t = torch.as_tensor(rows[:n], dtype=torch.long), torch.as_tensor(cols[:n], dtype=torch.long)
+        rows_t, cols_t = torch.as_tensor(rows, dtype=torch.long), torch.as_tensor(cols, dtype=torch.long)
         if out is None:
-            out = torch.empty((V, n, n), dtype=depth_host.dtype, pin_memory=pin)
+            out = torch.empty(self.resampled_shape(V), dtype=depth_host.dtype, pin_memory=pin)
         torch.index_select(depth_host.index_select(1, rows_t), 2, cols_t, out=out)
         return out
 
     def scatter_resampled(self, staging: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-        """Device side: put resampled depth (V,n,n) (already on the device) back at the pixels it was taken from in the
-        (V,H,W) layout __call__ reads, on the current stream."""
-        V, n, n2 = staging.shape
-        if (n, n2) != self.resampled_shape(V)[1:] or tuple(out.shape) != (V, self.cfg.H, self.cfg.W) or out.dtype != staging.dtype:
-            raise ValueError(f"resampled depth must be {self.resampled_shape(V)} and out (V,{self.cfg.H},{self.cfg.W}) of the same dtype")
+        """Device side: put resampled depth (V,R,C) (already on the device) back at the pixels it was taken from in the
+        (V,H,W) layout, on the current stream -- only for callers that need the frame layout (the fused kernel reads the
+        resampled form in place, see from_resampled)."""
+        V, R, Cc = staging.shape
+        if R > self.cfg.crop_size or Cc > self.cfg.crop_size or tuple(out.shape) != (V, self.cfg.H, self.cfg.W) or out.dtype != staging.dtype:
+            raise ValueError(f"resampled depth must be at most {self.resampled_shape(V)} and out (V,{self.cfg.H},{self.cfg.W}) of the same dtype")
+        staging = staging.contiguous()
         with torch.cuda.device(self.device):
             cabi.check(self.lib.v3d_scatter_resampled_depth(staging.data_ptr(), out.data_ptr(), cabi.depth_code(staging), V, self.cfg.H,
-                                                            self.cfg.W, self.row_map.data_ptr(), self.col_map.data_ptr(), n, n,
+                                                            self.cfg.W, self.row_map.data_ptr(), self.col_map.data_ptr(), R, Cc,
                                                             cabi.stream_ptr(self.device)), "v3d_scatter_resampled_depth")
         return out
 
-    def from_resampled(self, resampled: torch.Tensor, poses, intrinsics, scratch: torch.Tensor | None = None, **kw):
-        """__call__ on depth the loader already resampled ((V,n,n), pinned host or device): upload if needed, scatter into a
-        (V,H,W) scratch buffer (allocated unless given) and run the front end on it."""
+    def from_resampled(self, resampled: torch.Tensor, poses, intrinsics, **kw):
+        """__call__ on depth the loader already resampled ((V,R,C) with R, C >= grid*patch; pinned host or device): uploaded
+        if needed and read in place by the fused kernel (v3d_frontend_desc.depth_resampled) -- no scatter, no scratch."""
         if not resampled.is_cuda:
             resampled = resampled.to(self.device, non_blocking=True)
-        V = resampled.shape[0]
-        if scratch is None:
-            scratch = torch.empty((V, self.cfg.H, self.cfg.W), dtype=resampled.dtype, device=self.device)
-        self.scatter_resampled(resampled, scratch)
-        return self(scratch, poses.to(self.device), intrinsics.to(self.device), **kw)
+        return self(resampled, poses.to(self.device, non_blocking=True), intrinsics.to(self.device, non_blocking=True), resampled=True, **kw)
 
     def upload_bytes(self, n_frames: int, esize: int = 2) -> int:
         x_off, width, period, keep = self.upload_window(esize)
         return n_frames * (self.cfg.H // period) * keep * width
 
-    def __call__(self, depth, poses, intrinsics, tokens=None, out=None, clamp=None, want_coords=False):
+    def __call__(self, depth, poses, intrinsics, tokens=None, out=None, clamp=None, want_coords=False, resampled=False,
+                 coord_dtype: torch.dtype = torch.float32, pe: bool = True):
         """depth (V,H,W) uint16/int16-bits/int32/float32, poses & intrinsics (V,4,4) float32, all on the
         device.  tokens: optional (V, G*G, E) in cfg.dtype to add the PE to (may be `out`).
+        resampled: depth is (V,R,C) as the loader resampled it (depth[v,r,c] = raw[v,row_map[r],col_map[c]]).
+        coord_dtype: the dtype the reference's world_coords tensor would have (fp32 = the oracle's contract; bf16 / fp16
+        reproduce the roundings of the Trainer-cast / .half() tensors of llava_arch.py:396-420).
+        pe=False: stop after the coordinates (pooling + discretisation only), whatever the configured PE.
         Returns the PE (or tokens + PE) as (V, G*G, E); with want_coords also (pooled, pe_coords)."""
         cfg = self.cfg
         for name, t in (("depth", depth), ("poses", poses), ("intrinsics", intrinsics)):
             cabi.require_cuda(t, name)
         V, H, W = depth.shape
-        if (H, W) != (cfg.H, cfg.W):
+        if resampled:
+            n = cfg.grid * cfg.patch_size
+            if H < n or W < n:
+                raise ValueError(f"resampled depth is {H}x{W}, the {cfg.grid}x{cfg.grid} grid of {cfg.patch_size}-pixel patches needs {n}x{n}")
+        elif (H, W) != (cfg.H, cfg.W):
             raise ValueError(f"depth is {H}x{W}, front end was configured for {cfg.H}x{cfg.W}")
         depth = depth.contiguous()
         poses = poses.to(torch.float32).contiguous()
@@ -224,13 +230,15 @@ class FrontEnd:
         d.discrete = int(self.flags["discrete"])
         d.min_xyz, d.max_xyz = cabi.float3(cfg.min_xyz_range), cabi.float3(cfg.max_xyz_range)
         d.voxel_size, d.div_mode = cfg.voxel_size, cfg.div_mode
+        d.depth_resampled, d.coord_dtype = int(bool(resampled)), cabi.dtype_code(coord_dtype)
         pooled = pe_coords = None
-        if want_coords or not self.flags["sin3d"]:
+        use_pe = pe and self.flags["sin3d"]
+        if want_coords or not use_pe:
             shape = (V, G, G, 3) if self.n_points == 1 else (V, G, G, self.n_points, 3)
             pooled = torch.empty(shape, dtype=torch.float32, device=self.device)
             pe_coords = torch.empty(shape, dtype=torch.float32, device=self.device)
             d.pooled_out, d.pe_coords_out = pooled.data_ptr(), pe_coords.data_ptr()
-        if self.flags["sin3d"]:
+        if use_pe:
             if out is None:
                 out = torch.empty((V, G * G, E), dtype=cfg.dtype, device=self.device)
             elif out.shape != (V, G * G, E) or out.dtype != cfg.dtype or not out.is_contiguous():
@@ -247,5 +255,5 @@ class FrontEnd:
         with torch.cuda.device(self.device):
             cabi.check(self.lib.v3d_frontend_pe(C.byref(d), cabi.stream_ptr(self.device)), "v3d_frontend_pe")
         if want_coords:
-            return out, pooled, pe_coords
-        return out if self.flags["sin3d"] else pe_coords
+            return (out if use_pe else None), pooled, pe_coords
+        return out if use_pe else pe_coords

@@ -14,8 +14,12 @@
   LlavaMetaForCausalLM.{get_2dPool, add_token_per_grid}                     (called at :469 and :536; the slow-fast
       variant `add_faster_video`, which this package does not implement, keeps the reference's own method)
 The 500-line prepare_inputs_labels_for_multimodal itself is left alone: with VideoProcessor(lazy=True) the
-`world_coords` it receives is a handle over raw depth/pose/intrinsics, so the first patched helper it
-calls runs the fused kernel and the (V,384,384,3) tensor is never built (video_utils.LazyWorldCoords).
+`world_coords` it receives is a handle over raw depth/pose/intrinsics and the patched helpers return deferred values
+(lazy.py), so that the method's own call sequence ends in fused launches:
+  avg-discrete-sin3d video sample:  v3d_frontend_pe with the PE off (depth -> discretised patch coordinates, 9 KB per frame)
+                                    + v3d_pool_pe_grid (get_2dPool + PE + add + newline over the projector's tokens),
+  without spatial pooling / newline: ONE v3d_frontend_pe launch with tokens_in (depth + tokens -> tokens + PE),
+and the (V,384,384,3) coordinate tensor, the pooled tokens and the stand-alone PE tensor are never built.
 """
 from __future__ import annotations
 
@@ -24,14 +28,38 @@ import runpy
 import sys
 
 
+_originals: list = []  # (object, attribute name, original value) of everything install() rebound
+
+
+def uninstall() -> None:
+    """Restore what install() rebound (tests run the un-patched reference next to the patched one)."""
+    from . import position_encoding
+
+    while _originals:
+        obj, name, val = _originals.pop()
+        setattr(obj, name, val)
+    position_encoding.PositionEmbeddingSine3D.defer_add = False
+
+
+def _rebind(obj, name, val) -> None:
+    _originals.append((obj, name, getattr(obj, name)))
+    setattr(obj, name, val)
+
+
 def install(lazy: bool | None = None) -> dict:
     """Patch the reference modules in place; returns {dotted name: replacement} for inspection."""
     import importlib
 
-    from . import coords, position_encoding, projector_tail, video_utils
+    uninstall()
+
+    from . import cabi, coords, position_encoding, projector_tail, video_utils
+    from . import lazy as lazy_mod
 
     if lazy is None:
         lazy = os.environ.get("V3D_LAZY", "1") != "0"
+    # V3D_DEFER=0 keeps every patched helper eager (one launch per call, real tensors everywhere)
+    defer = os.environ.get("V3D_DEFER", "1") != "0"
+    position_encoding.PositionEmbeddingSine3D.defer_add = defer
     done = {}
 
     vu = importlib.import_module("llava.video_utils")
@@ -42,15 +70,18 @@ def install(lazy: bool | None = None) -> dict:
             if os.environ.get("V3D_PACK_DIR"):
                 kw.setdefault("pack_dir", os.environ["V3D_PACK_DIR"])
             super().__init__(*a, **kw)
+            if os.environ.get("V3D_MC_PRECOMPUTE", "0") == "1":
+                # 'mc-online*' strategies: DataLoader workers are forked and cannot touch CUDA -- sample every scene here
+                self.precompute_mc_order()
 
     for name, obj in (("unproject", video_utils.unproject), ("VideoProcessor", VideoProcessor),
                       ("merge_video_dict", video_utils.merge_video_dict)):
-        setattr(vu, name, obj)
+        _rebind(vu, name, obj)
         done[f"llava.video_utils.{name}"] = obj
 
     pe = importlib.import_module("llava.model.position_encoding")
     for name in ("PositionEmbeddingSine3D", "PositionEmbeddingMLP"):
-        setattr(pe, name, getattr(position_encoding, name))
+        _rebind(pe, name, getattr(position_encoding, name))
         done[f"llava.model.position_encoding.{name}"] = getattr(position_encoding, name)
 
     arch = importlib.import_module("llava.model.llava_arch")
@@ -66,24 +97,33 @@ def install(lazy: bool | None = None) -> dict:
         return coords.sample_n_points(world_coords, n_points)
 
     def discrete_coords(self, world_coords, xyz_min):
+        # the reference runs this on CUDA, where ATen multiplies by the reciprocal of the scalar divisor (cabi.div_mode_default)
         return coords.discrete_coords(world_coords, xyz_min, voxel_size=self.config.voxel_size,
-                                      min_xyz_range=self.config.min_xyz_range, max_xyz_range=self.config.max_xyz_range)
+                                      min_xyz_range=self.config.min_xyz_range, max_xyz_range=self.config.max_xyz_range,
+                                      div_mode=cabi.div_mode_default())
 
     ref_get_2dpool, ref_add_token_per_grid = cls.get_2dPool, cls.add_token_per_grid
 
     def get_2dPool(self, image_feature, stride=2):
         side = self.get_vision_tower().num_patches_per_side
+        mode = self.config.mm_spatial_pool_mode
         if side * side != image_feature.shape[1]:
             return ref_get_2dpool(self, image_feature, stride)
-        return projector_tail.get_2dPool(image_feature, stride, self.config.mm_spatial_pool_mode)
+        cabi.require_cuda(image_feature, "image_feature")
+        if defer and mode in ("bilinear", "average", "max"):
+            # deferred: `+ PE` (:515) and add_token_per_grid (:536) complete it in one kernel over the un-pooled tokens
+            return lazy_mod.LazyTokenPool(image_feature, stride, mode)
+        return projector_tail.get_2dPool(image_feature, stride, mode)
 
     def add_token_per_grid(self, image_feature):
         if getattr(self.config, "add_faster_video", False):
-            return ref_add_token_per_grid(self, image_feature)
-        return projector_tail.add_token_per_grid(image_feature, self.model.image_newline)
+            return ref_add_token_per_grid(self, lazy_mod._unwrap(image_feature))
+        if isinstance(image_feature, lazy_mod.LazyTokenPool):
+            return image_feature.finish(self.model.image_newline)
+        return projector_tail.add_token_per_grid(lazy_mod._unwrap(image_feature), self.model.image_newline)
 
     for fn in (average_coordinate_in_patch, minmax_coordinate_in_patch, sample_n_points, discrete_coords, get_2dPool, add_token_per_grid):
-        setattr(cls, fn.__name__, fn)
+        _rebind(cls, fn.__name__, fn)
         done[f"llava.model.llava_arch.LlavaMetaForCausalLM.{fn.__name__}"] = fn
     return done
 

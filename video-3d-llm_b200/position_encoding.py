@@ -10,6 +10,8 @@ import torch
 import torch.nn as nn
 
 from . import cabi
+from . import ops  # noqa: F401  (registers torch.ops.v3d.*)
+from .lazy import DeferredTensor, LazyPE, LazyPooled
 
 
 def sine3d_dim_t(num_feats: int, temperature: float = 10000) -> torch.Tensor:
@@ -53,6 +55,9 @@ class PositionEmbeddingSine3D(nn.Module):
 
     #: integer coordinates below this bound are served from the lookup table
     table_rows = 512
+    #: True (set by the overlay launcher): forward returns a deferred lazy.LazyPE so that the `tokens + PE` of
+    #: llava_arch.py:515 becomes one fused launch; a deferred coordinate input always yields a deferred PE
+    defer_add = False
 
     def __init__(self, embedding_size, temperature=10000, n_points=1):
         super().__init__()
@@ -61,32 +66,23 @@ class PositionEmbeddingSine3D(nn.Module):
         self.n_points = n_points
 
     def forward(self, x, add_to=None):
+        if isinstance(x, LazyPooled) or (self.defer_add and add_to is None and x.is_cuda):
+            pe = LazyPE(self, x)
+            return pe if add_to is None else pe + add_to
         cabi.require_cuda(x, "PositionEmbeddingSine3D input")
-        lib = cabi.load()
         if self.n_points > 1:
             x = x.flatten(1, 2)
-        B, N, _ = x.shape
-        n_tok = N // self.n_points
         out_dtype = x.dtype
-        coords = x.detach().to(torch.float32).contiguous()
-        tabs = get_tables(self.embedding_size, self.n_points, self.temperature, out_dtype, x.device, self.table_rows)
-        out = torch.empty((B, n_tok, self.embedding_size), dtype=out_dtype, device=x.device)
-        if add_to is not None:
-            if add_to.shape != out.shape or add_to.dtype != out_dtype:
-                raise ValueError("add_to must have the output's shape and dtype")
-            add_to = add_to.contiguous()
-        with torch.cuda.device(x.device):
-            cabi.check(lib.v3d_pe_sine3d(coords.data_ptr(), B * n_tok, self.n_points, self.embedding_size,
-                                         tabs.dim_t.data_ptr(), tabs.table.data_ptr(), tabs.rows, cabi.dtype_code(out_dtype),
-                                         cabi.ptr(add_to), out.data_ptr(), cabi.stream_ptr(x.device)), "v3d_pe_sine3d")
-        return out
+        if add_to is not None and (add_to.dtype != out_dtype or tuple(add_to.shape) != (x.shape[0], x.shape[1] // self.n_points, self.embedding_size)):
+            raise ValueError("add_to must have the output's shape and dtype")
+        return torch.ops.v3d.pe_sine3d(x, add_to, self.embedding_size, self.n_points, float(self.temperature), self.table_rows, out_dtype)
 
 
 class PositionEmbeddingMLP(nn.Module):
     """llava/model/position_encoding.py:52-84: Linear(3,512) -> LayerNorm -> ReLU -> Linear(512,E).
     Parameters live under mlp.{0,1,3}.{weight,bias} like the reference (train_3d.py:1818-1821 makes
-    them trainable).  Inference runs the tcgen05 kernel (hidden activations never reach HBM);
-    when gradients are needed the same math runs through torch autograd."""
+    them trainable).  A bf16 module runs the tcgen05 kernel (hidden activations never reach HBM) in
+    training and inference alike: torch.ops.v3d.pe_mlp carries the backward (ops.py)."""
 
     def __init__(self, embedding_size, temperature=10000, n_points=1):
         super().__init__()
@@ -105,23 +101,23 @@ class PositionEmbeddingMLP(nn.Module):
         if self.n_points > 1:
             # the reference's n_points > 1 branch dereferences an undefined name (position_encoding.py:79)
             raise NotImplementedError("PositionEmbeddingMLP supports n_points == 1 only, like the reference")
+        if isinstance(x, DeferredTensor):
+            x = x.materialize()
         cabi.require_cuda(x, "PositionEmbeddingMLP input")
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if needs_grad:
+        lin1, ln, lin2 = self.mlp[0], self.mlp[1], self.mlp[3]
+        # The tcgen05 kernel multiplies with W2 in bf16 and emits bf16: it serves bf16 modules (the recipe trains and
+        # evaluates in bf16).  Any other dtype runs the reference's own operator sequence on the device, so an fp32 / fp16
+        # model keeps its precision; train and eval go through the same path for a given dtype.
+        if lin2.weight.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
             pos = self.mlp(x)
             return pos if add_to is None else add_to + pos
-        lib = cabi.load()
         B, N, _ = x.shape
-        lin1, ln, lin2 = self.mlp[0], self.mlp[1], self.mlp[3]
-        coords = x.detach().to(torch.float32).contiguous()
-        f32 = lambda t: t.detach().to(torch.float32).contiguous()
-        w2 = lin2.weight.detach().to(torch.bfloat16).contiguous()
-        out = torch.empty((B, N, self.embedding_size), dtype=torch.bfloat16, device=x.device)
+        tok = None
         if add_to is not None:
-            add_to = add_to.to(torch.bfloat16).contiguous()
-        w1, b1, g, be, b2 = f32(lin1.weight), f32(lin1.bias), f32(ln.weight), f32(ln.bias), f32(lin2.bias)
-        with torch.cuda.device(x.device):
-            cabi.check(lib.v3d_pe_mlp(coords.data_ptr(), B * N, self.embedding_size, w1.data_ptr(), b1.data_ptr(), g.data_ptr(),
-                                      be.data_ptr(), float(ln.eps), w2.data_ptr(), b2.data_ptr(), cabi.ptr(add_to),
-                                      out.data_ptr(), cabi.stream_ptr(x.device)), "v3d_pe_mlp")
-        return out.to(x.dtype)
+            if add_to.dtype != torch.bfloat16 or tuple(add_to.shape) != (B, N, self.embedding_size):
+                pos = self.forward(x)
+                return add_to + pos
+            tok = add_to.reshape(B * N, self.embedding_size)
+        out = torch.ops.v3d.pe_mlp(x.detach().reshape(B * N, 3), lin1.weight, lin1.bias, ln.weight, ln.bias, float(ln.eps), lin2.weight,
+                                   lin2.bias, tok)
+        return out.view(B, N, self.embedding_size)

@@ -17,7 +17,8 @@ import math
 import torch
 
 from . import cabi
-from .position_encoding import PositionEmbeddingSine3D, get_tables
+from . import ops  # noqa: F401  (registers torch.ops.v3d.*)
+from .position_encoding import PositionEmbeddingSine3D
 
 _MODES = {"bilinear": cabi.TOKEN_POOL_BILINEAR, "average": cabi.TOKEN_POOL_AVERAGE, "max": cabi.TOKEN_POOL_MAX, "none": cabi.TOKEN_POOL_NONE}
 
@@ -41,34 +42,18 @@ def pool_pe_newline(image_feature: torch.Tensor, *, stride: int = 2, mode: str =
     Go = lib.v3d_token_pool_out_grid(G, int(stride), _MODES[mode])
     if Go <= 0:
         raise ValueError(f"bad stride {stride} for a {G}x{G} grid")
-    dt = image_feature.dtype
-    x = image_feature.contiguous()
-    d = cabi.PoolDesc()
-    d.tokens, d.n_frames, d.src_grid, d.E, d.dtype = x.data_ptr(), V, G, E, cabi.dtype_code(dt)
-    d.pool_mode, d.stride = _MODES[mode], int(stride)
-    keep = [x]
+    c, n_points, temperature, rows = None, 1, 10000.0, 0
     if coords is not None:
         if position_embedding is None:
             raise ValueError("coords need the position_embedding module they are encoded with")
-        n_points = position_embedding.n_points
-        c = coords.detach().to(torch.float32).reshape(V, Go * Go, n_points, 3).contiguous()
-        tabs = get_tables(position_embedding.embedding_size, n_points, position_embedding.temperature, dt, x.device,
-                          position_embedding.table_rows)
         if position_embedding.embedding_size != E:
             raise ValueError("embedding size of the PE module and of the tokens differ")
-        d.coords, d.n_points, d.dim_t, d.table, d.table_rows = c.data_ptr(), n_points, tabs.dim_t.data_ptr(), tabs.table.data_ptr(), tabs.rows
-        keep += [c, tabs]
-    nl = 0
-    if image_newline is not None:
-        newline = image_newline.detach().to(device=x.device, dtype=dt).contiguous()
-        if newline.shape != (E,):
-            raise ValueError("image_newline must have shape (E,)")
-        d.newline, nl = newline.data_ptr(), 1
-        keep.append(newline)
-    out = torch.empty((V, Go, Go + nl, E), dtype=dt, device=x.device)
-    d.out = out.data_ptr()
-    with torch.cuda.device(x.device):
-        cabi.check(lib.v3d_pool_pe_grid(d, cabi.stream_ptr(x.device)), "v3d_pool_pe_grid")
+        n_points, temperature, rows = position_embedding.n_points, float(position_embedding.temperature), position_embedding.table_rows
+        c = coords.detach().to(torch.float32).reshape(V, Go * Go, n_points, 3)
+    if image_newline is not None and image_newline.shape != (E,):
+        raise ValueError("image_newline must have shape (E,)")
+    out = torch.ops.v3d.pool_pe_grid(image_feature, int(stride), _MODES[mode], c, n_points, temperature, rows, image_newline)
+    nl = 0 if image_newline is None else 1
     if nl and flatten:
         return out.view(V * Go * (Go + 1), E)
     return out.view(V, Go * (Go + nl), E)

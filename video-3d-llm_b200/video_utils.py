@@ -135,11 +135,22 @@ class LazyWorldCoords:
     scene or (B,V,S,S,3) after merge_video_dict, backed by raw depth/pose/intrinsics."""
 
     def __init__(self, depth, poses, intrinsics, crop_size=384, strategy="center_crop", clamp=None, dtype=torch.float32,
-                 batched=False):
+                 batched=False, resampled=False, src_hw=None):
         self.depth, self.poses, self.intrinsics = depth, poses, intrinsics
-        self.crop_size, self.strategy, self.clamp = crop_size, strategy, clamp
+        self.crop_size, self.strategy = crop_size, strategy
+        # 'norm' clamp (llava/video_utils.py:232-234): (lo, hi) of ONE scene, or -- batched -- a list with one entry
+        # (or None) per scene: the reference clamps every scene to its own mesh AABB before stacking
+        self.clamp = clamp
         self.dtype = dtype
         self.batched = batched  # depth is (B,V,H,W) instead of (V,H,W)
+        # resampled: depth holds the crop_size x crop_size samples the loader already gathered (scene_pack.py) instead of
+        # full frames; src_hw is then the size of the frames they were taken from (it fixes the index maps)
+        self.resampled = bool(resampled)
+        self.src_hw = tuple(src_hw) if src_hw is not None else tuple(depth.shape[-2:])
+        if self.resampled and src_hw is None:
+            raise ValueError("resampled depth needs src_hw, the size of the frames it was taken from")
+        if batched and clamp is not None and not isinstance(clamp, list):
+            raise TypeError("a batched handle takes a list of per-scene clamps")
         self._full = None
 
     # ---- tensor-like surface used by the reference ------------------------------------------
@@ -166,10 +177,17 @@ class LazyWorldCoords:
     def __len__(self):
         return self.shape[0]
 
-    def _like(self, depth=None, poses=None, intrinsics=None, dtype=None, batched=None):
+    def _like(self, depth=None, poses=None, intrinsics=None, dtype=None, batched=None, clamp="same"):
         return LazyWorldCoords(self.depth if depth is None else depth, self.poses if poses is None else poses,
-                               self.intrinsics if intrinsics is None else intrinsics, self.crop_size, self.strategy, self.clamp,
-                               self.dtype if dtype is None else dtype, self.batched if batched is None else batched)
+                               self.intrinsics if intrinsics is None else intrinsics, self.crop_size, self.strategy,
+                               self.clamp if isinstance(clamp, str) else clamp,
+                               self.dtype if dtype is None else dtype, self.batched if batched is None else batched,
+                               resampled=self.resampled, src_hw=self.src_hw)
+
+    def _scene(self, b: int):
+        """Scene b of a batched handle, with its own clamp."""
+        return self._like(self.depth[b], self.poses[b], self.intrinsics[b], batched=False,
+                          clamp=None if self.clamp is None else self.clamp[b])
 
     def to(self, *args, **kwargs):
         device, dtype = kwargs.get("device"), kwargs.get("dtype")
@@ -211,11 +229,11 @@ class LazyWorldCoords:
         if not self.batched:
             raise TypeError("iterate a batched LazyWorldCoords (B,V,S,S,3)")
         for b in range(self.depth.shape[0]):
-            yield self._like(self.depth[b], self.poses[b], self.intrinsics[b], batched=False)
+            yield self._scene(b)
 
     def __getitem__(self, idx):
         if self.batched and isinstance(idx, int):
-            return self._like(self.depth[idx], self.poses[idx], self.intrinsics[idx], batched=False)
+            return self._scene(idx)
         return self.materialize()[idx]
 
     def view(self, *shape):
@@ -233,38 +251,52 @@ class LazyWorldCoords:
 
     # ---- evaluation ------------------------------------------------------------------------------
     def _maps(self, dev):
-        H, W = self.depth.shape[-2:]
+        H, W = self.src_hw
         return geometry.resample_maps(H, W, self.crop_size, self.strategy, dev)
+
+    def _full_depth(self, dev):
+        """(N,H,W) frames on `dev`; resampled depth is scattered back to the pixels it was taken from (everything else
+        stays zero and is never read through the index maps)."""
+        d = self.depth.reshape((-1,) + tuple(self.depth.shape[-2:])).to(dev)
+        if not self.resampled:
+            return d
+        H, W = self.src_hw
+        rm, cm = self._maps(dev)
+        full = torch.zeros((d.shape[0], H, W), dtype=d.dtype, device=dev)
+        lib = cabi.load()
+        with torch.cuda.device(dev):
+            cabi.check(lib.v3d_scatter_resampled_depth(d.contiguous().data_ptr(), full.data_ptr(), cabi.depth_code(d), d.shape[0], H, W,
+                                                       rm.data_ptr(), cm.data_ptr(), d.shape[1], d.shape[2], cabi.stream_ptr(dev)),
+                       "v3d_scatter_resampled_depth")
+        return full
 
     def materialize(self) -> torch.Tensor:
         """The tensor the reference would hold: (…,S,S,3) in self.dtype (llava/video_utils.py:296-321)."""
         if self._full is None:
+            if self.batched and self.clamp is not None:
+                self._full = torch.stack([self._scene(b).materialize() for b in range(self.depth.shape[0])])
+                return self._full
             dev = _device_for(self.depth)
             rm, cm = self._maps(dev)
-            d = self.depth.reshape((-1,) + tuple(self.depth.shape[-2:]))
-            full = unproject(self.intrinsics.reshape(-1, 4, 4), self.poses.reshape(-1, 4, 4), d, row_map=rm, col_map=cm, clamp=self.clamp)
+            if self.resampled and tuple(self.depth.shape[-2:]) != (self.crop_size, self.crop_size):
+                raise ValueError(f"cannot materialise {tuple(self.shape)} coordinates from {tuple(self.depth.shape[-2:])} resampled depth")
+            full = unproject(self.intrinsics.reshape(-1, 4, 4), self.poses.reshape(-1, 4, 4), self._full_depth(dev), row_map=rm, col_map=cm,
+                             clamp=self.clamp)
             self._full = full.reshape(tuple(self.shape)).to(self.dtype)
         return self._full
 
-    def pooled(self, patch_size: int, mode: str, trim: int = 6) -> torch.Tensor:
-        """Pooled coordinates (V,G,G[,n],3) straight from depth with the fused kernel (PE off)."""
-        from .frontend import FrontEnd
+    def pooled(self, patch_size: int, mode: str, trim: int = 6):
+        """Pooled coordinates (V,G,G[,n],3) straight from depth, deferred (lazy.LazyPooled): evaluated by the fused kernel
+        when -- and with whatever -- the caller finally consumes them (discretisation, PE, token add)."""
+        from .lazy import LazyPooled
 
         if self.batched:
             raise TypeError("pool one scene at a time (the reference iterates over the batch, llava_arch.py:396)")
-        dev = _device_for(self.depth)
-        H, W = self.depth.shape[-2:]
-        kind = mode  # 'avg' | 'minmax' | 'sample9' | ...
-        fe = _pool_frontends.get((H, W, self.crop_size, self.strategy, patch_size, trim, kind, str(dev)))
-        if fe is None:
-            fe = FrontEnd(device=dev, H=H, W=W, crop_size=self.crop_size, strategy=self.strategy, patch_size=patch_size, trim=trim,
-                          world_position_embedding_type=kind)
-            _pool_frontends[(H, W, self.crop_size, self.strategy, patch_size, trim, kind, str(dev))] = fe
-        _, pooled, _ = fe(self.depth.to(dev), self.poses.to(dev), self.intrinsics.to(dev), clamp=self.clamp, want_coords=True)
-        return pooled.to(self.dtype)
+        return LazyPooled(self, patch_size, mode, trim, cabi.load().v3d_pool_points(_POOL_CODES[mode]))
 
 
-_pool_frontends: dict = {}
+_POOL_CODES = {"avg": cabi.POOL_AVG, "minmax": cabi.POOL_MINMAX, "sample9": cabi.POOL_SAMPLE9, "sample5": cabi.POOL_SAMPLE5,
+               "sample1": cabi.POOL_SAMPLE1}
 
 
 class VideoProcessor:
@@ -360,6 +392,12 @@ class VideoProcessor:
         The reference caps the order at 32 picks (:93); so does the kernel's record."""
         from . import mc_sampling
 
+        if torch.utils.data.get_worker_info() is not None and not torch.cuda.is_initialized():
+            # CUDA cannot be initialised in a forked DataLoader worker (INTEGRATION.md "Process model")
+            raise RuntimeError(
+                f"frame_sampling_strategy={self.frame_sampling_strategy!r} computes the max-coverage order on the GPU, which a forked "
+                "DataLoader worker cannot do: call VideoProcessor.precompute_mc_order() in the parent process before the loader starts "
+                "(the launcher does when V3D_MC_PRECOMPUTE=1), or run with dataloader_num_workers=0 / multiprocessing_context='spawn'")
         info = self.scene[video_id]
         files = [os.path.join(self.video_folder, img["img_path"]) for img in info["images"]][::2]
         if len(files) < 32:
@@ -377,6 +415,17 @@ class VideoProcessor:
                                         "seed": seed}])[0]
         return {"video_id": video_id, "frame_files": [files[i] for i in res["order"][:max_pick]],
                 "voxel_nums": res["gains"][:max_pick], "num_all_voxels": res["n_all"], "num_select_voxels": res["n_sel"]}
+
+    def precompute_mc_order(self, video_ids=None) -> int:
+        """Run the online MC sampler for `video_ids` (default: every scene with a mesh universe) NOW, in this process, and
+        keep the records: forked DataLoader workers inherit them and never need the GPU.  Returns the number of scenes."""
+        if "online" not in self.frame_sampling_strategy:
+            return 0
+        ids = list(video_ids) if video_ids is not None else [v for v in self.scene if v.split("/")[-1] in self.pc_data]
+        for video_id in ids:
+            if video_id not in self.mc_sampling_files:
+                self.mc_sampling_files[video_id] = self.mc_sample_online(video_id)
+        return len(ids)
 
     # ---- geometry --------------------------------------------------------------------------------
     def _pack(self, video_id: str):
@@ -399,6 +448,25 @@ class VideoProcessor:
 
             return pack.load([scene_pack.frame_number(f) for f in frame_files])
         return self.load_frames_from_files(video_id, frame_files)
+
+    def world_coords(self, video_id: str, frame_files, crop_size: int = 384, strategy: str = "center_crop", do_normalize=None):
+        """The `world_coords` entry of preprocess() (:291-321) for a given frame list, without touching the RGB frames:
+        a LazyWorldCoords handle (lazy=True) or the (V,crop,crop,3) tensor.  With a packed scene that stores the depth
+        already resampled for (crop_size, strategy), a lazy handle carries those samples (48 % of the bytes) and the
+        fused kernel reads them in place."""
+        if do_normalize is None:
+            do_normalize = "norm" in self.frame_sampling_strategy
+        clamp = self._clamp_for(video_id, do_normalize)
+        pack = self._pack(video_id)
+        if self.lazy and pack is not None and pack.resampled_for == (crop_size, strategy):
+            from . import scene_pack
+
+            depth, poses, intr = pack.load_resampled([scene_pack.frame_number(f) for f in frame_files])
+            return LazyWorldCoords(depth, poses, intr, crop_size=crop_size, strategy=strategy, clamp=clamp, resampled=True,
+                                   src_hw=(pack.H, pack.W))
+        depth, poses, intr = self.load_frames(video_id, frame_files)
+        handle = LazyWorldCoords(depth, poses, intr, crop_size=crop_size, strategy=strategy, clamp=clamp)
+        return handle if self.lazy else handle.materialize()
 
     def load_frames_from_files(self, video_id: str, frame_files):
         """:212-230 as written: Image.open of the depth PNG, np.loadtxt of the pose, axis_align(f64) @ pose."""
@@ -439,9 +507,12 @@ class VideoProcessor:
                                                      do_shift=("shift" in self.frame_sampling_strategy))
         else:
             frame_files = self.sample_frame_files(video_id, force_sample=force_sample, frames_upbound=frames_upbound)
-        depth, poses, intr = self.load_frames(video_id, frame_files)
-        clamp = self._clamp_for(video_id, "norm" in self.frame_sampling_strategy)
-        V, H, W = depth.shape
+        pack = self._pack(video_id)
+        if pack is not None:
+            H, W = pack.H, pack.W
+        else:
+            with Image.open(frame_files[0].replace(".jpg", ".png")) as im:
+                W, H = im.size
 
         images = []
         for frame_file in frame_files:
@@ -455,12 +526,13 @@ class VideoProcessor:
             left, top = (new_width - crop_size) // 2, (new_height - crop_size) // 2
             images = [frame.resize((new_width, new_height)).crop((left, top, left + crop_size, top + crop_size)) for frame in images]
 
-        handle = LazyWorldCoords(depth, poses, intr, crop_size=crop_size, strategy=strategy, clamp=clamp)
+        clamp = self._clamp_for(video_id, "norm" in self.frame_sampling_strategy)
+        world_coords = self.world_coords(video_id, frame_files, crop_size, strategy)
         if self.lazy:
-            world_coords = handle
-            boundry = _LazyBoundary(depth, poses, intr, clamp)
+            # `boundry` (:273-277) is dropped by merge_video_dict: evaluated (from the full-resolution frames) only if read
+            boundry = _LazyBoundary(lambda: self.load_frames(video_id, frame_files), clamp)
         else:
-            world_coords = handle.materialize()
+            depth, poses, intr = self.load_frames(video_id, frame_files)
             boundry = boundary(intr, poses, depth, clamp)
         return {
             "images": images,
@@ -494,13 +566,13 @@ class VideoProcessor:
 class _LazyBoundary:
     """`boundry` is dropped by merge_video_dict and unused downstream; compute on demand."""
 
-    def __init__(self, depth, poses, intr, clamp):
-        self._args, self._val = (depth, poses, intr, clamp), None
+    def __init__(self, load, clamp):
+        self._load, self._clamp, self._val = load, clamp, None
 
     def tensor(self) -> torch.Tensor:
         if self._val is None:
-            d, p, k, c = self._args
-            self._val = boundary(k, p, d, c).cpu()
+            d, p, k = self._load()
+            self._val = boundary(k, p, d, self._clamp).cpu()
         return self._val
 
     def __getattr__(self, name):
@@ -521,9 +593,15 @@ def merge_video_dict(video_dict_list):
             vals = [vd[k] for vd in video_dict_list]
             if k == "world_coords" and isinstance(vals[0], LazyWorldCoords):
                 h0 = vals[0]
+                for v in vals[1:]:
+                    same = (v.crop_size, v.strategy, v.dtype, v.resampled, v.src_hw) == (h0.crop_size, h0.strategy, h0.dtype, h0.resampled, h0.src_hw)
+                    if not isinstance(v, LazyWorldCoords) or not same:
+                        raise ValueError("cannot stack world_coords handles with different crop size / strategy / dtype / layout")
+                clamps = [v.clamp for v in vals]
                 new_video_dict[k] = LazyWorldCoords(torch.stack([v.depth for v in vals]), torch.stack([v.poses for v in vals]),
-                                                    torch.stack([v.intrinsics for v in vals]), h0.crop_size, h0.strategy, h0.clamp,
-                                                    h0.dtype, batched=True)
+                                                    torch.stack([v.intrinsics for v in vals]), h0.crop_size, h0.strategy,
+                                                    None if all(c is None for c in clamps) else clamps, h0.dtype, batched=True,
+                                                    resampled=h0.resampled, src_hw=h0.src_hw)
             else:
                 new_video_dict[k] = torch.stack(vals)
         elif k in ["box_input"]:
