@@ -140,3 +140,97 @@ def projector_tail(image_feature: torch.Tensor, coords, embedding_size: int, ima
     if image_newline is not None:
         x = add_token_per_grid(x, image_newline)
     return x
+
+
+# ------------------------------------------------------------------------------------------
+# maximum-coverage sampler on the host: the CPU baselines of bench.py
+# ------------------------------------------------------------------------------------------
+def mc_as_written(depths: torch.Tensor, poses: torch.Tensor, intrinsics: torch.Tensor, pc_voxels, voxel_size: float = 0.1,
+                  seed: int = 0, max_pick: int = 32):
+    """scripts/3d/preprocessing/max_coverage_sampling.py:34-104 as the reference writes it, with CPU tensors in place of
+    `.to('cuda')` (:39) and random.seed(seed) right before the greedy loop: unproject every candidate frame at full
+    resolution, divide / round / int, `torch.unique(dim=0)` per frame (:47-50), Python tuples and sets, greedy with
+    random.choice tie-breaks.  Returns (order, gains, num_all_voxels, num_select_voxels, seconds per stage)."""
+    import random
+    import time
+
+    t0 = time.perf_counter()
+    world_coords = unproject(intrinsics, poses, depths)
+    world_coords = world_coords / voxel_size
+    world_coords = world_coords.round().int()
+    world_coords_discrete = {}
+    for f, coords in enumerate(world_coords):
+        coords = torch.unique(coords.view(-1, 3), dim=0)
+        world_coords_discrete[f] = [tuple(c) for c in coords.tolist()]
+    t1 = time.perf_counter()
+    pc_voxel = set(tuple(int(t) for t in c) for c in pc_voxels)
+    all_voxel = set()
+    for f in world_coords_discrete:
+        all_voxel.update(world_coords_discrete[f])
+    random.seed(seed)
+    picked, gains, used = [], [], set()
+    frames = dict(world_coords_discrete)
+    for _ in range(len(frames)):
+        best, ties = -1, []
+        for f in frames:
+            cur = set(frames[f]) & pc_voxel
+            g = len(cur) - len(used & cur)
+            if g > best:
+                best, ties = g, [f]
+            elif g == best:
+                ties.append(f)
+        f = random.choice(ties)
+        used.update(frames[f])
+        picked.append(f)
+        gains.append(best)
+        frames.pop(f)
+        if len(picked) >= max_pick:
+            break
+    t2 = time.perf_counter()
+    return picked, gains, len(all_voxel & pc_voxel), len(used & pc_voxel), {"voxelize_s": t1 - t0, "greedy_s": t2 - t1}
+
+
+def mc_packed_keys(depths: torch.Tensor, poses: torch.Tensor, intrinsics: torch.Tensor, pc_voxels, voxel_size: float = 0.1,
+                   seed: int = 0, max_pick: int = 32):
+    """The same selection with the obvious host optimisation (clearly labelled as such in the bench): voxel triples packed
+    into int64 keys, `np.unique` per frame, coverage as boolean rows over the mesh universe, greedy with numpy reductions.
+    Same picks as mc_as_written (the tie-break protocol is kept)."""
+    import random
+    import time
+
+    import numpy as np
+
+    t0 = time.perf_counter()
+    pc = np.asarray(pc_voxels, np.int64).reshape(-1, 3)
+    off = 1 << 20
+    key = lambda a: ((a[..., 0] + off) << 42) | ((a[..., 1] + off) << 21) | (a[..., 2] + off)  # noqa: E731
+    pc_keys = key(pc)
+    order_pc = np.argsort(pc_keys)
+    pc_sorted = pc_keys[order_pc]
+    F = depths.shape[0]
+    cover = np.zeros((F, len(pc_keys)), bool)
+    for f in range(F):
+        w = unproject(intrinsics[f:f + 1], poses[f:f + 1], depths[f:f + 1])
+        ids = (w / voxel_size).round().long().view(-1, 3).numpy()
+        k = np.unique(key(ids))
+        pos = np.searchsorted(pc_sorted, k)
+        pos[pos == len(pc_sorted)] = 0
+        hit = pc_sorted[pos] == k
+        cover[f, order_pc[pos[hit]]] = True
+    t1 = time.perf_counter()
+    n_all = int(cover.any(0).sum())
+    random.seed(seed)
+    used = np.zeros(len(pc_keys), bool)
+    alive = list(range(F))
+    picked, gains = [], []
+    while alive and len(picked) < max_pick:
+        g = (cover[alive] & ~used).sum(1)
+        best = int(g.max())
+        ties = [alive[i] for i in np.nonzero(g == best)[0]]
+        f = random.choice(ties)
+        used |= cover[f]
+        picked.append(f)
+        gains.append(best)
+        alive.remove(f)
+    t2 = time.perf_counter()
+    return picked, gains, n_all, int(used.sum()), {"voxelize_s": t1 - t0, "greedy_s": t2 - t1}

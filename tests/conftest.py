@@ -13,6 +13,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(autouse=True)
+def _dim_t_like_the_cpu_reference(request):
+    """The golden vectors and the CPU oracle hold the reference's results on the CPU, where dim_t comes from torch's CPU pow;
+    the parity tests therefore build the PE tables from that.  tests/test_gpu_overlay.py compares with the reference running
+    on the GPU and switches to the device-evaluated dim_t (the package default)."""
+    from video_3d_llm_b200 import position_encoding
+
+    prev = position_encoding.set_dim_t_source("device" if request.module.__name__.endswith("test_gpu_overlay") else "cpu")
+    yield
+    position_encoding.set_dim_t_source(prev)
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")

@@ -144,6 +144,7 @@ class LazyPooled(DeferredTensor):
     # ---- evaluation
     def frontend(self, device, embedding_size=None, temperature=10000.0, out_dtype=torch.bfloat16):
         """The FrontEnd (cached per configuration and device) that evaluates this value (+ the PE when embedding_size is given)."""
+        from . import position_encoding as _pe
         from .frontend import FrontEnd
 
         h = self.handle
@@ -151,7 +152,7 @@ class LazyPooled(DeferredTensor):
         disc = self.disc or dict(voxel_size=0.1, min_xyz_range=(-15.0, -15.0, -5.0), max_xyz_range=(15.0, 15.0, 5.0), div_mode=cabi.DIV_IEEE)
         H, W = h.src_hw
         key = (H, W, h.crop_size, h.strategy, self.patch_size, self.trim, kind, embedding_size, float(temperature), out_dtype,
-               disc["voxel_size"], disc["min_xyz_range"], disc["max_xyz_range"], disc["div_mode"], str(device))
+               disc["voxel_size"], disc["min_xyz_range"], disc["max_xyz_range"], disc["div_mode"], str(device), _pe._dim_t_source)
         fe = _frontends.get(key)
         if fe is None:
             fe = FrontEnd(device=device, H=H, W=W, crop_size=h.crop_size, strategy=h.strategy, patch_size=self.patch_size, trim=self.trim,

@@ -120,6 +120,35 @@ class MCSampler:
         plan = self.plan(scenes)
         return self.decode(self.run(plan))
 
+    def sample_and_encode(self, plan, frontend, strategy: str = "mc-ratio95", frames_upbound: int = 32, out=None):
+        """BASELINE configs[3] for the scenes of a plan: max-coverage order (voxelise + greedy) -> coverage-ratio prefix cut
+        (llava/video_utils.py:131-159) -> sin-3D PE of the SELECTED frames with the fused front end (the frames a training
+        sample built with this strategy would feed to llava_arch.py:396-515).
+        Returns (records (n,68) int32 on the device, selected candidate indices per scene, PE (n_selected, G*G, E))."""
+        rec = self.run(plan)
+        picks = [ratio_cut(r, strategy, frames_upbound) for r in self.decode(rec)]  # one D2H of 272 bytes per scene
+        depth = torch.cat([plan["keep"][i][0][torch.as_tensor(p, device=self.device)] for i, p in enumerate(picks)])
+        poses = torch.cat([plan["keep"][i][1][torch.as_tensor(p, device=self.device)] for i, p in enumerate(picks)])
+        intr = torch.cat([plan["keep"][i][2][torch.as_tensor(p, device=self.device)] for i, p in enumerate(picks)])
+        pe = frontend(depth, poses, intr, out=out)
+        return rec, picks, pe
+
+
+def ratio_cut(record: dict, strategy: str, frames_upbound: int = 32) -> list:
+    """llava/video_utils.py:131-159 on candidate indices: the first frames_upbound picks, cut at the first prefix whose
+    cumulative gain reaches ratio * num_all_voxels (0.95 / 0.90 by substring, else no cut), sorted by frame order."""
+    order, gains = record["order"][:frames_upbound], record["gains"][:frames_upbound]
+    ratio = 0.95 if "ratio95" in strategy else (0.9 if "ratio90" in strategy else 1.0)
+    if ratio != 1.0:
+        need, kept, covered = record["n_all"] * ratio, [], 0
+        for f, n in zip(order, gains):
+            kept.append(f)
+            covered += n
+            if covered >= need:
+                break
+        order = kept
+    return sorted(order)
+
 
 def voxel_ids(world: torch.Tensor, voxel_size: float = 0.1, div_mode: int = cabi.DIV_IEEE) -> torch.Tensor:
     """int(round(world / voxel_size)) (max_coverage_sampling.py:44-45) on the device."""
@@ -142,43 +171,71 @@ def mesh_to_voxels(xyz: torch.Tensor, voxel_size: float = 0.1) -> list:
 
 def main(args):
     """Drop-in for max_coverage_sampling.py:main -- same inputs (data/metadata/pcd_discrete_<voxel>.pkl,
-    the EmbodiedScan infos, posed_images) and the same output JSON."""
+    the EmbodiedScan infos, posed_images) and the same output JSON.  Under torchrun (WORLD_SIZE > 1) the scenes are
+    sharded round-robin over the ranks (sharding.shard_indices, like the reference's eval drivers split their questions,
+    llava/eval/model_scanqa.py:244-245), every rank samples its own scenes on its own GPU, ONE all-gather of the 272-byte
+    records brings them to every rank in scene order and rank 0 writes the JSON.  Scene i is sampled under
+    random.seed(seed + i) whatever the sharding, so the file does not depend on the number of GPUs."""
+    import torch.distributed as dist
+
+    from . import sharding
     from .video_utils import VideoProcessor
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    started = False
+    if world > 1 and not dist.is_initialized():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+        started = True
+    rank, world = sharding.world()
     with open(f"data/metadata/pcd_discrete_{args.voxel_size}.pkl", "rb") as f:
         pc_data = pickle.load(f)
-    vp = VideoProcessor(voxel_size=args.voxel_size, min_xyz_range=None, max_xyz_range=None)
+    vp = VideoProcessor(voxel_size=args.voxel_size, min_xyz_range=None, max_xyz_range=None,
+                        pack_dir=getattr(args, "pack_dir", None) or os.environ.get("V3D_PACK_DIR"))
     dev = torch.device("cuda", torch.cuda.current_device())
-    sampler = MCSampler(args.voxel_size, device=dev)
-    all_data = []
-    scene_ids = sorted(os.listdir(args.video_dir)) if getattr(args, "sorted", False) else os.listdir(args.video_dir)
+    div = getattr(args, "div_mode", None)
+    div_mode = cabi.div_mode_default() if div is None else {"ieee": cabi.DIV_IEEE, "reciprocal": cabi.DIV_RECIPROCAL}[div]
+    sampler = MCSampler(args.voxel_size, device=dev, div_mode=div_mode)
+    scene_ids = sorted(os.listdir(args.video_dir)) if (getattr(args, "sorted", False) or world > 1) else os.listdir(args.video_dir)
+
+    def candidates(scene_id):
+        info = vp.scene[f"scannet/{scene_id}"]
+        files = [os.path.join(vp.video_folder, img["img_path"]) for img in info["images"]][::2]
+        if len(files) < 32:
+            files = [os.path.join(vp.video_folder, img["img_path"]) for img in info["images"]]
+        return files
+
+    mine = sharding.shard_indices(len(scene_ids), rank, world)
     batch = max(1, int(getattr(args, "batch_scenes", 8)))
-    for b0 in range(0, len(scene_ids), batch):
-        group, metas = [], []
-        for k, scene_id in enumerate(scene_ids[b0:b0 + batch]):
-            video_id = f"scannet/{scene_id}"
-            info = vp.scene[video_id]
-            files = [os.path.join(vp.video_folder, img["img_path"]) for img in info["images"]][::2]
-            if len(files) < 32:
-                files = [os.path.join(vp.video_folder, img["img_path"]) for img in info["images"]]
-            depth, poses, intr = vp.load_frames(video_id, files)
+    local = torch.full((len(mine), cabi.MC_RECORD_INTS), -1, dtype=torch.int32, device=dev)
+    for b0 in range(0, len(mine), batch):
+        group = []
+        for i in mine[b0:b0 + batch]:
+            scene_id = scene_ids[i]
+            depth, poses, intr = vp.load_frames(f"scannet/{scene_id}", candidates(scene_id))
             pc = torch.tensor(np.asarray(pc_data[scene_id], dtype=np.int32).reshape(-1, 3), device=dev)
-            seed = getattr(args, "seed", 0) + b0 + k
-            group.append({"depth": depth.to(dev), "poses": poses.to(dev), "intrinsics": intr.to(dev), "pc_voxels": pc, "seed": seed})
-            metas.append((video_id, files))
+            group.append({"depth": depth.to(dev), "poses": poses.to(dev), "intrinsics": intr.to(dev), "pc_voxels": pc,
+                          "seed": getattr(args, "seed", 0) + i})
         # scenes of one launch share H, W; fall back to one scene per launch otherwise
         shapes = {tuple(g["depth"].shape[-2:]) for g in group}
-        runs = [group] if len(shapes) == 1 else [[g] for g in group]
-        results = []
-        for r in runs:
-            results.extend(sampler.sample(r))
-        for (video_id, files), res in zip(metas, results):
-            print(f"[{video_id.split('/')[-1]}] all voxels: {res['n_sel']}/{res['n_all']} | ratio: "
+        o = b0
+        for r in ([group] if len(shapes) == 1 else [[g] for g in group]):
+            local[o:o + len(r)] = sampler.run(sampler.plan(r))
+            o += len(r)
+    records = sharding.all_gather_records(local, len(scene_ids))  # (n_scenes, 68) in scene order on every rank
+    all_data = []
+    if rank == 0:
+        for scene_id, res in zip(scene_ids, MCSampler.decode(records)):
+            video_id, files = f"scannet/{scene_id}", candidates(scene_id)
+            print(f"[{scene_id}] all voxels: {res['n_sel']}/{res['n_all']} | ratio: "
                   f"{res['n_sel'] / max(res['n_all'], 1)} | image num: {len(res['order'])}/{len(files)}")
             all_data.append({"video_id": video_id, "frame_files": [files[i] for i in res["order"]], "voxel_nums": res["gains"],
                              "num_all_voxels": res["n_all"], "num_select_voxels": res["n_sel"]})
-    with open(args.output_file, "w") as f:
-        json.dump(all_data, f)
+        with open(args.output_file, "w") as f:
+            json.dump(all_data, f)
+    if started:
+        dist.barrier()
+        dist.destroy_process_group()
     return all_data
 
 
@@ -189,4 +246,9 @@ if __name__ == "__main__":
     parser.add_argument("--output_file", type=str, default="data/metadata/scannet_select_frames.json")
     parser.add_argument("--seed", type=int, default=0, help="scene i is sampled under random.seed(seed + i)")
     parser.add_argument("--batch_scenes", type=int, default=8)
+    parser.add_argument("--div_mode", choices=["ieee", "reciprocal"], default=None,
+                        help="x / voxel_size semantics: 'reciprocal' = ATen's CUDA kernel (what the reference script runs, default; "
+                             "or V3D_DIV_MODE), 'ieee' = torch CPU")
+    parser.add_argument("--pack_dir", default=None, help="packed scenes (scene_pack.py) instead of PNG/txt files")
+    parser.add_argument("--sorted", action="store_true", help="process scenes in sorted order (always on under torchrun)")
     main(parser.parse_args())

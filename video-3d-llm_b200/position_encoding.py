@@ -6,6 +6,8 @@ MLP variant) state_dict keys as the reference, so `LlavaMetaModel.__init__`
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -14,10 +16,25 @@ from . import ops  # noqa: F401  (registers torch.ops.v3d.*)
 from .lazy import DeferredTensor, LazyPE, LazyPooled
 
 
-def sine3d_dim_t(num_feats: int, temperature: float = 10000) -> torch.Tensor:
-    """llava/model/position_encoding.py:24-25, evaluated by torch on the CPU exactly as the reference
-    writes it (torch's fp32 pow is not correctly rounded, so this is the bit-exact source)."""
-    dim_t = torch.arange(num_feats, dtype=torch.float32)
+#: where dim_t is evaluated.  The reference builds it on x.device (position_encoding.py:24), i.e. with torch's CUDA pow
+#: for every real run; torch's fp32 pow is not correctly rounded and its CPU and CUDA results differ by one ulp for some
+#: channels, which moves sin/cos of large coordinates by up to ~8e-6.  "device" (default, or V3D_DIM_T=device) follows
+#: the reference on the GPU; "cpu" reproduces the reference run on the CPU (the golden vectors and the CPU oracle).
+_dim_t_source = os.environ.get("V3D_DIM_T", "device")
+
+
+def set_dim_t_source(source: str) -> str:
+    """'device' or 'cpu'; returns the previous setting."""
+    global _dim_t_source
+    if source not in ("device", "cpu"):
+        raise ValueError("dim_t source must be 'device' or 'cpu'")
+    prev, _dim_t_source = _dim_t_source, source
+    return prev
+
+
+def sine3d_dim_t(num_feats: int, temperature: float = 10000, device="cpu") -> torch.Tensor:
+    """llava/model/position_encoding.py:24-25, evaluated by torch exactly as the reference writes it."""
+    dim_t = torch.arange(num_feats, dtype=torch.float32, device=device)
     return temperature ** (2 * (dim_t // 2) / num_feats)
 
 
@@ -28,7 +45,7 @@ class Sine3DTables:
         lib = cabi.load()
         self.E, self.n_points, self.rows, self.dtype = embedding_size, n_points, rows, dtype
         self.nf = embedding_size // (3 * n_points)
-        self.dim_t = sine3d_dim_t(self.nf, temperature).to(device)
+        self.dim_t = sine3d_dim_t(self.nf, temperature, device if _dim_t_source == "device" else "cpu").to(device)
         nbytes = lib.v3d_pe_table_bytes(embedding_size, n_points, rows, cabi.dtype_code(dtype))
         if nbytes == 0:
             raise NotImplementedError(f"no PE table for E={embedding_size}, n_points={n_points} (needs E // (3*n_points) >= 8)")
@@ -42,7 +59,7 @@ _tables: dict = {}
 
 
 def get_tables(embedding_size, n_points, temperature, dtype, device, rows) -> Sine3DTables:
-    key = (embedding_size, n_points, float(temperature), dtype, str(torch.device(device)), rows)
+    key = (embedding_size, n_points, float(temperature), dtype, str(torch.device(device)), rows, _dim_t_source)
     if key not in _tables:
         _tables[key] = Sine3DTables(embedding_size, n_points, temperature, dtype, device, rows)
     return _tables[key]
