@@ -11,23 +11,31 @@ discretise -> sin-3D PE (E=1152) added to the bf16 vision tokens, ONE fused kern
 
 Printed JSON line (rank 0):
   value      frames/s of the whole job, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e        the same through the public API with HOST (pinned) depth/pose/intrinsics buffers: H2D copies
-             and a D2H read of the per-token voxel coordinates inside the timed region.  The pinned depth is
-             what the packed-scene loader emits (ScenePack.load(resample=...)): the reference's nearest resize +
-             crop applied on the host to the raw uint16 depth, i.e. the 378x378 samples per frame the kernel reads
+  e2e        the same batch through the public API the reference's scripts use: packed scenes on disk (page cache) ->
+             VideoProcessor(pack_dir) / SceneBatchLoader (host copies into pinned memory INSIDE the timed loop) -> H2D ->
+             the reference's call sequence per scene (average_coordinate_in_patch -> discrete_coords ->
+             tokens + world_position_embedding(coords)) -> D2H read of a result slice
   roofline   algorithmic bytes per launch / average launch time vs the measured HBM copy peak
   cpu_baseline  the reference's torch-CPU operator sequence (oracle/torch_port.py) on the host cores
+  overlay_path  device-resident cost of that call sequence (what the unchanged scripts launch under the overlay) for
+             BASELINE configs[0] (1 scene) and configs[1] (16 scenes), both grid geometries
+  config1    BASELINE configs[0] on the GPU: one 32-frame scene per launch, rotating buffers, and its end-to-end rate
   mc         secondary metric: max-coverage sampled scenes/s (voxelise + greedy, BASELINE configs[2]); mc.e2e: the
-             same with all candidate frames uploaded from pinned host memory every step
-  default_recipe_geometry / mlp_pe / projector_tail / host_ingest   secondary objects: the reference-default 14x14 grid
-             with E=3584, the tcgen05 learned-projection PE, the pool + PE + newline kernel, PNG/txt vs packed ingest
+             same with all candidate frames uploaded from pinned host memory every step; mc.cpu_baseline: the
+             reference's loop as written (bounded sample) and a packed-key host variant
+  config4    BASELINE configs[3]: 256 scenes, mc-ratio95 cut + PE of the selected frames, scene-sharded, all-gather
+  host_limits   pinned H2D GB/s per rank (all ranks at once) and loader memcpy GB/s: the ceilings of `e2e`
+  default_recipe_geometry / mlp_pe / projector_tail / host_ingest   further secondary objects
 `--impl reference` times the CPU port only (rank 0), on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
+import pickle
+import shutil
 import statistics
 import subprocess
 import sys
@@ -50,6 +58,10 @@ BYTES_PE_PER_FRAME = GRID * GRID * EMB * 2
 BYTES_PER_FRAME_FUSED_ADD = BYTES_IN_PER_FRAME + 2 * BYTES_PE_PER_FRAME  # 3 645 080
 WORKLOAD = (f"{SCENES} scenes x {FRAMES} frames uniform sampling, depth {H}x{W} u16 -> fused unproject+pool+PE+add "
             f"into {EMB}-d tokens on the {GRID}x{GRID} grid (BASELINE configs[1])")
+# the same dict in both arms (the reference arm times a bounded sample of it, stated in cpu_baseline.sample)
+CONFIG = {"workload": WORKLOAD, "scenes_per_rank": SCENES, "frames_per_scene": FRAMES, "patch": PATCH, "grid": GRID, "embedding": EMB,
+          "pe_dtype": "bf16", "world_position_embedding_type": "avg-discrete-sin3d",
+          "l2": "inputs larger than L2: one step touches 1.87 GB (depth 315 MB + tokens 860 MB in + 860 MB out)"}
 
 
 def dist_env():
@@ -68,13 +80,40 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def csrc_hash() -> str:
+    """Identifies the kernel sources a profile was taken on (profiles/traffic.json records it)."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "video-3d-llm_b200", "csrc")
+    for fn in sorted(os.listdir(d)) + ["../../include/v3d.h"]:
+        with open(os.path.join(d, fn), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic():
-    """dram bytes per launch of the fused kernel from the committed ncu capture, if any."""
+    """dram bytes per launch of the fused kernel from the committed ncu capture -- only if that capture was taken on the
+    kernel sources being run (profiles/traffic.json holds their hash), else None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(p):
         with open(p) as f:
-            return json.load(f).get("k_fused_dram_bytes_per_launch")
+            d = json.load(f)
+        if d.get("csrc_hash") == csrc_hash():
+            return d.get("k_fused_dram_bytes_per_launch")
     return None
+
+
+def pin_cores(local: int, n_local: int) -> list:
+    """Give each rank of the node its own slice of the cores this process may run on (the GPUs of the pool's boxes all
+    report the same CPU affinity / NUMA node, so ranks would otherwise pile their loader threads onto the same cores),
+    before any pinned buffer is allocated.  Returns the cores."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(1, n_local))
+        mine = cores[local * per:(local + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return mine
+    except (AttributeError, OSError):
+        return list(range(os.cpu_count() or 1))
 
 
 class ClockSampler:
@@ -128,6 +167,8 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+
+
 # ---------------------------------------------------------------------------------------------
 # CPU legs
 # ---------------------------------------------------------------------------------------------
@@ -137,7 +178,7 @@ def cpu_reference_leg(steps: int, warmup: int, with_boundary: bool = False):
     from oracle import torch_port as TP
     from video_3d_llm_b200 import synthetic
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     sc = synthetic.make_scene(100, FRAMES, n_total=300, device="cpu")
     depth = torch.from_numpy(sc.depth_u16().astype(np.int32))  # the reference holds int32 depth (video_utils.py:217)
     tokens = synthetic.make_tokens(100, FRAMES, GRID * GRID, EMB)
@@ -150,7 +191,10 @@ def cpu_reference_leg(steps: int, warmup: int, with_boundary: bool = False):
             times.append(dt)
     best, mean = min(times), sum(times) / len(times)
     return {"frames_per_s_best": FRAMES / best, "frames_per_s_mean": FRAMES / mean, "ms_per_step": mean * 1e3,
-            "cores": torch.get_num_threads(), "sample": f"1 scene x {FRAMES} frames per step, {steps} steps after {warmup} warm-up"}
+            "cores": torch.get_num_threads(),
+            "sample": f"1 scene x {FRAMES} frames per step ({steps} steps after {warmup} warm-up) of the {SCENES}-scene batch: the reference "
+                      "processes scenes one at a time; torch-CPU operator sequence of the reference, oracle/torch_port.py, pinned "
+                      "bit-exact on the reference's outputs"}
 
 
 def cpu_c_oracle_leg():
@@ -169,6 +213,48 @@ def cpu_c_oracle_leg():
     return {"value": FRAMES / best, "unit": "frames/s", "cores": O.num_threads(), "kind": "port (C/OpenMP oracle)"}
 
 
+MC_CAND, MC_SCENES = 150, 16
+
+
+def mc_cpu_leg(sample_frames: int = 12):
+    """CPU baselines of the MC metric: (1) the reference's loop AS WRITTEN (torch.unique(dim=0) per frame,
+    Python tuples and sets, max_coverage_sampling.py:39-104) on a bounded sample -- `sample_frames` candidate frames of
+    one 480x640 scene, ~1 s per frame -- extrapolated to the 150-candidate scene the GPU leg times; (2) a packed-key
+    host variant (int64 keys + np.unique + numpy greedy) and (3) the C/OpenMP oracle, both on the full 150-frame scene."""
+    from oracle import oracle as O
+    from oracle import torch_port as TP
+    from video_3d_llm_b200 import synthetic
+
+    torch.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    seed = 500
+    sc = synthetic.make_scene(seed, MC_CAND, n_total=300, frame_indices=np.arange(0, 300, 2), device="cpu")
+    pc = synthetic.mesh_voxels(sc.room, sc.boxes, seed)
+    d32 = torch.from_numpy(sc.depth_u16().astype(np.int32))
+    sel = np.linspace(0, MC_CAND - 1, sample_frames, dtype=int)
+    t0 = time.perf_counter()
+    *_, st = TP.mc_as_written(d32[sel], sc.poses[sel], sc.intrinsics[sel], pc, 0.1, seed)
+    t_sample = time.perf_counter() - t0
+    # voxelisation is linear in the frames; one greedy round scans every remaining frame, and the full scene runs 32 rounds
+    rounds = min(32, sample_frames)
+    est = st["voxelize_s"] * MC_CAND / sample_frames + st["greedy_s"] * (MC_CAND / sample_frames) * (32 / rounds)
+    t0 = time.perf_counter()
+    pk = TP.mc_packed_keys(d32, sc.poses, sc.intrinsics, pc, 0.1, seed)
+    t_packed = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    co = O.mc_sample_scene(sc.depth_u16(), sc.poses.numpy(), sc.intrinsics.numpy(), pc, 0.1, 32, seed)
+    t_c = time.perf_counter() - t0
+    assert list(co[0]) == list(pk[0]), "host MC variants disagree"
+    return {"value": 1.0 / est, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"reference loop as written (oracle/torch_port.py::mc_as_written) on {sample_frames} of the {MC_CAND} candidate frames "
+                      f"of one scene: {t_sample:.1f} s (voxelise+unique {st['voxelize_s']:.1f} s, greedy {st['greedy_s']:.2f} s); extrapolated to "
+                      f"{MC_CAND} frames / 32 rounds = {est:.0f} s per scene",
+            "seconds_per_scene_extrapolated": est,
+            "packed_keys": {"value": 1.0 / t_packed, "unit": "scenes/s", "seconds_per_scene": t_packed,
+                            "what": "int64 voxel keys + np.unique per frame + numpy greedy, full 150-frame scene (oracle/torch_port.py::mc_packed_keys)"},
+            "c_oracle": {"value": 1.0 / t_c, "unit": "scenes/s", "seconds_per_scene": t_c, "cores": O.num_threads(),
+                         "what": "C/OpenMP oracle (oracle/v3d_oracle.c), full 150-frame scene"}}
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -178,13 +264,19 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference path = torch-CPU operator sequence (oracle/torch_port.py, pinned bit-exact "
-                   "against the reference); the reference itself is Python and /root/reference does not travel to the GPU box"},
+        "dtype": "f32", "data": "synthetic", "config": dict(CONFIG),
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "notes": "reference path = torch-CPU operator sequence (oracle/torch_port.py, pinned bit-exact against the reference); the "
+                 "reference itself is Python and /root/reference does not travel to the GPU box",
     }
+    if not args.no_mc_cpu:
+        try:
+            line["mc"] = {"metric": "MC-sampled scenes/sec (voxelise + greedy max-coverage, 32 picks)", "cpu_baseline": mc_cpu_leg()}
+            line["mc"]["value"], line["mc"]["unit"] = line["mc"]["cpu_baseline"]["value"], "scenes/s"
+        except Exception as e:  # secondary object; never fails the arm
+            line["mc"] = {"error": repr(e)}
     emit(line)
 
 
@@ -203,16 +295,204 @@ def make_batch(rank: int, dev):
     return depth, poses, intr, tokens
 
 
+def timed(fn, reps: int, warm: int = 2):
+    """Average milliseconds of fn() over `reps` back-to-back calls on the current stream (CUDA events)."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def write_packed_dataset(root: str, depth, poses, intr, rank: int):
+    """The config-2 batch as packed scenes on disk (scene_pack.py, with the resampled stack) plus the minimal metadata a
+    VideoProcessor needs; returns (VideoProcessor(pack_dir, lazy=True), samples [(video_id, frame_files)])."""
+    from video_3d_llm_b200 import scene_pack
+    from video_3d_llm_b200 import video_utils as VU
+
+    for d in ("emb", "meta", "packs"):
+        os.makedirs(os.path.join(root, d), exist_ok=True)
+    infos = []
+    d_np = depth.cpu().numpy().view(np.uint16).reshape(SCENES, FRAMES, H, W)
+    p_np = poses.cpu().numpy().reshape(SCENES, FRAMES, 4, 4)
+    k_np = intr.cpu().numpy().reshape(SCENES, FRAMES, 4, 4)
+    for s in range(SCENES):
+        name = f"scene{1000 * rank + 100 + s:04d}_00"
+        scene_pack.write_pack(os.path.join(root, "packs", name + ".v3dpack"), [10 * i for i in range(FRAMES)], p_np[s], k_np[s, 0], d_np[s],
+                              resample=(384, "center_crop"))
+        infos.append({"sample_idx": f"scannet/{name}", "axis_align_matrix": np.eye(4).tolist(), "depth_cam2img": k_np[s, 0].tolist(),
+                      "images": [{"img_path": f"scannet/posed_images/{name}/{10 * i:05d}.jpg"} for i in range(FRAMES)]})
+    for split in ("train", "val", "test"):
+        with open(os.path.join(root, "emb", f"embodiedscan_infos_{split}.pkl"), "wb") as f:
+            pickle.dump({"data_list": infos if split == "train" else []}, f)
+    for fn in ("scannet_train_gt_box.json", "scannet_val_pred_box.json"):
+        with open(os.path.join(root, "meta", fn), "w") as f:
+            json.dump({i["sample_idx"]: [[0.0, 0.0, 0.5, 1.0, 1.0, 1.0]] for i in infos}, f)
+    vp = VU.VideoProcessor(video_folder=root, annotation_dir=os.path.join(root, "emb"), voxel_size=0.1, min_xyz_range=[-15, -15, -5],
+                           max_xyz_range=[15, 15, 5], frame_sampling_strategy="uniform", metadata_dir=os.path.join(root, "meta"),
+                           pack_dir=os.path.join(root, "packs"), lazy=True)
+    samples = [(i["sample_idx"], vp.sample_frame_files(i["sample_idx"], force_sample=True, frames_upbound=FRAMES)) for i in infos]
+    return vp, samples
+
+
+def reference_call_sequence(scene, tokens, pe_module, patch):
+    """What prepare_inputs_labels_for_multimodal does per scene (llava_arch.py:396, 416, 510-515) on the overlay's helpers."""
+    from video_3d_llm_b200 import cabi
+    from video_3d_llm_b200 import coords as C
+
+    c = C.average_coordinate_in_patch(scene, patch_size=patch)
+    d = C.discrete_coords(c, None, voxel_size=0.1, min_xyz_range=[-15, -15, -5], max_xyz_range=[15, 15, 5], div_mode=cabi.div_mode_default())
+    return tokens + pe_module(d.flatten(1, 2).detach())
+
+
+def e2e_leg(rank, world, dev, vp, samples, tokens, steps: int, batch_scenes: int, threads: int):
+    """End to end through the public API, host work inside the timed loop (see the module docstring).  Returns
+    (frames/s over all ranks, h2d bytes, d2h bytes, note)."""
+    import torch.distributed as dist
+
+    from video_3d_llm_b200 import video_utils as VU
+    from video_3d_llm_b200.position_encoding import PositionEmbeddingSine3D
+
+    pe = PositionEmbeddingSine3D(EMB)
+    pe.defer_add = True
+    loader = VU.SceneBatchLoader(vp, samples, batch_scenes=batch_scenes, threads=threads, prefetch=2, loop=True)
+    it = iter(loader)
+    up = torch.cuda.Stream(device=dev)
+    cur = torch.cuda.current_stream(dev)
+    tok = tokens.view(SCENES, FRAMES, GRID * GRID, EMB)
+    probe = torch.empty((batch_scenes, FRAMES, 64), dtype=torch.bfloat16, device=dev)
+    h_probe = [torch.empty(probe.shape, dtype=probe.dtype).pin_memory() for _ in range(2)]
+    read = [None, None]
+
+    def upload():
+        h = next(it)  # blocks until the loader threads have filled this batch's pinned buffers
+        with torch.cuda.stream(up):
+            hd = h.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(up)
+        return hd, ev
+
+    def step(i, cur_batch):
+        hd, ev = cur_batch
+        nxt = upload()  # the H2D of step i+1 overlaps the kernels of step i
+        cur.wait_event(ev)
+        for b, scene in enumerate(hd):
+            out = reference_call_sequence(scene, tok[b % SCENES], pe, PATCH)
+            probe[b].copy_(out[:, 0, :64])
+        for t in (hd.depth, hd.poses, hd.intrinsics):
+            t.record_stream(cur)
+        h_probe[i % 2].copy_(probe, non_blocking=True)
+        read[i % 2] = torch.cuda.Event()
+        read[i % 2].record(cur)
+        if read[(i + 1) % 2] is not None:
+            read[(i + 1) % 2].synchronize()  # the host holds the result of step i-1: one step in flight
+        return nxt
+
+    batch = upload()
+    for i in range(2):
+        batch = step(i, batch)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        batch = step(i, batch)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    loader.close()
+    te = torch.tensor([dt], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    n_frames = batch_scenes * FRAMES
+    hd = batch[0]
+    h2d = hd.depth.numel() * hd.depth.element_size() + hd.poses.numel() * 4 + hd.intrinsics.numel() * 4
+    return world * n_frames * steps / float(te.item()), int(h2d), int(probe.numel() * 2), float(te.item()) / steps * 1e3
+
+
+def overlay_leg(dev, depth, poses, intr, tokens):
+    """Device-resident cost of the call sequence the unchanged scripts execute under the overlay, per
+    BASELINE config and grid geometry: lazy handle -> helpers -> `tokens + PE` per scene, exactly as
+    prepare_inputs_labels_for_multimodal iterates the batch."""
+    from video_3d_llm_b200 import projector_tail as PT
+    from video_3d_llm_b200 import video_utils as VU
+    from video_3d_llm_b200.lazy import LazyTokenPool
+    from video_3d_llm_b200.position_encoding import PositionEmbeddingSine3D
+
+    peak = measured_peaks()[0]
+    out = {}
+    d5 = depth.view(SCENES, FRAMES, H, W)
+    handle = VU.LazyWorldCoords(d5, poses.view(SCENES, FRAMES, 4, 4), intr.view(SCENES, FRAMES, 4, 4), batched=True).to(torch.bfloat16)
+    # (a) BASELINE geometry: 27x27 grid of 14-pixel windows, E=1152, un-pooled tokens -> ONE v3d_frontend_pe launch per scene
+    pe = PositionEmbeddingSine3D(EMB)
+    pe.defer_add = True
+    tok = tokens.view(SCENES, FRAMES, GRID * GRID, EMB)
+    # (b) default recipe: 14x14 grid of 27-pixel windows, E=3584, projector output on the 27x27 grid -> coordinates launch +
+    #     pool + PE + newline launch per scene
+    E2 = 3584
+    pe2 = PositionEmbeddingSine3D(E2)
+    pe2.defer_add = True
+    n_sets = 4  # config 1 touches ~0.1 GB per launch: rotate buffer sets so that HBM, not the 126 MB L2, is exercised
+    tok2 = torch.randn((n_sets, FRAMES, 729, E2), device=dev, dtype=torch.float32).to(torch.bfloat16)
+    newline = torch.randn(E2, device=dev).to(torch.bfloat16)
+    scenes = list(handle)
+
+    def seq_a(b):
+        return reference_call_sequence(scenes[b], tok[b], pe, PATCH)
+
+    def seq_b(b, t):
+        pooled = LazyTokenPool(t, 2, "bilinear")                       # get_2dPool under the overlay (:469)
+        feat = reference_call_sequence(scenes[b], pooled, pe2, 27)     # :396, :416, :515
+        return feat.finish(newline)                                    # add_token_per_grid (:536)
+
+    bytes_a = BYTES_PER_FRAME_FUSED_ADD * FRAMES
+    bytes_b = (BYTES_IN_PER_FRAME + 729 * E2 * 2 + 14 * 15 * E2 * 2) * FRAMES
+    for name, n_scenes in (("config1", 1), ("config2", SCENES)):
+        k = [0]
+
+        def run_a():
+            for b in range(n_scenes):
+                seq_a((k[0] + b) % SCENES)
+            k[0] += n_scenes
+
+        def run_b():
+            for b in range(n_scenes):
+                seq_b((k[0] + b) % SCENES, tok2[(k[0] + b) % n_sets])
+            k[0] += n_scenes
+
+        reps = 40 if n_scenes == 1 else 6
+        ms_a, ms_b = timed(run_a, reps), timed(run_b, reps)
+        out[name] = {
+            "scenes": n_scenes, "frames": n_scenes * FRAMES,
+            "grid27_E1152_unpooled": {"launches_per_scene": ["v3d_frontend_pe(tokens_in)"], "ms": ms_a, "frames_per_s": n_scenes * FRAMES / ms_a * 1e3,
+                                      "hbm_gbs": bytes_a * n_scenes / ms_a / 1e6, "frac_of_measured_hbm_peak": bytes_a * n_scenes / ms_a / 1e6 / peak},
+            "grid14_E3584_default_recipe": {"launches_per_scene": ["v3d_frontend_pe(pe off)", "v3d_pool_pe_grid"], "ms": ms_b,
+                                            "frames_per_s": n_scenes * FRAMES / ms_b * 1e3, "hbm_gbs": bytes_b * n_scenes / ms_b / 1e6,
+                                            "frac_of_measured_hbm_peak": bytes_b * n_scenes / ms_b / 1e6 / peak,
+                                            "algorithmic_bytes_per_frame": bytes_b // FRAMES},
+        }
+    out["note"] = ("CUDA-event time of the Python call sequence (helpers -> deferred handles -> fused launches), launch overhead "
+                   "included; config1 rotates 4 token buffer sets / 16 depth scenes so that inputs come from HBM")
+    del tok2
+    return out
+
+
 def mc_leg(rank: int, world: int, dev, steps: int, warmup: int):
     """Secondary metric: MC-sampled scenes/s (BASELINE configs[2]): 300-frame scenes -> 150 candidate
-    frames, 0.1 m voxels, 32 picks; voxelise + greedy, plus the all-gather of the 272-byte records."""
+    frames, 0.1 m voxels, 32 picks; voxelise + greedy, plus the all-gather of the 272-byte records.
+    Returns (result dict, scenes, sampler, plan) -- the scenes are reused by the config-4 leg."""
     import torch.distributed as dist
 
     from video_3d_llm_b200 import synthetic
     from video_3d_llm_b200.mc_sampling import MCSampler
     from video_3d_llm_b200 import sharding
 
-    n_scenes, cand = 16, 150
+    n_scenes, cand = MC_SCENES, MC_CAND
     scenes = []
     for s in range(n_scenes):
         seed = 1000 * rank + 500 + s
@@ -250,35 +530,147 @@ def mc_leg(rank: int, world: int, dev, steps: int, warmup: int):
     ms = float(t.item())
     depth_bytes = sum(s["depth"].numel() * 2 + s["depth"].shape[0] * 80 + s["pc_voxels"].numel() * 4 + 272 for s in scenes)
     res = sampler.decode(rec)
-    # the same with the candidate frames coming from pinned host memory each step (reported separately: SURVEY 8d)
-    e2e = None
-    if world == 1:
-        h_depth = [s["depth"].cpu().pin_memory() for s in scenes]
-        for _ in range(2):
-            for s, h in zip(scenes, h_depth):
-                s["depth"].copy_(h, non_blocking=True)
-            sampler.decode(sampler.run(plan))
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n_e2e = 3
-        for _ in range(n_e2e):
-            for s, h in zip(scenes, h_depth):
-                s["depth"].copy_(h, non_blocking=True)
-            sampler.decode(sampler.run(plan))  # records read back to the host
-        e2e_s = time.perf_counter() - t0
-        e2e = {"value": n_scenes * n_e2e / e2e_s, "unit": "scenes/s", "h2d_bytes_per_step": int(sum(h.numel() * 2 for h in h_depth)),
-               "d2h_bytes_per_step": int(rec.numel() * 4),
-               "note": "all 150 candidate frames of every scene uploaded in full each step (92 MB per scene): PCIe-bound"}
-        del h_depth
-    return {
+    # the same with the candidate frames coming from pinned host memory each step (reported separately: SURVEY 8d), every N
+    h_depth = [s["depth"].cpu().pin_memory() for s in scenes]
+
+    def e2e_step():
+        for s, h in zip(scenes, h_depth):
+            s["depth"].copy_(h, non_blocking=True)
+        return sampler.decode(sharding.all_gather_records(sampler.run(plan)))  # records gathered and read back to the host
+
+    for _ in range(2):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n_e2e = 3
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    te = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    e2e = {"value": world * n_scenes * n_e2e / float(te.item()), "unit": "scenes/s", "h2d_bytes_per_step": int(sum(h.numel() * 2 for h in h_depth)),
+           "d2h_bytes_per_step": int(allrec.numel() * 4),
+           "note": "all 150 candidate frames of every scene uploaded in full each step (92 MB per scene): PCIe-bound"}
+    del h_depth
+    out = {
         "metric": "MC-sampled scenes/sec (voxelise + greedy max-coverage, 32 picks)", "value": world * n_scenes * steps / (ms / 1e3),
         "unit": "scenes/s", "ms_per_step": ms / steps, "scenes_per_rank": n_scenes, "candidate_frames": cand, "voxel_size": 0.1,
         "voxelize_ms": ev[0].elapsed_time(ev[1]), "greedy_ms": ev[1].elapsed_time(ev[2]),
         "algorithmic_bytes_per_step": depth_bytes,
         "hbm_gbs_achieved_voxelize": depth_bytes / (ev[0].elapsed_time(ev[1]) / 1e3) / 1e9,
+        "frac_of_measured_hbm_peak_voxelize": depth_bytes / (ev[0].elapsed_time(ev[1]) / 1e3) / 1e9 / measured_peaks()[0],
         "e2e": e2e, "allgather_bytes": int(allrec.numel() * 4), "mean_picks": float(np.mean([len(r["order"]) for r in res])),
         "mean_coverage": float(np.mean([r["n_sel"] / max(r["n_all"], 1) for r in res])),
     }
+    return out, scenes, sampler, plan
+
+
+CONFIG4_SCENES = 256
+
+
+def config4_leg(rank: int, world: int, dev, scenes, sampler, plan):
+    """BASELINE configs[3] as written: 256 scenes, mc-ratio95 (voxelise + greedy + coverage-ratio cut) AND the sin-3D PE of
+    the selected frames, scenes sharded round-robin over the ranks (sharding.shard_indices), ONE all-gather of the per-scene
+    records at the end; strong scaling (the 256 scenes are fixed, every rank owns 256 / N of them).  The 256 scene slots
+    cycle through the 16 distinct 150-candidate scenes this rank generated for the MC leg (scene s uses the data of slot
+    s mod 16: 1.5 GB of depth per pass, far beyond L2); PE on the reference-default grid (14x14 windows of 27 pixels, E=3584)."""
+    import torch.distributed as dist
+
+    from video_3d_llm_b200 import sharding
+    from video_3d_llm_b200.frontend import FrontEnd
+
+    mine = sharding.shard_indices(CONFIG4_SCENES, rank, world)
+    fe = FrontEnd(device=dev, patch_size=27, embedding_size=3584)
+    pe_buf = torch.empty((len(scenes) * 32, 196, 3584), dtype=torch.bfloat16, device=dev)  # at most 32 frames per scene
+    local = torch.empty((len(mine), plan["records"].shape[1]), dtype=torch.int32, device=dev)
+    n_pass = (len(mine) + len(scenes) - 1) // len(scenes)
+
+    def run_all():
+        n_sel = 0
+        for p in range(n_pass):
+            rec, picks, pe = sampler.sample_and_encode(plan, fe, "mc-ratio95", 32, out=None)
+            lo, hi = p * len(scenes), min((p + 1) * len(scenes), len(mine))
+            local[lo:hi] = rec[: hi - lo]
+            n_sel += sum(len(x) for x in picks[: hi - lo])
+        return sharding.all_gather_records(local, CONFIG4_SCENES), n_sel
+
+    run_all()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    allrec, n_sel = run_all()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    ns = torch.tensor([n_sel], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ns)
+        dist.barrier()
+    ms = float(t.item())
+    del pe_buf
+    return {"workload": "256 scenes x 150 candidate frames, mc-ratio95 + sin-3D PE (14x14 grid, E=3584) of the selected frames, scene-sharded, "
+                        "one all-gather of the records (BASELINE configs[3])",
+            "scenes": CONFIG4_SCENES, "scenes_per_rank": len(mine), "distinct_scenes_per_rank": len(scenes), "scaling": "strong",
+            "ms": ms, "value": CONFIG4_SCENES / (ms / 1e3), "unit": "scenes/s", "selected_frames_total": int(ns.item()),
+            "mean_selected_frames_per_scene": float(ns.item()) / CONFIG4_SCENES, "records_gathered": list(allrec.shape),
+            "allgather_bytes": int(allrec.numel() * 4)}
+
+
+def host_limits_leg(rank: int, world: int, dev, threads: int):
+    """The two host-side ceilings of `e2e`, measured with every rank of the node active at the same time: pinned H2D
+    bandwidth per rank, and the loader's page-cache -> pinned-memory copy bandwidth with `threads` threads."""
+    import concurrent.futures as cf
+
+    import torch.distributed as dist
+
+    n = 256 << 20
+    src = torch.empty(n, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(n, dtype=torch.uint8, device=dev)
+    dst.copy_(src, non_blocking=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(4):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    h2d = 4 * n / (e0.elapsed_time(e1) / 1e3) / 1e9
+    # host copy: `threads` threads each copying slices of a 256 MB buffer into pinned memory (what SceneBatchLoader does)
+    a = np.ones(n, np.uint8)
+    b = src.numpy()
+    parts = [(i * n // threads, (i + 1) * n // threads) for i in range(threads)]
+
+    def cp(lo_hi):
+        b[lo_hi[0]:lo_hi[1]] = a[lo_hi[0]:lo_hi[1]]
+
+    with cf.ThreadPoolExecutor(threads) as ex:
+        list(ex.map(cp, parts))
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            list(ex.map(cp, parts))
+        memcpy = 3 * n / (time.perf_counter() - t0) / 1e9
+    vals = torch.tensor([h2d, memcpy], device=dev)
+    if world > 1:
+        mn = vals.clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        sm = vals.clone()
+        dist.all_reduce(sm)
+        dist.barrier()
+    else:
+        mn, sm = vals, vals
+    return {"h2d_pinned_gbs_per_rank_min": float(mn[0]), "h2d_pinned_gbs_sum": float(sm[0]), "loader_memcpy_gbs_per_rank_min": float(mn[1]),
+            "loader_memcpy_gbs_sum": float(sm[1]), "loader_threads_per_rank": threads, "ranks_active": world,
+            "note": "all ranks measure at the same time; e2e moves 151 MB per 512-frame step through both (page cache -> pinned, pinned -> HBM)"}
 
 
 def tail_leg(dev, n_frames: int = 512, steps: int = 10):
@@ -416,6 +808,9 @@ def run_ours(args):
     rank, world, local = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference for the CPU leg)")
+    n_local = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    cores = pin_cores(local, n_local)  # before any pinned allocation
+    threads = max(1, min(16, len(cores)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -464,72 +859,42 @@ def run_ours(args):
     ms = float(t.item())
     value = world * n_frames * K / (ms / 1e3)
 
-    # ---- end to end: host (pinned) depth/pose/intrinsics in, per-token voxel coordinates out ---
-    # pinned host inputs as the packed-scene loader emits them (ScenePack.load(resample=...)): the nearest-neighbour resize +
-    # crop of the reference's preprocess (video_utils.py:291-308) applied to the raw uint16 depth on the host -- per frame
-    # exactly the 378 x 378 samples the kernel reads (47 % of the frame), contiguous
-    h_depth, h_poses, h_intr = fe.pack_resampled(depth.cpu()), poses.cpu().pin_memory(), intr.cpu().pin_memory()
-    h_coords = [torch.empty((n_frames, GRID, GRID, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+    # ---- end to end through the public API, host work inside the timed loop -----------------------------------------
+    root = tempfile.mkdtemp(prefix=f"v3d_bench_r{rank}_", dir="/dev/shm" if os.path.isdir("/dev/shm") and args.packs_in_shm else None)
+    try:
+        vp, samples = write_packed_dataset(root, depth, poses, intr, rank)
+        Ke = max(3, min(K, 10))
+        e2e_value, h2d, d2h, e2e_ms = e2e_leg(rank, world, dev, vp, samples, tokens, Ke, SCENES, threads)
+        # BASELINE configs[0]: one 32-frame scene per step (what per_device_train_batch_size 1 launches), same path
+        c1_e2e, c1_h2d, c1_d2h, c1_ms = e2e_leg(rank, world, dev, vp, samples, tokens, 4 * Ke, 1, threads)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    limits = host_limits_leg(rank, world, dev, threads)
 
-    # The step is split into chunks so that the upload of chunk i+1 (copy stream) overlaps the scatter + kernel of chunk i,
-    # and the device buffers exist twice so that the uploads of step i+1 start while step i's last kernels and its result
-    # read-back are still running.  Every step copies its inputs from pinned host memory and reads its result back.
-    n_chunks = 8
-    bounds = [(i * n_frames // n_chunks, (i + 1) * n_frames // n_chunks) for i in range(n_chunks)]
-    up = torch.cuda.Stream(device=dev)
-    sets = [{"depth": torch.empty_like(depth), "poses": torch.empty_like(poses), "intr": torch.empty_like(intr),
-             "stage": torch.empty(h_depth.shape, dtype=h_depth.dtype, device=dev),
-             "coords": torch.empty((n_frames, GRID, GRID, 3), dtype=torch.float32, device=dev),
-             "free": None, "read": None} for _ in range(2)]
-    step_no = [0]
+    # ---- BASELINE configs[0] on the device: one scene per launch, rotating over the 16 scenes' buffers (HBM, not L2) --
+    k1 = [0]
 
-    def e2e_step():
-        cur = torch.cuda.current_stream(dev)
-        i = step_no[0]
-        step_no[0] += 1
-        S = sets[i % 2]
-        if S["read"] is not None:
-            S["read"].synchronize()  # the host has the result of step i-2 before its buffers are reused
-        events = []
-        with torch.cuda.stream(up):
-            if S["free"] is not None:
-                up.wait_event(S["free"])  # step i-2's kernels are done with this buffer set
-            S["poses"].copy_(h_poses, non_blocking=True)
-            S["intr"].copy_(h_intr, non_blocking=True)
-            for a, b in bounds:
-                S["stage"][a:b].copy_(h_depth[a:b], non_blocking=True)  # one contiguous DMA per chunk
-                ev = torch.cuda.Event()
-                ev.record(up)
-                events.append(ev)
-        for (a, b), ev in zip(bounds, events):
-            cur.wait_event(ev)
-            fe.scatter_resampled(S["stage"][a:b], S["depth"][a:b])  # back to the pixels the samples were taken from
-            _, _, pe_coords = fe(S["depth"][a:b], S["poses"][a:b], S["intr"][a:b], tokens=tokens[a:b], out=out[a:b], want_coords=True)
-            S["coords"][a:b].copy_(pe_coords)
-        S["free"] = torch.cuda.Event()
-        S["free"].record(cur)
-        h_coords[i % 2].copy_(S["coords"], non_blocking=True)
-        S["read"] = torch.cuda.Event()
-        S["read"].record(cur)
+    def one_scene():
+        b = k1[0] % SCENES
+        k1[0] += 1
+        a, e = b * FRAMES, (b + 1) * FRAMES
+        fe(depth[a:e], poses[a:e], intr[a:e], tokens=tokens[a:e], out=out[a:e])
 
-    for _ in range(2):
-        e2e_step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    Ke = max(3, min(K, 10))
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dist.barrier()
-    e2e_value = world * n_frames * Ke / float(te.item())
-    h2d = h_depth.numel() * h_depth.element_size() + h_poses.numel() * 4 + h_intr.numel() * 4
-    d2h = h_coords[0].numel() * 4
+    c1_dev_ms = timed(one_scene, 64, 8)
+    config1 = None
+    overlay = None
+    if rank == 0:
+        peak0 = measured_peaks()[0]
+        config1 = {"workload": f"1 scene x {FRAMES} frames per launch (BASELINE configs[0]), same kernel and geometry as the headline",
+                   "ms_per_launch": c1_dev_ms, "frames_per_s": FRAMES / c1_dev_ms * 1e3,
+                   "hbm_gbs": BYTES_PER_FRAME_FUSED_ADD * FRAMES / c1_dev_ms / 1e6,
+                   "frac_of_measured_hbm_peak": BYTES_PER_FRAME_FUSED_ADD * FRAMES / c1_dev_ms / 1e6 / peak0,
+                   "ctas": FRAMES * GRID, "e2e": {"value": c1_e2e, "unit": "frames/s", "ms_per_step": c1_ms, "h2d_bytes_per_step": c1_h2d,
+                                                  "d2h_bytes_per_step": c1_d2h}}
+        try:
+            overlay = overlay_leg(dev, depth, poses, intr, tokens)
+        except Exception as e:
+            overlay = {"error": repr(e)}
 
     # secondary: the reference's default recipe geometry (27-pixel windows -> 14x14 grid, E = 3584)
     recipe = None
@@ -537,22 +902,20 @@ def run_ours(args):
         fe2 = FrontEnd(device=dev, patch_size=27, embedding_size=3584)
         tok2 = torch.randn((n_frames, 196, 3584), device=dev, dtype=torch.float32).to(torch.bfloat16)
         out2 = torch.empty_like(tok2)
-        for _ in range(3):
-            fe2(depth, poses, intr, tokens=tok2, out=out2)
-        torch.cuda.synchronize()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        for _ in range(10):
-            fe2(depth, poses, intr, tokens=tok2, out=out2)
-        r1.record()
-        torch.cuda.synchronize()
-        rms = r0.elapsed_time(r1) / 10
+        rms = timed(lambda: fe2(depth, poses, intr, tokens=tok2, out=out2), 10, 3)
         rbytes = (BYTES_IN_PER_FRAME + 2 * 196 * 3584 * 2) * n_frames
         recipe = {"workload": "same depth batch, patch 27 -> 14x14 grid, E=3584, fused add (train_multi.sh:82-87 defaults)",
                   "ms": rms, "frames_per_s": n_frames / (rms / 1e3), "hbm_gbs": rbytes / rms / 1e6,
                   "frac_of_measured_hbm_peak": rbytes / rms / 1e6 / measured_peaks()[0]}
         del tok2, out2
-    mc = mc_leg(rank, world, dev, steps=max(2, min(K, 5)), warmup=1)
+    del out
+    mc, mc_scenes, mc_sampler, mc_plan = mc_leg(rank, world, dev, steps=max(2, min(K, 5)), warmup=1)
+    try:
+        c4 = config4_leg(rank, world, dev, mc_scenes, mc_sampler, mc_plan)
+    except Exception as e:
+        if world > 1:
+            raise
+        c4 = {"error": repr(e)}
     mlp = mlp_leg(dev, steps=5) if rank == 0 else None
     tail = None
     if rank == 0:
@@ -571,25 +934,32 @@ def run_ours(args):
         peak, peak_src = measured_peaks()
         kernel_s = (ms_local / 1e3) / K
         achieved = BYTES_PER_FRAME_FUSED_ADD * n_frames / kernel_s / 1e9
+        cfg = dict(CONFIG)
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_rank": n_frames, "patch": PATCH, "grid": GRID, "embedding": EMB,
-                       "pe_dtype": "bf16", "world_position_embedding_type": "avg-discrete-sin3d",
-                       "l2": "inputs larger than L2: one step touches 1.87 GB (depth 315 MB + tokens 860 MB in + 860 MB out)",
-                       "parallelism": f"scene-sharded x{world}, no data-path collective"},
+            "data": "synthetic", "config": cfg,
+            "parallelism": f"scene-sharded x{world}, no data-path collective", "host_cores_per_rank": len(cores),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "traffic": ncu_traffic(), "traffic_source": "profiles/traffic.json (ncu --set full of this kernel source hash), null if the sources changed since",
+                         "csrc_hash": csrc_hash(), "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": BYTES_PER_FRAME_FUSED_ADD * n_frames, "kernel": "k_fused",
                          "avg_launch_us": kernel_s * 1e6},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": Ke, "note": "pinned host depth as the packed-scene loader emits it (nearest resize + crop applied to the raw uint16 depth on the host: the 378x378 samples per frame the kernel reads; contiguous DMAs + device-side scatter into the frame layout)/pose/intrinsics -> device each step, device buffers double-buffered so that the uploads of the next step overlap the tail of the current one; vision tokens are produced on the "
-                    "device by the vision tower and stay resident; per-token voxel coordinates read back"},
-            "gpu_launches": K,  # timed region: K launches of k_fused (the e2e leg launches 4 per step, the mc leg 4 per step)
+                    "steps": Ke, "ms_per_step": e2e_ms, "loader_threads": threads,
+                    "note": "packed scenes (page cache) -> SceneBatchLoader threads copy the resampled depth of 16 scenes x 32 frames into "
+                            "pinned memory INSIDE the timed loop -> H2D on a copy stream -> per scene the reference's call sequence "
+                            "(average_coordinate_in_patch -> discrete_coords -> tokens + world_position_embedding) = one fused launch "
+                            "reading the resampled depth in place -> D2H of a result slice; one step in flight; vision tokens are "
+                            "produced on the device by the vision tower and stay resident"},
+            "gpu_launches": K,  # timed region: K launches of k_fused (e2e: 16 per step; mc: 4 per step)
             "clocks": clk,
+            "config1": config1,
+            "overlay_path": overlay,
+            "host_limits": limits,
             "default_recipe_geometry": recipe,
             "mc": mc,
+            "config4": c4,
             "mlp_pe": mlp,
             "projector_tail": tail,
             "host_ingest": ingest,
@@ -597,12 +967,16 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             r = cpu_reference_leg(steps=3, warmup=1)
             line["cpu_baseline"] = {"value": r["frames_per_s_mean"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
-                                    "sample": r["sample"] + " (torch-CPU operator sequence of the reference, oracle/torch_port.py)",
-                                    "best": r["frames_per_s_best"]}
+                                    "sample": r["sample"], "best": r["frames_per_s_best"]}
             try:
                 line["cpu_baseline_c_oracle"] = cpu_c_oracle_leg()
             except Exception as e:  # the C oracle is optional for the bench
                 line["cpu_baseline_c_oracle"] = {"error": str(e)}
+            if not args.no_mc_cpu:
+                try:
+                    line["mc"]["cpu_baseline"] = mc_cpu_leg()
+                except Exception as e:
+                    line["mc"]["cpu_baseline"] = {"error": repr(e)}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -628,7 +1002,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-mc-cpu", action="store_true", help="skip the CPU baseline of the MC metric (~30 s)")
+    ap.add_argument("--packs-in-shm", action="store_true", help="write the e2e leg's packed scenes to /dev/shm instead of the temp dir")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

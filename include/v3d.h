@@ -95,6 +95,12 @@ int v3d_expand_depth_window(const void* packed_dev, void* depth_dev, size_t pitc
 int v3d_scatter_resampled_depth(const void* packed_dev, void* depth_dev, int depth_dtype, int V, int H, int W, const int32_t* row_map,
                                 const int32_t* col_map, int out_h, int out_w, v3d_stream_t stream);
 
+/* Loader helper, HOST memory only (no device work, `stream` not involved): copy n_blocks blocks of bytes_each bytes from
+ * src_host[i] to dst_host + i*bytes_each on up to n_threads native threads -- the frames of a batch from the page cache
+ * (packed scenes, scene_pack.py) into one pinned buffer in a single call.  Replaces the per-frame `Image.open` / `np.array`
+ * loop of llava/video_utils.py:212-218 on the packed-scene path. */
+int v3d_host_gather(void* dst_host, const void* const* src_host, size_t bytes_each, int n_blocks, int n_threads);
+
 /* ---- helpers on materialised coordinates (API parity with the reference's call structure) --
  * v3d_pool_coords replaces llava/model/llava_arch.py:213-223 `average_coordinate_in_patch`,
  * :225-239 `minmax_coordinate_in_patch`, :241-257 `sample_n_points`.

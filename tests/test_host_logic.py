@@ -127,3 +127,26 @@ def test_lazy_preprocess_and_merge_without_touching_cuda(dataset, D):
     d2 = dict(d)
     d2["box_input"] = [1.0, 2.0, 3.0]
     assert VU.merge_video_dict([d2])["box_input"].shape == (1, 3)
+
+
+def test_mc_ratio_cut_matches_the_reference_prefix_rule():
+    """mc_sampling.ratio_cut (candidate indices) against the oracle's restatement of sample_frame_files_mc
+    (llava/video_utils.py:131-159) on file names, incl. exact-threshold and no-cut cases."""
+    from oracle import oracle as O
+    from video_3d_llm_b200 import mc_sampling
+
+    rng = np.random.default_rng(5)
+    for trial in range(50):
+        n = int(rng.integers(1, 33))
+        order = rng.permutation(150)[:n].tolist()
+        gains = sorted(rng.integers(0, 400, n).tolist(), reverse=True)
+        n_all = int(sum(gains) + rng.integers(0, 50))
+        if trial % 7 == 0:
+            n_all = int(round(sum(gains[: max(1, n // 2)]) / 0.95))  # lands on / next to the threshold
+        rec = {"order": order, "gains": gains, "n_all": n_all, "n_sel": sum(gains)}
+        files = [f"data/scannet/posed_images/s/{10 * f:05d}.jpg" for f in order]
+        for strategy in ("mc-ratio95", "mc-ratio90-norm", "mc", "mc-online-ratio95"):
+            for ub in (32, 8, 3):
+                got = mc_sampling.ratio_cut(rec, strategy, ub)
+                ref = O.mc_prefix_cut(files, gains, n_all, strategy, ub)
+                assert [f"data/scannet/posed_images/s/{10 * f:05d}.jpg" for f in got] == ref

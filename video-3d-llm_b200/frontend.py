@@ -66,6 +66,18 @@ class FrontEnd:
             if self.flags["discrete"]:
                 rows = 1 + max(int(round((hi - lo) / cfg.voxel_size)) for lo, hi in zip(cfg.min_xyz_range, cfg.max_xyz_range))
             self.tables = get_tables(cfg.embedding_size, self.n_points, cfg.temperature, cfg.dtype, self.device, max(rows, 2))
+        d = cabi.FrontendDesc()
+        d.depth_scale = cfg.depth_scale
+        d.row_map, d.col_map = self.row_map.data_ptr(), self.col_map.data_ptr()
+        d.src_col_min, d.src_col_max = self.src_col_min, self.src_col_max
+        d.patch, d.grid, d.pool_mode = cfg.patch_size, cfg.grid, _POOL[self.flags["pool"]]
+        d.discrete = int(self.flags["discrete"])
+        d.min_xyz, d.max_xyz = cabi.float3(cfg.min_xyz_range), cabi.float3(cfg.max_xyz_range)
+        d.voxel_size, d.div_mode = cfg.voxel_size, cfg.div_mode
+        if self.tables is not None:
+            d.pe_mode, d.E, d.dtype = cabi.PE_SINE3D, cfg.embedding_size, cabi.dtype_code(cfg.dtype)
+            d.dim_t, d.table, d.table_rows = self.tables.dim_t.data_ptr(), self.tables.table.data_ptr(), self.tables.rows
+        self._desc0 = bytes(d)
 
     @property
     def tokens_per_frame(self) -> int:
@@ -206,8 +218,9 @@ class FrontEnd:
         pe=False: stop after the coordinates (pooling + discretisation only), whatever the configured PE.
         Returns the PE (or tokens + PE) as (V, G*G, E); with want_coords also (pooled, pe_coords)."""
         cfg = self.cfg
-        for name, t in (("depth", depth), ("poses", poses), ("intrinsics", intrinsics)):
-            cabi.require_cuda(t, name)
+        if not (depth.is_cuda and poses.is_cuda and intrinsics.is_cuda):
+            for name, t in (("depth", depth), ("poses", poses), ("intrinsics", intrinsics)):
+                cabi.require_cuda(t, name)
         V, H, W = depth.shape
         if resampled:
             n = cfg.grid * cfg.patch_size
@@ -215,21 +228,19 @@ class FrontEnd:
                 raise ValueError(f"resampled depth is {H}x{W}, the {cfg.grid}x{cfg.grid} grid of {cfg.patch_size}-pixel patches needs {n}x{n}")
         elif (H, W) != (cfg.H, cfg.W):
             raise ValueError(f"depth is {H}x{W}, front end was configured for {cfg.H}x{cfg.W}")
-        depth = depth.contiguous()
-        poses = poses.to(torch.float32).contiguous()
-        intrinsics = intrinsics.to(torch.float32).contiguous()
+        if not depth.is_contiguous():
+            depth = depth.contiguous()
+        if poses.dtype != torch.float32 or not poses.is_contiguous():
+            poses = poses.to(torch.float32).contiguous()
+        if intrinsics.dtype != torch.float32 or not intrinsics.is_contiguous():
+            intrinsics = intrinsics.to(torch.float32).contiguous()
         G, E = cfg.grid, cfg.embedding_size
-        d = cabi.FrontendDesc()
+        # the per-configuration fields are filled once (self._desc0); a call copies the struct and sets what changes
+        d = cabi.FrontendDesc.from_buffer_copy(self._desc0)
         d.depth, d.depth_dtype, d.poses, d.intr = depth.data_ptr(), cabi.depth_code(depth), poses.data_ptr(), intrinsics.data_ptr()
-        d.n_frames, d.H, d.W, d.depth_scale = V, H, W, cfg.depth_scale
-        d.row_map, d.col_map = self.row_map.data_ptr(), self.col_map.data_ptr()
-        d.src_col_min, d.src_col_max = self.src_col_min, self.src_col_max
-        d.patch, d.grid, d.pool_mode = cfg.patch_size, G, _POOL[self.flags["pool"]]
+        d.n_frames, d.H, d.W = V, H, W
         if clamp is not None:
             d.has_clamp, d.clamp_lo, d.clamp_hi = 1, cabi.float3(clamp[0]), cabi.float3(clamp[1])
-        d.discrete = int(self.flags["discrete"])
-        d.min_xyz, d.max_xyz = cabi.float3(cfg.min_xyz_range), cabi.float3(cfg.max_xyz_range)
-        d.voxel_size, d.div_mode = cfg.voxel_size, cfg.div_mode
         d.depth_resampled, d.coord_dtype = int(bool(resampled)), cabi.dtype_code(coord_dtype)
         pooled = pe_coords = None
         use_pe = pe and self.flags["sin3d"]
@@ -246,10 +257,10 @@ class FrontEnd:
             if tokens is not None:
                 if tokens.shape != out.shape or tokens.dtype != cfg.dtype:
                     raise ValueError(f"tokens must be {tuple(out.shape)} {cfg.dtype}, got {tuple(tokens.shape)} {tokens.dtype}")
-                tokens = tokens.contiguous()
-            d.pe_mode, d.E, d.dtype = cabi.PE_SINE3D, E, cabi.dtype_code(cfg.dtype)
-            d.dim_t, d.table, d.table_rows = self.tables.dim_t.data_ptr(), self.tables.table.data_ptr(), self.tables.rows
-            d.tokens_in, d.pe_out = cabi.ptr(tokens), out.data_ptr()
+                if not tokens.is_contiguous():
+                    tokens = tokens.contiguous()
+                d.tokens_in = tokens.data_ptr()
+            d.pe_out = out.data_ptr()
         else:
             d.pe_mode = cabi.PE_NONE
         with torch.cuda.device(self.device):

@@ -151,8 +151,8 @@ class LazyPooled(DeferredTensor):
         kind = self.mode + ("-discrete" if self.disc is not None else "") + ("-sin3d" if embedding_size else "")
         disc = self.disc or dict(voxel_size=0.1, min_xyz_range=(-15.0, -15.0, -5.0), max_xyz_range=(15.0, 15.0, 5.0), div_mode=cabi.DIV_IEEE)
         H, W = h.src_hw
-        key = (H, W, h.crop_size, h.strategy, self.patch_size, self.trim, kind, embedding_size, float(temperature), out_dtype,
-               disc["voxel_size"], disc["min_xyz_range"], disc["max_xyz_range"], disc["div_mode"], str(device), _pe._dim_t_source)
+        key = (H, W, h.crop_size, h.strategy, self.patch_size, self.trim, kind, embedding_size, temperature, out_dtype,
+               disc["voxel_size"], disc["min_xyz_range"], disc["max_xyz_range"], disc["div_mode"], device, _pe._dim_t_source)
         fe = _frontends.get(key)
         if fe is None:
             fe = FrontEnd(device=device, H=H, W=W, crop_size=h.crop_size, strategy=h.strategy, patch_size=self.patch_size, trim=self.trim,
@@ -178,7 +178,11 @@ class LazyPooled(DeferredTensor):
             dev = _device_for(self.handle.depth)
             fe = self.frontend(dev)
             depth, poses, intr, clamp, resampled = self.inputs(dev)
-            pooled, pe_coords = torch.ops.v3d.frontend_coords(depth, poses, intr, ops.frontend_key(fe), clamp, self.dtype, resampled)
+            if _dispatch():
+                pooled, pe_coords = torch.ops.v3d.frontend_coords(depth, poses, intr, ops.frontend_key(fe), clamp, self.dtype, resampled)
+            else:
+                _, pooled, pe_coords = fe(depth, poses, intr, clamp=ops._clamp_arg(clamp), want_coords=True, resampled=resampled,
+                                          coord_dtype=self.dtype, pe=False)
             val = (pe_coords if self.disc is not None else pooled).to(self.dtype)
             self._val = val.flatten(1, 2) if self.flat else val
         return self._val
@@ -186,6 +190,15 @@ class LazyPooled(DeferredTensor):
 
 _frontends: dict = {}
 _ADD_FUNCS = None
+
+
+def _dispatch(*tensors) -> bool:
+    """Route a launch through torch.ops.v3d.* (autograd formula, traceable node) or call the library directly?  The
+    dispatcher costs tens of microseconds per call, which is as much as the kernel itself for one 32-frame scene; it is
+    only needed when a gradient has to flow or the call is being traced."""
+    if torch.compiler.is_compiling():
+        return True
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
 def _add_funcs():
@@ -226,9 +239,13 @@ class LazyPE(DeferredTensor):
         if isinstance(c, LazyPooled):
             fe = c.frontend(device, m.embedding_size, m.temperature, out_dtype)
             depth, poses, intr, clamp, resampled = c.inputs(device)
-            return torch.ops.v3d.frontend_pe(depth, poses, intr, tokens, ops.frontend_key(fe), clamp, c.dtype, resampled)
+            if _dispatch(tokens):
+                return torch.ops.v3d.frontend_pe(depth, poses, intr, tokens, ops.frontend_key(fe), clamp, c.dtype, resampled)
+            return fe(depth, poses, intr, tokens=tokens, clamp=ops._clamp_arg(clamp), resampled=resampled, coord_dtype=c.dtype)
         x = c.reshape(c.shape[0], -1, 3)
-        return torch.ops.v3d.pe_sine3d(x, tokens, m.embedding_size, m.n_points, float(m.temperature), m.table_rows, out_dtype)
+        if _dispatch(tokens):
+            return torch.ops.v3d.pe_sine3d(x, tokens, m.embedding_size, m.n_points, float(m.temperature), m.table_rows, out_dtype)
+        return ops.pe_sine3d_impl(x, tokens, m.embedding_size, m.n_points, float(m.temperature), m.table_rows, out_dtype)
 
     def materialize(self) -> torch.Tensor:
         if self._val is None:

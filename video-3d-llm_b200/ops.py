@@ -87,9 +87,8 @@ def _(depth, poses, intrinsics, fe, clamp, coord_dtype, resampled):
 
 
 # ---- stand-alone sin-3D PE ----------------------------------------------------------------------------------------
-@torch.library.custom_op("v3d::pe_sine3d", mutates_args=())
-def pe_sine3d(coords: torch.Tensor, tokens: Optional[torch.Tensor], embedding_size: int, n_points: int, temperature: float,
-              table_rows: int, out_dtype: torch.dtype) -> torch.Tensor:
+def pe_sine3d_impl(coords: torch.Tensor, tokens: Optional[torch.Tensor], embedding_size: int, n_points: int, temperature: float,
+                   table_rows: int, out_dtype: torch.dtype) -> torch.Tensor:
     """coords (B, N*n_points, 3) any float dtype -> (B, N, E) in out_dtype (+ tokens)."""
     from .position_encoding import get_tables
 
@@ -108,6 +107,9 @@ def pe_sine3d(coords: torch.Tensor, tokens: Optional[torch.Tensor], embedding_si
                                      tabs.rows, cabi.dtype_code(out_dtype), cabi.ptr(tokens), out.data_ptr(),
                                      cabi.stream_ptr(coords.device)), "v3d_pe_sine3d")
     return out
+
+
+pe_sine3d = torch.library.custom_op("v3d::pe_sine3d", mutates_args=())(pe_sine3d_impl)
 
 
 @pe_sine3d.register_fake

@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import cabi
 from . import ops  # noqa: F401  (registers torch.ops.v3d.*)
-from .lazy import DeferredTensor, LazyPE, LazyPooled
+from .lazy import DeferredTensor, LazyPE, LazyPooled, _dispatch
 
 
 #: where dim_t is evaluated.  The reference builds it on x.device (position_encoding.py:24), i.e. with torch's CUDA pow
@@ -92,7 +92,9 @@ class PositionEmbeddingSine3D(nn.Module):
         out_dtype = x.dtype
         if add_to is not None and (add_to.dtype != out_dtype or tuple(add_to.shape) != (x.shape[0], x.shape[1] // self.n_points, self.embedding_size)):
             raise ValueError("add_to must have the output's shape and dtype")
-        return torch.ops.v3d.pe_sine3d(x, add_to, self.embedding_size, self.n_points, float(self.temperature), self.table_rows, out_dtype)
+        if _dispatch(add_to):
+            return torch.ops.v3d.pe_sine3d(x, add_to, self.embedding_size, self.n_points, float(self.temperature), self.table_rows, out_dtype)
+        return ops.pe_sine3d_impl(x, add_to, self.embedding_size, self.n_points, float(self.temperature), self.table_rows, out_dtype)
 
 
 class PositionEmbeddingMLP(nn.Module):

@@ -615,8 +615,8 @@ def merge_video_dict(video_dict_list):
 class SceneBatchLoader:
     """Background loader of `world_coords` batches for a list of samples: what a DataLoader with
     pin_memory=True and a collate of merge_video_dict produces, without the per-sample tensors and the stack copy --
-    worker THREADS (the copies release the GIL) read every scene's frames from its packed binary straight into a ring of
-    pinned batch buffers, `prefetch` batches ahead of the consumer.
+    every scene's frames go from its packed binary straight into a ring of pinned batch buffers, one native
+    multi-threaded gather per batch (v3d_host_gather), `prefetch` batches ahead of the consumer.
 
         loader = SceneBatchLoader(vp, samples, batch_scenes=16)        # samples: [(video_id, frame_files), ...]
         for handle in loader:                                          # batched LazyWorldCoords over pinned memory
@@ -651,30 +651,44 @@ class SceneBatchLoader:
         self._ring = [(torch.empty((self.B, self.V) + shape, dtype=store, pin_memory=pin),
                        torch.empty((self.B, self.V, 4, 4), dtype=torch.float32, pin_memory=pin),
                        torch.empty((self.B, self.V, 4, 4), dtype=torch.float32, pin_memory=pin)) for _ in range(self.prefetch + 1)]
-        self._pool = ThreadPoolExecutor(max_workers=max(1, int(threads)), thread_name_prefix="v3d-load")
+        # batches are assembled by `prefetch` Python threads, each issuing ONE native multi-threaded gather per batch
+        self._pool = ThreadPoolExecutor(max_workers=self.prefetch, thread_name_prefix="v3d-load")
+        self.threads = max(1, int(threads))
+        self._lib = cabi.load()
         self._do_norm = "norm" in vp.frame_sampling_strategy
 
     def __len__(self):
         return len(self.samples) // self.B
 
-    def _load_scene(self, slot: int, b: int, idx: int):
-        video_id = self.samples[idx][0]
-        pack = self.vp._pack(video_id)
-        if pack is None or (pack.H, pack.W) != self.src_hw or (pack.resampled_for == (self.crop_size, self.strategy)) != self.resampled:
-            raise ValueError(f"{video_id}: packed scene missing or of a different layout than the first sample's")
+    def _load_batch(self, batch: int, slot: int):
+        """Fill ring slot `slot` with batch `batch`: ONE native gather of every frame of every scene (v3d_host_gather, the
+        interpreter lock is released for its duration), poses / intrinsics with numpy.  Returns the per-scene clamps."""
+        import ctypes as C
+
         depth, poses, intr = self._ring[slot]
-        rows = pack.rows(self._frame_numbers[idx])
-        src = pack.resampled if self.resampled else pack.depth
-        dst = depth[b].numpy().view(pack.depth_dtype)
-        for o, r in enumerate(rows):
-            dst[o] = src[r]
-        poses[b].numpy()[...] = pack.poses[rows]
-        intr[b].numpy()[...] = pack.intr[None]
-        return self.vp._clamp_for(video_id, self._do_norm)
+        n = len(self.samples)
+        srcs = (C.c_void_p * (self.B * self.V))()
+        clamps = []
+        frame_bytes = depth[0, 0].numel() * depth.element_size()
+        for b in range(self.B):
+            idx = (batch * self.B + b) % n
+            video_id = self.samples[idx][0]
+            pack = self.vp._pack(video_id)
+            if pack is None or (pack.H, pack.W) != self.src_hw or (pack.resampled_for == (self.crop_size, self.strategy)) != self.resampled:
+                raise ValueError(f"{video_id}: packed scene missing or of a different layout than the first sample's")
+            rows = pack.rows(self._frame_numbers[idx])
+            src = pack.resampled if self.resampled else pack.depth
+            base = src.ctypes.data
+            for o, r in enumerate(rows):
+                srcs[b * self.V + o] = base + int(r) * frame_bytes
+            poses[b].numpy()[...] = pack.poses[rows]
+            intr[b].numpy()[...] = pack.intr[None]
+            clamps.append(self.vp._clamp_for(video_id, self._do_norm))
+        cabi.check(self._lib.v3d_host_gather(depth.data_ptr(), srcs, frame_bytes, self.B * self.V, self.threads), "v3d_host_gather")
+        return clamps
 
     def _submit(self, batch: int, slot: int):
-        n = len(self.samples)
-        return [self._pool.submit(self._load_scene, slot, b, (batch * self.B + b) % n) for b in range(self.B)]
+        return self._pool.submit(self._load_batch, batch, slot)
 
     def __iter__(self):
         n_batches = len(self)
@@ -689,8 +703,8 @@ class SceneBatchLoader:
                 nxt += 1
             if not pending:
                 return
-            slot, futs = pending.pop(0)
-            clamps = [f.result() for f in futs]
+            slot, fut = pending.pop(0)
+            clamps = fut.result()
             depth, poses, intr = self._ring[slot]
             yield LazyWorldCoords(depth, poses, intr, self.crop_size, self.strategy, None if all(c is None for c in clamps) else clamps,
                                   batched=True, resampled=self.resampled, src_hw=self.src_hw)
