@@ -189,6 +189,12 @@ typedef struct v3d_frontend_desc {
    * every pooled mean and every step of the discretisation is rounded to it, like ATen's element-wise kernels do.
    * V3D_F32 = the fp32 contract of the oracle.  NOTE: V3D_BF16 is 0 -- set this field explicitly. */
   int coord_dtype;
+  /* 0 (default): the recipe configuration (uint16 depth, avg pooling, discretised coordinates, table-backed PE added to
+   * bf16/fp16 tokens, no clamp, pooled_out == NULL) runs as a streaming kernel that forms every patch mean algebraically
+   * from exact integer sums over the window and accepts it only if a proven error band around it discretises to a single
+   * integer; coordinates inside the band are recomputed with the reference's operator sequence in the same launch.  The
+   * results are the same bit for bit either way; 1 forces the operator-sequence kernel everywhere (tests, profiling). */
+  int exact_pooling;
 } v3d_frontend_desc;
 
 int v3d_frontend_pe(const v3d_frontend_desc* desc, v3d_stream_t stream);

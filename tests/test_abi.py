@@ -65,7 +65,7 @@ int main(void) {
   F(v3d_frontend_desc, max_xyz); F(v3d_frontend_desc, voxel_size); F(v3d_frontend_desc, div_mode); F(v3d_frontend_desc, pe_mode);
   F(v3d_frontend_desc, E); F(v3d_frontend_desc, dim_t); F(v3d_frontend_desc, table); F(v3d_frontend_desc, table_rows);
   F(v3d_frontend_desc, dtype); F(v3d_frontend_desc, tokens_in); F(v3d_frontend_desc, pe_out); F(v3d_frontend_desc, pooled_out);
-  F(v3d_frontend_desc, pe_coords_out); F(v3d_frontend_desc, depth_resampled); F(v3d_frontend_desc, coord_dtype);
+  F(v3d_frontend_desc, pe_coords_out); F(v3d_frontend_desc, depth_resampled); F(v3d_frontend_desc, coord_dtype); F(v3d_frontend_desc, exact_pooling);
   printf("sizeof.v3d_mc_scene %zu\n", sizeof(v3d_mc_scene));
   F(v3d_mc_scene, depth); F(v3d_mc_scene, poses); F(v3d_mc_scene, intr); F(v3d_mc_scene, pc_voxels); F(v3d_mc_scene, n_frames);
   F(v3d_mc_scene, n_pc); F(v3d_mc_scene, seed); F(v3d_mc_scene, hash_table); F(v3d_mc_scene, hash_slots); F(v3d_mc_scene, bitsets);

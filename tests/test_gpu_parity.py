@@ -828,3 +828,50 @@ def test_object_features_match_reference(golden_dir):
     got2 = C.object_features(tok, m)
     ref2 = O.object_features(bf16_bits(tok).reshape(-1, 1152), m.cpu().numpy())
     assert_bf16_close(bf16_bits(got2), ref2, max_frac=5e-3)
+
+
+@pytest.mark.parametrize("patch,E", [(27, 3584), (14, 1152), (27, 1152)])
+def test_algebraic_patch_means_equal_the_operator_sequence(patch, E):
+    """The streaming kernel (k_fused_ring) forms patch means from exact integer sums and verifies them against a proven
+    error band (v3d_fused_ring.cu); coordinates inside the band, and frames whose camera does not qualify, are recomputed
+    with the reference's operator sequence in the same launch.  The result must be what the operator-sequence kernel
+    (k_fused, itself pinned on the oracle and the goldens) gives, bit for bit -- on ordinary scenes, far from the origin
+    (large |P_i3|: wide band), on walls that sit exactly on voxel boundaries (every coordinate inside the band), with
+    projective / NaN / huge cameras (nothing qualifies), with depth the loader already resampled, and in place."""
+    fe = FrontEnd(device=DEV, patch_size=patch, embedding_size=E)
+    fe_exact = FrontEnd(device=DEV, patch_size=patch, embedding_size=E)
+    fe_exact.exact_pooling = True
+    cases = 0
+    for seed, kind in ((31, None), (32, "far"), (33, "wall"), (34, "projective"), (35, "nan_pose"), (36, "huge_focal"), (37, "resampled")):
+        n_frames = 40 if kind is None else 7  # more patch rows than CTAs for one case, fewer for the others
+        sc = synthetic.make_scene(seed, n_frames, n_total=40, device=DEV)
+        poses, intr, depth = sc.poses.clone(), sc.intrinsics.clone(), sc.depth.clone()
+        if kind == "far":
+            poses[:, :3, 3] += torch.tensor((250.0, -180.0, 3.0), device=DEV)
+        elif kind == "wall":
+            # a fronto-parallel wall whose world z lands exactly on the half-voxel plane: camera looks down the world z axis
+            poses[:] = torch.eye(4, device=DEV)
+            poses[:, 2, 3] = 0.05
+            depth[:] = 2000
+        elif kind == "projective":
+            poses[1::2, 3, :] = torch.tensor((0.01, -0.02, 0.03, 1.5), device=DEV)
+        elif kind == "nan_pose":
+            poses[2, 1, 2] = float("nan")
+            poses[4, 0, 3] = float("inf")
+        elif kind == "huge_focal":
+            intr[3, 0, 0] = 3e30
+            intr[5, 1, 1] = 1e-30
+        tok = synthetic.make_tokens(seed, n_frames, fe.tokens_per_frame, E).to(DEV)
+        kw = {}
+        if kind == "resampled":
+            depth = fe.pack_resampled(depth.cpu(), pin=False).to(DEV)
+            kw = dict(resampled=True)
+        a = fe(depth, poses, intr, tokens=tok, **kw)
+        b = fe_exact(depth, poses, intr, tokens=tok, **kw)
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16)), (seed, kind)
+        if kind is None:
+            inplace = tok.clone()
+            fe(depth, poses, intr, tokens=inplace, out=inplace)
+            assert torch.equal(inplace.view(torch.int16), b.view(torch.int16))
+        cases += 1
+    assert cases == 7

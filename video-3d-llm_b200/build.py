@@ -58,14 +58,20 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
     os.makedirs(OUT_DIR, exist_ok=True)
     objs = []
     procs = []
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(os.path.dirname(HERE), "include", "v3d.h"), os.path.abspath(__file__)]
+    hdr_time = max(os.path.getmtime(h) for h in headers)
     for src in sources():
         obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + (("." + out) if out else "") + ".o")
+        objs.append(obj)
+        # objects are reused when neither their source nor any header changed (default flags only)
+        if not defines and not out and not verbose and os.environ.get("V3D_FORCE_BUILD", "0") != "1" and os.path.isfile(obj) \
+                and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr_time):
+            continue
         cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
     failed = False
     for src, p in procs:
         out, _ = p.communicate()

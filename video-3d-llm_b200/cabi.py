@@ -48,7 +48,7 @@ class FrontendDesc(C.Structure):
         ("pe_mode", C.c_int), ("E", C.c_int), ("dim_t", C.c_void_p), ("table", C.c_void_p), ("table_rows", C.c_int),
         ("dtype", C.c_int), ("tokens_in", C.c_void_p), ("pe_out", C.c_void_p),
         ("pooled_out", C.c_void_p), ("pe_coords_out", C.c_void_p),
-        ("depth_resampled", C.c_int), ("coord_dtype", C.c_int),
+        ("depth_resampled", C.c_int), ("coord_dtype", C.c_int), ("exact_pooling", C.c_int),
     ]
 
     def __init__(self, *a, **kw):

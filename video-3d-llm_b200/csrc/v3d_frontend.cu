@@ -10,6 +10,7 @@
 #include <type_traits>
 
 #include "v3d_common.cuh"
+#include "v3d_fused.cuh"
 #include "v3d_pe.cuh"
 
 namespace v3d {
@@ -653,37 +654,6 @@ __global__ void __launch_bounds__(kThreads) k_pe_sine3d(const float* __restrict_
 // ============================================================================================
 // 4. the fused kernel: one CTA per (frame, patch row)
 // ============================================================================================
-struct FusedParams {
-  const void* depth;
-  const float* poses;
-  const float* intr;
-  const float* coords_in;  // FROM_DEPTH == false: (V,S,S,3) materialised coordinates
-  int n_frames, H, W, S;
-  float depth_scale;
-  const int32_t* row_map;
-  const int32_t* col_map;
-  int patch, grid, Sp, Sp_pad;  // Sp = patch*grid columns/rows used
-  int pool_mode, n_points;
-  Clamp clamp;
-  Discretize disc;
-  int pe_mode;
-  PeGeom g;
-  const float* dim_t;
-  const void* table;
-  const void* tokens_in;
-  void* pe_out;
-  float* pooled_out;
-  float* pe_coords_out;
-  // TMA staging: bytes [col_lo_byte, col_lo_byte + span) of each needed depth row
-  int col_lo_byte, span;
-  // depth is already resampled: sample (r, c) of the (H, W) buffer belongs to dst pixel (r, c), whose source pixel
-  // coordinates (for u - cx, v - cy) are still (row_map[r], col_map[c])
-  int resampled;
-  // dtype of the coordinate tensor the reference would hold (bf16 under the HF Trainer, fp16 in the eval scripts): each
-  // unprojected (and clamped) coordinate and each pooled mean is rounded to it; V3D_F32 = the fp32 contract
-  int coord_dtype;
-};
-
 // xyz of one resampled row live in three planes of kPlane floats (x | y | z), double buffered.  The
 // plane stride is a compile-time constant so that the three stores of a pixel and the chain loads use
 // immediate offsets; 520 % 32 == 8 keeps the planes on different banks.
@@ -728,11 +698,6 @@ __device__ __forceinline__ float chain_add(float acc, const float* src, int P) {
   return acc;
 }
 
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-  uint32_t r;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(addr));
-  return r;
-}
 __device__ __forceinline__ void sts_xyz(uint32_t addr, float x, float y, float z) {
   asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+%4], %2;\n\tst.shared.f32 [%0+%5], %3;" ::"r"(addr), "f"(x), "f"(y),
                "f"(z), "n"(kPlane * 4), "n"(2 * kPlane * 4)
@@ -1521,6 +1486,8 @@ int v3d_frontend_pe(const v3d_frontend_desc* d, v3d_stream_t stream) {
     p.span = hi - lo;
   }
   cudaStream_t s = (cudaStream_t)stream;
+  // the recipe configuration streams through k_fused_ring (v3d_fused_ring.cu); same results bit for bit
+  if (!d->exact_pooling && fused_ring_supported(p, d->depth_dtype, use_tma, d->dtype)) return launch_fused_ring(p, d->dtype, s);
   return dispatch_out(d->pe_mode == V3D_PE_NONE ? V3D_BF16 : d->dtype, [&](auto tag) {
     using T = decltype(tag);
     return launch_fused_dt<true, T>(d->depth_dtype, use_tma, p, s);

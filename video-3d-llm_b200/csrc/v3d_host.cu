@@ -62,12 +62,16 @@ class CopyPool {
     }
     while ((int)workers_.size() < n) {
       const int id = (int)workers_.size();
-      workers_.emplace_back([this, id] { loop(id); });
+      unsigned long born;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        born = epoch_;  // a worker only reacts to jobs posted after it was created
+      }
+      workers_.emplace_back([this, id, born] { loop(id, born); });
       workers_.back().detach();
     }
   }
-  void loop(int id) {
-    unsigned long seen = 0;
+  void loop(int id, unsigned long seen) {
     for (;;) {
       std::function<void(int)>* f = nullptr;
       {

@@ -45,6 +45,10 @@ class FrontEndConfig:
 class FrontEnd:
     """Callable bound to one configuration and device; caches maps, dim_t and the PE table."""
 
+    #: True forces the reference's operator sequence for every patch mean (v3d_frontend_desc.exact_pooling); the results
+    #: are identical either way -- this is a switch for tests and profiling
+    exact_pooling = False
+
     def __init__(self, config: FrontEndConfig | None = None, device=None, **overrides):
         cfg = dataclasses.replace(config or FrontEndConfig(), **overrides)
         self.cfg = cfg
@@ -242,6 +246,7 @@ class FrontEnd:
         if clamp is not None:
             d.has_clamp, d.clamp_lo, d.clamp_hi = 1, cabi.float3(clamp[0]), cabi.float3(clamp[1])
         d.depth_resampled, d.coord_dtype = int(bool(resampled)), cabi.dtype_code(coord_dtype)
+        d.exact_pooling = int(bool(self.exact_pooling))
         pooled = pe_coords = None
         use_pe = pe and self.flags["sin3d"]
         if want_coords or not use_pe:

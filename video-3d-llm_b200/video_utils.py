@@ -436,7 +436,10 @@ class VideoProcessor:
             from . import scene_pack
 
             path = scene_pack.pack_path(self.pack_dir, video_id)
-            self._packs[video_id] = scene_pack.ScenePack(path) if os.path.isfile(path) else None
+            pack = scene_pack.ScenePack(path) if os.path.isfile(path) else None
+            # loader threads race here; the FIRST mapping must stay the cached one -- a replaced ScenePack would be unmapped
+            # while another thread still copies from its pages (v3d_host_gather takes raw addresses)
+            self._packs.setdefault(video_id, pack)
         return self._packs[video_id]
 
     def load_frames(self, video_id: str, frame_files):
@@ -710,4 +713,11 @@ class SceneBatchLoader:
                                   batched=True, resampled=self.resampled, src_hw=self.src_hw)
 
     def close(self):
-        self._pool.shutdown(wait=False, cancel_futures=True)
+        """Cancel queued batches and WAIT for the one being gathered: it writes into the pinned ring, which must outlive it."""
+        self._pool.shutdown(wait=True, cancel_futures=True)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
