@@ -41,7 +41,8 @@ struct RingGeom {
   int slots;         // ring slots
   int span_limit;    // largest (u_last - u0) / (v_last - v0) for which the 32-bit window sums are exact
   double inv_n;      // 1 / pixels per patch
-  int pool_groups;   // independent groups of pool warps (each owns two depth buffers)
+  int pool_groups;   // independent groups of pool warps
+  int depth_bufs;    // depth buffers per group (1: the next patch row's depth rows are requested when the current one is done)
 };
 
 struct RingSmem {
@@ -74,7 +75,7 @@ __host__ __device__ inline RingSmem ring_smem(const FusedParams& p, const RingGe
   b = (b + 15) & ~(size_t)15;
   m.depth = b;
   m.depth_stride = (size_t)p.patch * p.span;
-  b += (size_t)2 * r.pool_groups * m.depth_stride;
+  b += (size_t)r.depth_bufs * r.pool_groups * m.depth_stride;
   b = (b + 127) & ~(size_t)127;
   m.ring = b;
   b += (size_t)r.slots * r.stage_chunks * 16;
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_fused_ring(const FusedParam
     auto issue_depth = [&](int n) {  // the group's first warp: stage the P depth rows of the group's n-th item
       const int item = (int)blockIdx.x + (grp + n * NG) * (int)gridDim.x;
       const int f = item / G, gi = item - f * G;
-      const uint32_t b = (uint32_t)(grp * 2 + (n & 1));
+      const uint32_t b = (uint32_t)(grp * r.depth_bufs + (r.depth_bufs == 2 ? (n & 1) : 0));
       const uint32_t bar = dbar0 + 8u * b;
       if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(P * p.span)) : "memory");
       __syncwarp();
@@ -375,18 +376,18 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_fused_ring(const FusedParam
     };
     if (gwarp == 0) {
       if (grp < nk) issue_depth(0);
-      if (grp + NG < nk) issue_depth(1);
+      if (r.depth_bufs == 2 && grp + NG < nk) issue_depth(1);
     }
     int n = 0;
     for (int ord = grp; ord < nk; ord += NG, ++n) {
       const int item = (int)blockIdx.x + ord * (int)gridDim.x;
       const int f = item / G, gi = item - f * G;
       const uint32_t is = (uint32_t)ord % kItemSlots;
-      const uint32_t b = (uint32_t)(grp * 2 + (n & 1));
+      const uint32_t b = (uint32_t)(grp * r.depth_bufs + (r.depth_bufs == 2 ? (n & 1) : 0));
       // camera coefficients of the frame: the last three threads of the group, while the others wait for the depth rows
       if (tg >= GT - 3) make_axis_coef(p.intr, p.poses, f, tg - (GT - 3), p.depth_scale, coef + (tg - (GT - 3)));
       if (ord >= kItemSlots) mbar_wait_addr(ifree0 + 8u * is, (((uint32_t)ord / kItemSlots) - 1u) & 1u);
-      mbar_wait_addr(dbar0 + 8u * b, ((uint32_t)n >> 1) & 1u);
+      mbar_wait_addr(dbar0 + 8u * b, (r.depth_bufs == 2 ? ((uint32_t)n >> 1) : (uint32_t)n) & 1u);
       // column sums over the P staged rows: S0 = sum d, S2 = sum (v - v0)*d, and the largest depth; two columns at a time
       {
         const uint32_t dbase = smem_u32(s_depth) + (uint32_t)(b * m.depth_stride) - (uint32_t)p.col_lo_byte;
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_fused_ring(const FusedParam
       }
       // s_off of this slot is complete; this depth buffer, the coefficients and the column sums are free again
       if (tg == 0) mbar_arrive_addr(iready0 + 8u * is);  // release: visible to the waiters
-      if (gwarp == 0 && ord + 2 * NG < nk) issue_depth(n + 2);
+      if (gwarp == 0 && ord + r.depth_bufs * NG < nk) issue_depth(n + r.depth_bufs);
     }
     return;
   }
@@ -545,7 +546,12 @@ static int ring_geom(const FusedParams& p, RingGeom* r) {
   r->n_stage = (p.grid + r->stage_rows - 1) / r->stage_rows;
   r->inv_n = 1.0 / ((double)p.patch * (double)p.patch);
   // four groups when their eight depth buffers leave most of the shared memory to the ring
-  r->pool_groups = ((size_t)8 * p.patch * p.span <= (size_t)112 * 1024) ? 4 : 2;
+  r->pool_groups = 4;
+  r->depth_bufs = 1;
+  if (const char* e = getenv("V3D_RING_POOL")) {  // experiments: "<groups><depth buffers>", e.g. 42
+    r->pool_groups = (e[0] == '2') ? 2 : 4;
+    r->depth_bufs = (e[1] == '2') ? 2 : 1;
+  }
   r->span_limit = (int)min((unsigned long long)4095, 0xffffffffull / ((unsigned long long)p.patch * p.patch * 65535ull));
   return 1;
 }
