@@ -98,7 +98,7 @@ def ncu_traffic():
         with open(p) as f:
             d = json.load(f)
         if d.get("csrc_hash") == csrc_hash():
-            return d.get("k_fused_dram_bytes_per_launch")
+            return d.get("dram_bytes_per_launch", d.get("k_fused_dram_bytes_per_launch"))
     return None
 
 
@@ -943,7 +943,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "traffic_source": "profiles/traffic.json (ncu --set full of this kernel source hash), null if the sources changed since",
                          "csrc_hash": csrc_hash(), "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "algorithmic_bytes_per_launch": BYTES_PER_FRAME_FUSED_ADD * n_frames, "kernel": "k_fused",
+                         "algorithmic_bytes_per_launch": BYTES_PER_FRAME_FUSED_ADD * n_frames, "kernel": "k_fused_ring",
                          "avg_launch_us": kernel_s * 1e6},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": Ke, "ms_per_step": e2e_ms, "loader_threads": threads,
@@ -952,7 +952,7 @@ def run_ours(args):
                             "(average_coordinate_in_patch -> discrete_coords -> tokens + world_position_embedding) = one fused launch "
                             "reading the resampled depth in place -> D2H of a result slice; one step in flight; vision tokens are "
                             "produced on the device by the vision tower and stay resident"},
-            "gpu_launches": K,  # timed region: K launches of k_fused (e2e: 16 per step; mc: 4 per step)
+            "gpu_launches": K,  # timed region: K launches of k_fused_ring (e2e: 16 per step; mc: 4 per step)
             "clocks": clk,
             "config1": config1,
             "overlay_path": overlay,
