@@ -24,6 +24,7 @@ Printed JSON line (rank 0):
              same with all candidate frames uploaded from pinned host memory every step; mc.cpu_baseline: the
              reference's loop as written (bounded sample) and a packed-key host variant
   config4    BASELINE configs[3]: 256 scenes, mc-ratio95 cut + PE of the selected frames, scene-sharded, all-gather
+  config5    (--config5) BASELINE configs[4]: the front end at 64 frames in front of a random-init Qwen2-7B bf16 prefill
   host_limits   pinned H2D GB/s per rank (all ranks at once) and loader memcpy GB/s: the ceilings of `e2e`
   default_recipe_geometry / mlp_pe / projector_tail / host_ingest   further secondary objects
 `--impl reference` times the CPU port only (rank 0), on a bounded sample of the same workload.
@@ -802,6 +803,82 @@ def mlp_leg(dev, steps: int):
             "hbm_gbs": byts / ms / 1e6, "frames_per_s": SCENES * FRAMES / (ms / 1e3)}
 
 
+def config5_leg(rank: int, world: int, dev, frames: int = 64, text_tokens: int = 128, steps: int = 3):
+    """BASELINE configs[4] (opt-in, `--config5`): the front end at frames_upbound = 64 in front of a random-init
+    LLaVA-Video-7B language model (Qwen2-7B shape: 28 layers, hidden 3584, 28 heads / 4 KV heads, MLP 18944; transformers'
+    stock implementation with SDPA attention -- a library consumer, not part of this package) doing one bf16 prefill over
+    the scene's tokens, one replica per rank (data parallel by scene).  Per step: pinned depth/pose/intrinsics of one scene
+    -> H2D -> patch coordinates (27-pixel windows, discretised) -> bilinear pool of the projector output + sin-3D PE + newline
+    (the default recipe's 64 x 210 tokens) -> [text | vision] embeddings -> prefill -> D2H of the next-token id.  Reports the
+    front end's share of the step (it must stay off the critical path)."""
+    import torch.distributed as dist
+    from transformers import Qwen2Config
+    from transformers.models.qwen2.modeling_qwen2 import Qwen2ForCausalLM
+
+    from video_3d_llm_b200 import projector_tail as PT
+    from video_3d_llm_b200 import synthetic
+    from video_3d_llm_b200.frontend import FrontEnd
+    from video_3d_llm_b200.position_encoding import PositionEmbeddingSine3D
+
+    E, side, Go = 3584, 27, 14
+    cfg = Qwen2Config(hidden_size=E, num_hidden_layers=28, num_attention_heads=28, num_key_value_heads=4, intermediate_size=18944,
+                      vocab_size=152064, max_position_embeddings=32768, rms_norm_eps=1e-6, rope_theta=1000000.0, tie_word_embeddings=False)
+    cfg._attn_implementation = "sdpa"
+    torch.manual_seed(1234 + rank)
+    with torch.device(dev):
+        model = Qwen2ForCausalLM(cfg).to(torch.bfloat16).eval()  # random init, on the device
+    n_params = sum(p.numel() for p in model.parameters())
+    sc = synthetic.make_scene(500 + rank, frames, n_total=300, device="cpu")
+    h_depth, h_poses, h_intr = sc.depth.pin_memory(), sc.poses.pin_memory(), sc.intrinsics.pin_memory()
+    fe = FrontEnd(device=dev, patch_size=27, embedding_size=E)
+    pe = PositionEmbeddingSine3D(E)
+    g = torch.Generator(device=dev).manual_seed(9)
+    proj_out = torch.randn((frames, side * side, E), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)  # mm_projector output
+    newline = torch.randn(E, generator=g, device=dev).to(torch.bfloat16)
+    text = torch.randn((1, text_tokens, E), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16) * 0.02
+    h_tok = torch.empty((1,), dtype=torch.int64).pin_memory()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step():
+        ev[0].record()
+        depth, poses, intr = (t.to(dev, non_blocking=True) for t in (h_depth, h_poses, h_intr))
+        ev[1].record()
+        coords = fe(depth, poses, intr, pe=False)  # (V,14,14,3) discretised patch coordinates
+        vis = PT.pool_pe_newline(proj_out, coords=coords.flatten(1, 2), position_embedding=pe, image_newline=newline)
+        ev[2].record()
+        emb = torch.cat((text, vis.view(1, -1, E)), dim=1)
+        with torch.no_grad():
+            logits = model(inputs_embeds=emb, use_cache=False, logits_to_keep=1).logits
+        h_tok.copy_(logits[0, -1].argmax(), non_blocking=True)
+        ev[3].record()
+        return emb.shape[1]
+
+    for _ in range(2):
+        n_tok = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    fe_ms = h2d_ms = tot_ms = 0.0
+    for _ in range(steps):
+        n_tok = step()
+        torch.cuda.synchronize()
+        h2d_ms += ev[0].elapsed_time(ev[1])
+        fe_ms += ev[1].elapsed_time(ev[2])
+        tot_ms += ev[0].elapsed_time(ev[3])
+    t = torch.tensor([tot_ms / steps, fe_ms / steps, h2d_ms / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot, fem, h2d = (float(v) for v in t.tolist())
+    del model
+    torch.cuda.empty_cache()
+    return {"workload": f"{frames} frames (frames_upbound = 64) -> 27-pixel patch coordinates -> pool + sin-3D PE + newline ({frames} x 210 tokens) -> "
+                        f"random-init Qwen2-7B prefill over {n_tok} tokens, bf16, one replica per rank (BASELINE configs[4])",
+            "llm": "transformers Qwen2ForCausalLM (library), SDPA attention, random init", "llm_params": n_params, "prefill_tokens": int(n_tok),
+            "ms_per_step": tot, "frontend_ms": fem, "h2d_ms": h2d, "frontend_share_of_step": fem / tot, "scenes_per_s": world / (tot / 1e3),
+            "frames_per_s": world * frames / (tot / 1e3), "h2d_bytes_per_step": int(h_depth.numel() * 2 + h_poses.numel() * 4 + h_intr.numel() * 4),
+            "d2h_bytes_per_step": 8}
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -917,6 +994,14 @@ def run_ours(args):
             raise
         c4 = {"error": repr(e)}
     mlp = mlp_leg(dev, steps=5) if rank == 0 else None
+    c5 = None
+    if args.config5:
+        try:
+            c5 = config5_leg(rank, world, dev)
+        except Exception as e:
+            if world > 1:
+                raise
+            c5 = {"error": repr(e)}
     tail = None
     if rank == 0:
         try:
@@ -960,6 +1045,7 @@ def run_ours(args):
             "default_recipe_geometry": recipe,
             "mc": mc,
             "config4": c4,
+            "config5": c5,
             "mlp_pe": mlp,
             "projector_tail": tail,
             "host_ingest": ingest,
@@ -1004,6 +1090,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-mc-cpu", action="store_true", help="skip the CPU baseline of the MC metric (~30 s)")
+    ap.add_argument("--config5", action="store_true", help="also run BASELINE configs[4]: the front end in front of a random-init Qwen2-7B prefill (~1 min)")
     ap.add_argument("--packs-in-shm", action="store_true", help="write the e2e leg's packed scenes to /dev/shm instead of the temp dir")
     args = ap.parse_args()
     if args.impl == "reference":
