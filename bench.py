@@ -798,7 +798,7 @@ def mlp_leg(dev, steps: int):
             peak_tf = float(json.load(f)["bf16_tflops"])
     except OSError:
         pass
-    return {"kernel": "k_pe_mlp (tcgen05.mma cta_group::1 M128 N128 K16, TMEM accumulators)", "tokens": M, "K": 512, "N": E,
+    return {"kernel": "k_pe_mlp (tcgen05.mma cta_group::1 M128 N128 K16, A and accumulators in TMEM, TMA-staged epilogue)", "tokens": M, "K": 512, "N": E,
             "ms": ms, "tflops": flops / ms / 1e9, "frac_of_measured_bf16_peak": flops / ms / 1e9 / peak_tf,
             "hbm_gbs": byts / ms / 1e6, "frames_per_s": SCENES * FRAMES / (ms / 1e3)}
 

@@ -505,6 +505,27 @@ def test_mc_full_size_properties():
             used |= bits[f]
 
 
+def test_mc_full_size_scene_against_the_oracle():
+    """One BASELINE config 3 scene at full size (150 candidate frames of 480x640, 0.1 m voxels) against the C oracle
+    (oracle/v3d_oracle.c restates max_coverage_sampling.py:39-104 with every rounding explicit; pinned on the reference's own
+    output in tests/test_oracle_golden.py): coverage bitsets of all 150 frames, pick order with the seeded tie-breaks, gains
+    and both counts must be identical."""
+    seed = 704
+    sc = synthetic.make_scene(seed, 150, n_total=300, frame_indices=np.arange(0, 300, 2), device="cpu")
+    pc = synthetic.mesh_voxels(sc.room, sc.boxes, seed)
+    order, gains, n_all, n_sel, bitsets = O.mc_sample_scene(sc.depth_u16(), sc.poses.numpy(), sc.intrinsics.numpy(), pc, 0.1, 32, seed)
+    sampler = mc_sampling.MCSampler(device=DEV)
+    plan = sampler.plan([{"depth": sc.depth.to(DEV), "poses": sc.poses.to(DEV), "intrinsics": sc.intrinsics.to(DEV),
+                          "pc_voxels": torch.from_numpy(pc).to(DEV), "seed": seed}])
+    res = sampler.decode(sampler.run(plan))[0]
+    got_bits = sampler.bitsets(plan, 0)
+    ref_bits = np.asarray(bitsets).reshape(150, -1)
+    np.testing.assert_array_equal(got_bits[:, : ref_bits.shape[1]].astype(np.uint32), ref_bits.astype(np.uint32))
+    assert res["order"] == list(order) and res["gains"] == list(gains)
+    assert (res["n_all"], res["n_sel"]) == (n_all, n_sel)
+    assert len(order) == 32
+
+
 def test_mc_sampler_golden(golden_dir):
     """Against the output of the reference's own max_coverage_sampling.main (tests/golden/dataset.json)."""
     with open(os.path.join(golden_dir, "dataset.json")) as f:

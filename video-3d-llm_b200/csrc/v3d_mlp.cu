@@ -24,8 +24,9 @@
 
 namespace v3d {
 
-static constexpr int kMlpThreads = 384;        // 12 warps: TMA, MMA, 2 spare, 8 producer/epilogue
-static constexpr int kEpiThreads = 256;        // warps 4-11
+// warps: TMA, MMA, 2 spare, then PARTS producer/epilogue warps per TMEM lane quadrant (each a 1/PARTS share of the k range
+// when the A operand is built and of an N tile's columns in the epilogue)
+__host__ __device__ constexpr int mlp_threads(int parts) { return 128 + 128 * parts; }
 static constexpr int kHidden = 512;          // nn.Linear(3, 512) of the reference module
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;           // 64 bf16 = 128 bytes = one swizzle atom
@@ -35,6 +36,18 @@ static constexpr int kNumKBlocks = kHidden / kBlockK;  // 8
 #endif
 #ifndef V3D_MLP_PREFETCH
 #define V3D_MLP_PREFETCH 0
+#endif
+#ifndef V3D_MLP_TMA_STAGE
+#define V3D_MLP_TMA_STAGE 1  // epilogue staging tiles filled / drained by TMA (0: plain loads and stores)
+#endif
+#ifndef V3D_MLP_PARTS
+#define V3D_MLP_PARTS 4  // producer/epilogue warps per TMEM lane quadrant of the TMA-staged variant (2 or 4)
+#endif
+#ifndef V3D_MLP_MCAST
+#define V3D_MLP_MCAST 0  // 1: W2 stages multicast to the two CTAs of a cluster (measured: no gain)
+#endif
+#ifndef V3D_MLP_TOK_PF
+#define V3D_MLP_TOK_PF 2  // N tiles ahead of the epilogue at which a tile's token block is pulled into L2 (0 = off)
 #endif
 static constexpr int kStages = V3D_MLP_STAGES;  // W2 ring (16 KB per stage at BLOCK_N = 128)
 static constexpr uint32_t kTmemColsA = 256;  // first TMEM column of the A operand (128 lanes x 256 cols x 2 bf16)
@@ -117,6 +130,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+#ifdef V3D_MLP_TRACE
+// diagnostic build: cycles the MMA thread of CTA 0 spends waiting for (0) the A operand, (1) a drained accumulator, (2) a W2
+// stage, and (3) its total; (4) cycles an epilogue warp of CTA 0 spends producing A
+__device__ unsigned long long g_mlp_trace[8];
+#define MLP_T0() const long long t0__ = clock64()
+#define MLP_ACC(k) g_mlp_trace_local[k] += clock64() - t0__
+#else
+#define MLP_T0() do { } while (0)
+#define MLP_ACC(k) do { } while (0)
+#endif
+
 struct MlpParams {
   const float* coords;   // (M,3)
   const float* w1;       // (512,3)
@@ -135,26 +159,36 @@ struct MlpParams {
 //   then: float4 gw1[512], float2 gb[512], barriers, tmem base, LN moments, epilogue staging
 static constexpr int kMaxE = 8192;  // bias staged in shared memory
 
-template <int BLOCK_N>
+// TMA_STAGE: the epilogue's token blocks arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B = the staging tile's XOR
+// pattern) into two staging tiles per warp and the results leave by TMA stores from the same tiles.
+template <int BLOCK_N, bool TMA_STAGE, int PARTS>
 struct MlpSmem {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kOffB = 0;
   static constexpr int kOffW1 = kOffB + kStages * kBBytes;
   static constexpr int kOffGB = kOffW1 + kHidden * 16;
   static constexpr int kOffBar = kOffGB + kHidden * 8;
-  // barriers: b_full[S], b_empty[S], a_full, tmem_full[2], tmem_empty[2]
-  static constexpr int kNumBars = 2 * kStages + 1 + 4;
+  // barriers: b_full[S], b_empty[S], a_full, tmem_full[2], tmem_empty[2], tok_full[4*PARTS warps][2]
+  static constexpr int kNumBars = 2 * kStages + 1 + 4 + 8 * PARTS;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kOffMom = kOffTmem + 16;   // 16 floats: LayerNorm moment data
-  static constexpr int kOffStage = (kOffMom + 64 + 127) & ~127;  // epilogue staging: 4 warps x 32 rows x BLOCK_N bf16
-  static constexpr int kStageBytesPerWarp = 32 * (BLOCK_N / 2) * 2;  // 32 rows x half an N tile, bf16
-  static constexpr int kOffBias = kOffStage + 8 * kStageBytesPerWarp;  // b2 (E floats, E <= kMaxE)
-  static constexpr int kTotal = kOffBias + kMaxE * 4;
+  static constexpr int kOffStage = (kOffMom + 64 + 1023) & ~1023;  // epilogue staging: 8 warps x (1 or 2) x 32 rows x BLOCK_N/2 bf16
+  static constexpr int kStageBytesPerWarp = 32 * (BLOCK_N / PARTS) * 2;  // 32 rows x this warp's share of an N tile, bf16
+  static constexpr int kStageBufs = TMA_STAGE ? 2 : 1;
+  static constexpr int kOffBias = kOffStage + 4 * PARTS * kStageBufs * kStageBytesPerWarp;  // b2 (E floats)
+  static constexpr int total(int E) { return kOffBias + E * 4; }
 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant__ CUtensorMap w2_map, const MlpParams p) {
-  using S = MlpSmem<BLOCK_N>;
+// MCAST: launched in clusters of two CTAs that walk their M tiles in lockstep; every W2 stage is fetched from L2 once and
+// delivered to both CTAs' rings by one multicast TMA load (the CTAs issue alternate stages), which halves the W2 stream
+// out of L2 -- with one CTA per SM each re-reading all of W2 for every 128 tokens that stream, not HBM, is what the
+// tensor pipe waits for.
+template <int BLOCK_N, bool TMA_STAGE, int PARTS, bool MCAST>
+__global__ void __launch_bounds__(mlp_threads(PARTS), 1) k_pe_mlp(const __grid_constant__ CUtensorMap w2_map, const __grid_constant__ CUtensorMap tok_map,
+                                                           const __grid_constant__ CUtensorMap tok_io_map,
+                                                           const __grid_constant__ CUtensorMap out_io_map, const MlpParams p) {
+  using S = MlpSmem<BLOCK_N, TMA_STAGE, PARTS>;
+  constexpr int kMlpThreads = mlp_threads(PARTS), kEpiThreads = 128 * PARTS;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -220,13 +254,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&w2_map) : "memory");
     for (int i = 0; i < kStages; ++i) {
       mbar_init(b_full + i, 1);
-      mbar_init(b_empty + i, 1);
+      mbar_init(b_empty + i, MCAST ? 2 : 1);  // MCAST: the MMAs of both CTAs have read the stage
     }
     mbar_init(a_full, kEpiThreads);
     for (int i = 0; i < 2; ++i) {
       mbar_init(t_full + i, 1);
       mbar_init(t_empty + i, kEpiThreads);
     }
+    for (int i = 0; i < 8 * PARTS; ++i) mbar_init(bars + 2 * kStages + 5 + i, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -240,18 +275,37 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
 
   const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
   const int n_tiles = p.E / BLOCK_N;
+  // M tiles of this CTA: blockIdx.x + j * gridDim.x.  With MCAST both CTAs of a cluster make the same number of passes;
+  // a pass past the end recomputes the last tile without storing it.
+  const int n_iter = MCAST ? (m_tiles + (int)gridDim.x - 1) / (int)gridDim.x : (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int j) { return min((int)blockIdx.x + j * (int)gridDim.x, m_tiles - 1); };
+  uint32_t cta_rank = 0;
+  if constexpr (MCAST) {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    // the peer's barriers are initialised before anything of ours reaches them
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
 
   if (warp == 0) {
     // ================= TMA producer: W2 tiles for every (m tile, n tile, k block) =================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
+      for (int j = 0; j < n_iter; ++j)
         for (int nt = 0; nt < n_tiles; ++nt)
           for (int kb = 0; kb < kNumKBlocks; ++kb, ++it) {
             const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
             mbar_wait(b_empty + stage, phase ^ 1);
             mbar_arrive_expect_tx(b_full + stage, (uint32_t)S::kBBytes);
-            tma_load_2d(s_b + stage * S::kBBytes, &w2_map, kb * kBlockK, nt * BLOCK_N, b_full + stage);
+            if constexpr (MCAST) {
+              if ((it & 1u) == cta_rank)  // one load, delivered to the same slot and barrier of both CTAs
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+                        smem_u32(s_b + stage * S::kBBytes)),
+                    "l"(&w2_map), "r"(kb * kBlockK), "r"(nt * BLOCK_N), "r"(smem_u32(b_full + stage)), "h"((uint16_t)3)
+                    : "memory");
+            } else {
+              tma_load_2d(s_b + stage * S::kBBytes, &w2_map, kb * kBlockK, nt * BLOCK_N, b_full + stage);
+            }
           }
     }
   } else if (warp == 1) {
@@ -259,49 +313,73 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
       uint32_t it = 0, acc_it = 0, a_phase = 0;
-      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, a_phase ^= 1) {
-        mbar_wait(a_full, a_phase);  // A operand of this M tile is in tensor memory
+#ifdef V3D_MLP_TRACE
+      long long g_mlp_trace_local[4] = {0, 0, 0, 0};
+      const long long t_start = clock64();
+#endif
+      for (int j = 0; j < n_iter; ++j, a_phase ^= 1) {
+        { MLP_T0(); mbar_wait(a_full, a_phase); MLP_ACC(0); }  // A operand of this M tile is in tensor memory
         tcgen05_fence_after();
         for (int nt = 0; nt < n_tiles; ++nt, ++acc_it) {
           const uint32_t acc = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
-          mbar_wait(t_empty + acc, acc_phase ^ 1);  // epilogue has drained this accumulator
+          { MLP_T0(); mbar_wait(t_empty + acc, acc_phase ^ 1); MLP_ACC(1); }  // epilogue has drained this accumulator
           tcgen05_fence_after();
           const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
           for (int kb = 0; kb < kNumKBlocks; ++kb, ++it) {
             const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
-            mbar_wait(b_full + stage, phase);
+            { MLP_T0(); mbar_wait(b_full + stage, phase); MLP_ACC(2); }
             tcgen05_fence_after();
             const uint32_t ta = tmem_base + kTmemColsA + kb * (kBlockK / 2);
             const uint64_t db = make_kmajor_sw128_desc(s_b + stage * S::kBBytes);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)  // UMMA_K = 16 bf16: 8 TMEM columns of A, 32 bytes (+2 in the >>4 field) of B
               umma_bf16_ts(tmem_d, ta + 8 * k, db + 2 * k, idesc, (kb | k) != 0);
-            umma_commit(b_empty + stage);  // frees the W2 slot when these MMAs have read it
+            // frees the W2 slot when these MMAs have read it (MCAST: in both CTAs, whose loads fill both rings)
+            if constexpr (MCAST)
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                               smem_u32(b_empty + stage)),
+                           "h"((uint16_t)3)
+                           : "memory");
+            else
+              umma_commit(b_empty + stage);
           }
           umma_commit(t_full + acc);  // accumulator complete
         }
       }
+#ifdef V3D_MLP_TRACE
+      if (blockIdx.x == 0) {
+        for (int i = 0; i < 3; ++i) g_mlp_trace[i] = (unsigned long long)g_mlp_trace_local[i];
+        g_mlp_trace[3] = (unsigned long long)(clock64() - t_start);
+      }
+#endif
     }
   } else if (warp >= 4) {
     // ================= A producer + epilogue: thread = token row = TMEM lane =====================
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
-    const int half = (warp - 4) >> 2;  // which half of the k range (A production) / of the N tile's columns (epilogue)
+    const int half = (warp - 4) >> 2;  // which share of the k range (A production) / of the N tile's columns (epilogue)
     const int r = q * 32 + lane;       // row inside the M tile
-    uint32_t acc_it = 0;
-    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
-      const int m = mt * kBlockM + r;
-      const bool row_ok = m < p.M;
-      // L2 prefetch of the token rows by the TMA unit, one M tile ahead of their use in the epilogue (the very
-      // first tile is requested here, before its A operand is built)
-      if (V3D_MLP_PREFETCH && threadIdx.x == 128 && p.tokens != nullptr) {  // (off by default)
-        for (int t = (mt == (int)blockIdx.x ? mt : mt + (int)gridDim.x); t <= mt + (int)gridDim.x && t < m_tiles; t += gridDim.x) {
-          const size_t rows = (size_t)min(kBlockM, p.M - t * kBlockM);
-          const unsigned char* src = reinterpret_cast<const unsigned char*>(p.tokens + (size_t)t * kBlockM * p.E);
-          const size_t bytes = rows * (size_t)p.E * 2;
-          for (size_t o = 0; o < bytes; o += 32768) tma_prefetch_l2(src + o, (uint32_t)min((size_t)32768, bytes - o));
+    uint32_t acc_it = 0, tile_seq = 0;
+    // The epilogue reads the tokens of an N tile as 128 rows x 256 bytes, 2304+ bytes apart: left to plain loads that is
+    // one DRAM round trip per tile on the critical path of the accumulator hand-over (ncu: a fifth of all stall samples
+    // on the first use of those loads).  One thread asks the TMA unit to pull the (128 x BLOCK_N) block into L2
+    // V3D_MLP_TOK_PF tiles ahead -- across M tiles -- so that the loads, issued one tile ahead, hit L2.
+    auto prefetch_tokens = [&](int mt_, int nt_) {
+      if (V3D_MLP_TOK_PF > 0 && threadIdx.x == 128 && p.tokens != nullptr) {
+        if (nt_ >= n_tiles) {
+          nt_ -= n_tiles;
+          mt_ += (int)gridDim.x;
         }
+        if (mt_ < m_tiles && nt_ < n_tiles)
+          asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tok_map), "r"(nt_ * BLOCK_N), "r"(mt_ * kBlockM)
+                       : "memory");
       }
-      // ---- (a) hidden activations of this token: Linear(3,512) -> LayerNorm -> ReLU -> bf16
+    };
+    for (int i = 0; i < V3D_MLP_TOK_PF; ++i) prefetch_tokens((int)blockIdx.x, i);
+    // (a) the A operand of M tile mt_: hidden activations of this thread's token (Linear(3,512) -> LayerNorm -> ReLU -> bf16)
+    // into tensor memory, then one arrival on a_full
+    auto produce_a = [&](int mt_) {
+      const int m = mt_ * kBlockM + r;
+      const bool row_ok = m < p.M;
       float c0 = 0.f, c1 = 0.f, c2 = 0.f;
       if (row_ok) {
         c0 = __ldg(p.coords + 3 * (size_t)m);
@@ -318,7 +396,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
       const float nmr = -mean * rstd;
       const uint32_t ta_row = tmem_base + ((uint32_t)(q * 32) << 16) + kTmemColsA;
 #pragma unroll 1
-      for (int kb = half * (kNumKBlocks / 2); kb < (half + 1) * (kNumKBlocks / 2); ++kb) {  // 64 features = 32 TMEM columns per store
+      for (int kb = half * (kNumKBlocks / PARTS); kb < (half + 1) * (kNumKBlocks / PARTS); ++kb) {  // 64 features = 32 TMEM columns per store
         uint32_t packed[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -339,6 +417,23 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
       tmem_st_wait();
       tcgen05_fence_before();  // order the TMEM stores before the MMA thread's reads
       mbar_arrive(a_full);
+    };
+    for (int j = 0; j < n_iter; ++j) {
+      const int mt = tile_of(j);
+      const bool real = (int)blockIdx.x + j * (int)gridDim.x < m_tiles;  // a pass past the end (MCAST) stores nothing
+      // L2 prefetch of the token rows by the TMA unit, one M tile ahead of their use in the epilogue (the very
+      // first tile is requested here, before its A operand is built)
+      if (V3D_MLP_PREFETCH && threadIdx.x == 128 && p.tokens != nullptr) {  // (off by default)
+        for (int t = (mt == (int)blockIdx.x ? mt : mt + (int)gridDim.x); t <= mt + (int)gridDim.x && t < m_tiles; t += gridDim.x) {
+          const size_t rows = (size_t)min(kBlockM, p.M - t * kBlockM);
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(p.tokens + (size_t)t * kBlockM * p.E);
+          const size_t bytes = rows * (size_t)p.E * 2;
+          for (size_t o = 0; o < bytes; o += 32768) tma_prefetch_l2(src + o, (uint32_t)min((size_t)32768, bytes - o));
+        }
+      }
+      // With the TMA-staged epilogue the A operand of the NEXT M tile is built before the last N tile of this one is
+      // drained (below), so only the first M tile is built here.
+      if (!TMA_STAGE || j == 0) produce_a(mt);
 
       // ---- (b) epilogue of every N tile of this M tile.
       // Global traffic is warp-coalesced: a warp instruction moves 512 contiguous bytes (2 rows x 256 B at
@@ -346,15 +441,99 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
       // conflict-free both ways) turns that into the row-per-thread order of the TMEM accumulator and back.
       // The token segment of the NEXT N tile is requested before the current accumulator is touched, so
       // its latency hides behind this tile's TMEM loads, math and stores.
-      constexpr int kHalfN = BLOCK_N / 2;             // columns of an N tile this warp owns
+      constexpr int kHalfN = BLOCK_N / PARTS;         // columns of an N tile this warp owns
       constexpr int kChunks = kHalfN / 8;             // 16-byte chunks per row
+      const int col0 = half * kHalfN;                // first column (inside the N tile) of this warp
+      const int row0 = mt * kBlockM + q * 32;        // first global row of this warp
+      const bool add = p.tokens != nullptr;
+      if constexpr (TMA_STAGE) {
+        // ---- staging tiles filled and drained by the TMA unit.  Tile sequence of this warp: every (M tile, N tile) of the CTA
+        // in order, `seq` counts them; tile s uses staging buffer s & 1.  The token block of tile s+1 is requested at the
+        // start of tile s, into the buffer tile s-1 has just been stored from.
+        static_assert(!TMA_STAGE || kChunks == 8 || kChunks == 4, "staging rows are one 128-byte or 64-byte swizzle atom");
+        uint64_t* tokbar = bars + 2 * kStages + 5 + (warp - 4) * 2;
+        unsigned char* stage0 = smem + S::kOffStage + (warp - 4) * 2 * S::kStageBytesPerWarp;
+        auto issue_load = [&](int mt_, int nt_, uint32_t buf) {  // lane 0
+          mbar_arrive_expect_tx(tokbar + buf, (uint32_t)S::kStageBytesPerWarp);
+          tma_load_2d(stage0 + buf * S::kStageBytesPerWarp, &tok_io_map, nt_ * BLOCK_N + col0, mt_ * kBlockM + q * 32, tokbar + buf);
+        };
+        if (add && lane == 0 && j == 0) {  // the first two tiles of this warp
+          issue_load(mt, 0, 0);
+          if (n_tiles > 1) issue_load(mt, 1, 1);
+          else if (j + 1 < n_iter) issue_load(tile_of(j + 1), 0, 1);
+        }
+        for (int nt = 0; nt < n_tiles; ++nt, ++tile_seq) {
+          const uint32_t buf = tile_seq & 1u;
+          unsigned char* stage = stage0 + buf * S::kStageBytesPerWarp;
+          const uint32_t acc = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
+          prefetch_tokens(mt, nt + V3D_MLP_TOK_PF);
+          if (nt == n_tiles - 1 && j + 1 < n_iter) {
+            // Every MMA of this M tile has completed once the last accumulator is full: the A operand is free.  Build the
+            // next M tile's A first -- its MMAs then run (into the other accumulator) while this last N tile is drained --
+            // instead of leaving the tensor pipe idle through the last epilogue AND the A production.
+            mbar_wait(t_full + acc, acc_phase);
+            tcgen05_fence_after();
+            produce_a(tile_of(j + 1));
+          }
+          if (lane == 0 && tile_seq >= 1) {
+            // the previous tile's store has read its buffer: refill it with the next tile's tokens
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (add) {
+              if (nt + 1 < n_tiles) issue_load(mt, nt + 1, buf ^ 1u);
+              else if (j + 1 < n_iter) issue_load(tile_of(j + 1), 0, buf ^ 1u);
+            }
+          }
+          if (add) mbar_wait(tokbar + buf, (tile_seq >> 1) & 1u);
+          mbar_wait(t_full + acc, acc_phase);
+          tcgen05_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + col0;
+#pragma unroll
+          for (int cc = 0; cc < kHalfN / 32; ++cc) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + cc * 32, v);
+            tmem_ld_wait();
+            const float* bias = s_bias + nt * BLOCK_N + col0 + cc * 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t o[4];
+              const int chunk = cc * 4 + i;
+              // the TMA unit's swizzle: 16-byte chunk index ^ address bits [7,10) (128-byte rows) / [7,9) (64-byte rows)
+              const int sw = (kChunks == 8) ? (lane & 7) : ((lane >> 1) & 3);
+              uint4* slot = reinterpret_cast<uint4*>(stage + lane * (kHalfN * 2) + ((chunk ^ sw) << 4));
+              uint4 tk = make_uint4(0u, 0u, 0u, 0u);
+              if (add) tk = *slot;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int e = i * 8 + 2 * j;
+                // Linear output in bf16 (fp32 accumulate + bias, one rounding), then the bf16 add of llava_arch.py:515
+                const float2 bb = *reinterpret_cast<const float2*>(bias + e);  // same address for the whole warp: broadcast
+                __nv_bfloat162 pe = __floats2bfloat162_rn(__uint_as_float(v[e]) + bb.x, __uint_as_float(v[e + 1]) + bb.y);
+                if (add) {
+                  const uint32_t tw = (j == 0) ? tk.x : (j == 1) ? tk.y : (j == 2) ? tk.z : tk.w;
+                  pe = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&tw), pe);
+                }
+                o[j] = *reinterpret_cast<const uint32_t*>(&pe);
+              }
+              *slot = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          tcgen05_fence_before();
+          mbar_arrive(t_empty + acc);  // 256 arrivals release the accumulator
+          fence_proxy_async_smem();    // the tile's shared-memory writes are visible to the TMA store
+          __syncwarp();
+          if (lane == 0 && real) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&out_io_map), "r"(smem_u32(stage)),
+                         "r"(nt * BLOCK_N + col0), "r"(row0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++acc_it;
+        }
+      } else {
       constexpr int kRowsPerInst = 32 / kChunks;      // rows covered by one warp instruction
       constexpr int kInst = 32 / kRowsPerInst;        // warp instructions per N tile (= kChunks)
       unsigned char* stage = smem + S::kOffStage + (warp - 4) * S::kStageBytesPerWarp;
-      const int col0 = half * kHalfN;                // first column (inside the N tile) of this warp
       const int my_chunk = lane % kChunks, my_rsub = lane / kChunks;
-      const int row0 = mt * kBlockM + q * 32;        // first global row of this warp
-      const bool add = p.tokens != nullptr;
       uint4 tok_a[kInst], tok_b[kInst];
       auto load_tokens = [&](uint4 (&t)[kInst], int nt) {
         if (add && nt < n_tiles) {
@@ -370,6 +549,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
       };
       auto epilogue_tile = [&](const uint4 (&t)[kInst], int nt) {
         const uint32_t acc = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
+        prefetch_tokens(mt, nt + V3D_MLP_TOK_PF);
         if (add) {
 #pragma unroll
           for (int i = 0; i < kInst; ++i) *reinterpret_cast<uint4*>(stage_addr(i * kRowsPerInst + my_rsub, my_chunk)) = t[i];
@@ -426,9 +606,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_pe_mlp(const __grid_constant
           epilogue_tile(tok_b, nt + 1);
         }
       }
+      }
     }
   }
   // ---- teardown
+  if constexpr (MCAST)  // the peer may still multicast into this CTA's ring / arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (TMA_STAGE && warp >= 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's TMA stores are done
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -453,7 +637,7 @@ static EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool TMA_STAGE, int PARTS, bool MCAST>
 static int launch_mlp(const MlpParams& p, const void* w2, cudaStream_t s) {
   EncodeTiledFn encode = get_encode_tiled();
   V3D_REQUIRE(encode != nullptr, V3D_E_CUDA, "v3d_pe_mlp: cuTensorMapEncodeTiled not available from the driver");
@@ -466,19 +650,69 @@ static int launch_mlp(const MlpParams& p, const void* w2, cudaStream_t s) {
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   V3D_REQUIRE(r == CUDA_SUCCESS, V3D_E_CUDA, "v3d_pe_mlp: cuTensorMapEncodeTiled failed (%d)", (int)r);
-  using S = MlpSmem<BLOCK_N>;
-  const int smem = S::kTotal + 1024;  // slack for the 1024-byte alignment of the dynamic window
-  auto kern = k_pe_mlp<BLOCK_N>;
+  // the token / output matrices as 2-D tensors: (128 rows x BLOCK_N columns) blocks for the L2 prefetch, (32 rows x 64
+  // columns, 128-byte swizzle) blocks for the epilogue warps' staging tiles
+  const cuuint64_t tdim[2] = {(cuuint64_t)p.E, (cuuint64_t)p.M};
+  const cuuint64_t tstride[1] = {(cuuint64_t)p.E * 2};
+  auto encode_io = [&](CUtensorMap* m, const void* base, cuuint32_t bw, cuuint32_t bh, CUtensorMapSwizzle sw) -> CUresult {
+    const cuuint32_t tbox[2] = {bw, bh};
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), tdim, tstride, tbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  const CUtensorMapSwizzle io_swizzle = (BLOCK_N / PARTS) * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap tok_map, tok_io_map, out_io_map;
+  memset(&tok_map, 0, sizeof(tok_map));
+  memset(&tok_io_map, 0, sizeof(tok_io_map));
+  memset(&out_io_map, 0, sizeof(out_io_map));
+  if (p.tokens != nullptr) {
+    V3D_REQUIRE(encode_io(&tok_map, p.tokens, BLOCK_N, kBlockM, CU_TENSOR_MAP_SWIZZLE_NONE) == CUDA_SUCCESS, V3D_E_CUDA,
+                "v3d_pe_mlp: cuTensorMapEncodeTiled (token prefetch) failed");
+    if (TMA_STAGE)
+      V3D_REQUIRE(encode_io(&tok_io_map, p.tokens, BLOCK_N / PARTS, 32, io_swizzle) == CUDA_SUCCESS, V3D_E_CUDA,
+                  "v3d_pe_mlp: cuTensorMapEncodeTiled (token tiles) failed");
+  }
+  if (TMA_STAGE)
+    V3D_REQUIRE(encode_io(&out_io_map, p.out, BLOCK_N / PARTS, 32, io_swizzle) == CUDA_SUCCESS, V3D_E_CUDA,
+                "v3d_pe_mlp: cuTensorMapEncodeTiled (output tiles) failed");
+  using S = MlpSmem<BLOCK_N, TMA_STAGE, PARTS>;
+  const int smem = S::total(p.E) + 1024;  // slack for the 1024-byte alignment of the dynamic window
+  auto kern = k_pe_mlp<BLOCK_N, TMA_STAGE, PARTS, MCAST>;
   V3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
-  const int grid = m_tiles < num_sms() ? m_tiles : num_sms();
-  kern<<<grid, kMlpThreads, smem, s>>>(map, p);
+  int grid = m_tiles < num_sms() ? m_tiles : num_sms();
+  if (MCAST) {
+    grid &= ~1;  // whole clusters of two
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)mlp_threads(PARTS));
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    V3D_CUDA(cudaLaunchKernelEx(&cfg, kern, map, tok_map, tok_io_map, out_io_map, p));
+    return check_launch("k_pe_mlp");
+  }
+  kern<<<grid, mlp_threads(PARTS), smem, s>>>(map, tok_map, tok_io_map, out_io_map, p);
   return check_launch("k_pe_mlp");
 }
 
 }  // namespace v3d
 
 using namespace v3d;
+
+#ifdef V3D_MLP_TRACE
+extern "C" int v3d_debug_mlp_trace(unsigned long long* out_host) {
+  V3D_CUDA(cudaDeviceSynchronize());
+  V3D_CUDA(cudaMemcpyFromSymbol(out_host, g_mlp_trace, sizeof(unsigned long long) * 8));
+  return V3D_OK;
+}
+#endif
 
 extern "C" int v3d_pe_mlp(const float* coords, int M, int E, const float* w1, const float* b1, const float* gamma,
                           const float* beta, float ln_eps, const void* w2_bf16, const float* b2, const void* tokens_in,
@@ -503,6 +737,14 @@ extern "C" int v3d_pe_mlp(const float* coords, int M, int E, const float* w1, co
   p.E = E;
   p.eps = ln_eps;
   cudaStream_t s = (cudaStream_t)stream;
-  if (E % 128 == 0) return launch_mlp<128>(p, w2_bf16, s);
-  return launch_mlp<64>(p, w2_bf16, s);
+  if (E % 128 == 0) {
+    // staging tiles by TMA need two tiles per warp: fits next to the 8-stage W2 ring up to E = 5120
+    if (V3D_MLP_TMA_STAGE && MlpSmem<128, true, V3D_MLP_PARTS>::total(E) + 1024 <= 227 * 1024) {
+      // clusters of two need at least two M tiles
+      if (V3D_MLP_MCAST && (M + kBlockM - 1) / kBlockM >= 2) return launch_mlp<128, true, V3D_MLP_PARTS, true>(p, w2_bf16, s);
+      return launch_mlp<128, true, V3D_MLP_PARTS, false>(p, w2_bf16, s);
+    }
+    return launch_mlp<128, false, 2, false>(p, w2_bf16, s);
+  }
+  return launch_mlp<64, false, 2, false>(p, w2_bf16, s);
 }
