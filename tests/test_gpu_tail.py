@@ -155,3 +155,49 @@ def test_tail_full_size_properties():
     ref = TP.projector_tail(tokens[:2].cpu(), coords[:2].cpu(), E, newline.cpu(), 2, "bilinear").view(2, Go, Go + 1, E)
     d = (o4[:2].cpu().float() - ref.float()).abs()
     assert float((d > 0).float().mean()) <= 1e-3 and float(d.max()) <= 2.0 ** -7 * 8
+
+
+@pytest.mark.parametrize("mode", ["bilinear", "average"])
+def test_pool_commutes_with_the_last_linear_of_the_projector(mode):
+    """projector_tail.project_pool_pe_newline runs the projector's last Linear on the pooled tokens (3.7x fewer GEMM rows).
+    In fp32 the two orders agree to rounding noise (the pool is a convex combination and the bias passes through); in bf16
+    they differ by the roundings that moved: the result must stay within 4 bf16 ulps of the output scale of the reference
+    order (mm_projector -> get_2dPool -> + PE -> add_token_per_grid), element-wise, and agree to 2^-8 of that scale in the
+    mean."""
+    from video_3d_llm_b200 import projector_tail as PT
+    from video_3d_llm_b200.position_encoding import PositionEmbeddingSine3D
+
+    torch.manual_seed(11)
+    V, side, C, E = 3, 27, 256, 1152
+    Go = 14 if mode == "bilinear" else 13  # math.ceil(27 / 2) for the interpolation, 27 // 2 for the 2x2 windows (llava_arch.py:196-206)
+    proj32 = torch.nn.Sequential(torch.nn.Linear(C, E), torch.nn.GELU(), torch.nn.Linear(E, E)).to(DEV).eval()
+    x32 = torch.randn((V, side * side, C), device=DEV)
+    coords = torch.randint(0, 101, (V, Go * Go, 3), device=DEV).float()
+    newline32 = torch.randn(E, device=DEV)
+    pe = PositionEmbeddingSine3D(E)
+    with torch.no_grad():
+        # fp32: algebraic identity
+        a = PT.pool_pe_newline(proj32(x32), stride=2, mode=mode, coords=coords, position_embedding=pe, image_newline=newline32)
+        b = PT.project_pool_pe_newline(x32, proj32, stride=2, mode=mode, coords=coords, position_embedding=pe, image_newline=newline32)
+        assert a.shape == b.shape == (V * Go * (Go + 1), E)
+        scale = a.abs().max().item()
+        assert (a - b).abs().max().item() <= 2e-5 * scale
+        # bf16: the recipe's dtype
+        proj16 = torch.nn.Sequential(torch.nn.Linear(C, E), torch.nn.GELU(), torch.nn.Linear(E, E)).to(DEV).eval()
+        proj16.load_state_dict(proj32.state_dict())
+        proj16 = proj16.to(torch.bfloat16)
+        x16, nl16, c16 = x32.to(torch.bfloat16), newline32.to(torch.bfloat16), coords.to(torch.bfloat16)
+        ref = PT.pool_pe_newline(proj16(x16), stride=2, mode=mode, coords=c16, position_embedding=pe, image_newline=nl16).float()
+        got = PT.project_pool_pe_newline(x16, proj16, stride=2, mode=mode, coords=c16, position_embedding=pe, image_newline=nl16).float()
+        scale = ref.abs().max().item()
+        err = (got - ref).abs()
+        assert err.max().item() <= 4 * 2.0 ** -8 * scale, err.max().item() / scale
+        assert err.mean().item() <= 2.0 ** -8 * scale
+        # newline rows are untouched by the reordering
+        rows = ref.view(V, Go, Go + 1, E)[:, :, Go]
+        assert torch.equal(got.view(V, Go, Go + 1, E)[:, :, Go], rows)
+        # 'max' does not commute: the reference order is kept
+        cm = c16[:, : 13 * 13]
+        m1 = PT.pool_pe_newline(proj16(x16), stride=2, mode="max", coords=cm, position_embedding=pe, image_newline=nl16)
+        m2 = PT.project_pool_pe_newline(x16, proj16, stride=2, mode="max", coords=cm, position_embedding=pe, image_newline=nl16)
+        assert torch.equal(m1, m2)

@@ -8,7 +8,9 @@ model --
 
 `get_2dPool` and `add_token_per_grid` keep the reference's names, arguments and results as functions of explicit
 inputs (the reference reads config/model attributes from `self`); `pool_pe_newline` is the three steps in one
-kernel launch.  The projector's two Linear layers stay with cuBLAS: they are plain library GEMMs.
+kernel launch.  The projector's two Linear layers stay with cuBLAS: they are plain library GEMMs -- but
+`project_pool_pe_newline` runs the last one on the POOLED tokens (the bilinear / average pool is linear with weights
+that sum to one, so it commutes with Linear + bias): 3.7x fewer GEMM rows for the 27x27 -> 14x14 recipe.
 """
 from __future__ import annotations
 
@@ -67,3 +69,34 @@ def get_2dPool(image_feature: torch.Tensor, stride: int = 2, mm_spatial_pool_mod
 def add_token_per_grid(image_feature: torch.Tensor, image_newline: torch.Tensor) -> torch.Tensor:
     """llava_arch.py:307-328 (add_faster_video off): (V, G*G, E) -> (V*G*(G+1), E)."""
     return pool_pe_newline(image_feature, mode="none", image_newline=image_newline)
+
+
+def project_pool_pe_newline(vision_features: torch.Tensor, mm_projector: torch.nn.Module, *, stride: int = 2, mode: str = "bilinear",
+                            coords: torch.Tensor | None = None, position_embedding: PositionEmbeddingSine3D | None = None,
+                            image_newline: torch.Tensor | None = None, flatten: bool = True) -> torch.Tensor:
+    """mm_projector -> get_2dPool -> + PE -> add_token_per_grid (llava/model/multimodal_projector/builder.py:41-48,
+    llava_arch.py:191-210, 515, 307-328) with the pool moved in front of the projector's last Linear.
+
+    `get_2dPool(Linear(h)) == Linear(get_2dPool(h))` in real arithmetic for the bilinear and average modes (every output
+    token is a convex combination of input tokens, and the bias passes through weights that sum to one), so the last
+    Linear -- for `mlp2x_gelu` 3584 x 3584 per token, by far the most expensive step between the vision tower and the
+    language model -- runs on Go*Go = 196 instead of G*G = 729 tokens per frame.  What changes is the rounding: the
+    reference rounds the Linear's 729 outputs to the token dtype and pools them, this rounds the pooled hidden
+    activations and the Linear's 196 outputs; the two results differ by a few ulps of the token dtype (tests/test_gpu_tail.py
+    states the bound), which is why this is an opt-in entry point for a maintainer who edits llava_arch.py:469-536 and
+    not what the overlay launcher installs.  The GEMMs stay library GEMMs (cuBLAS through torch).
+
+    vision_features: (V, G*G, C) vision-tower output.  mm_projector: nn.Linear, or an nn.Sequential whose last module is an
+    nn.Linear (`linear`, `mlpNx_gelu` of the reference's builder); anything else, and mode 'max', runs the reference order."""
+    cabi.require_cuda(vision_features, "vision_features")
+    last = mm_projector if isinstance(mm_projector, torch.nn.Linear) else None
+    head = None
+    if isinstance(mm_projector, torch.nn.Sequential) and len(mm_projector) > 0 and isinstance(mm_projector[-1], torch.nn.Linear):
+        last, head = mm_projector[-1], mm_projector[:-1]
+    if last is None or mode not in ("bilinear", "average"):
+        return pool_pe_newline(mm_projector(vision_features), stride=stride, mode=mode, coords=coords, position_embedding=position_embedding,
+                               image_newline=image_newline, flatten=flatten)
+    h = vision_features if head is None else head(vision_features)
+    pooled = pool_pe_newline(h.contiguous(), stride=stride, mode=mode)  # (V, Go*Go, hidden): k_pool_pe_grid, pool only
+    y = last(pooled)
+    return pool_pe_newline(y, mode="none", coords=coords, position_embedding=position_embedding, image_newline=image_newline, flatten=flatten)
