@@ -314,6 +314,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_fused_ring(const FusedParam
     if (lane != 0) return;
     const unsigned char* src = reinterpret_cast<const unsigned char*>(p.tokens_in) + (size_t)blockIdx.x * item_bytes;
     const size_t src_step = (size_t)gridDim.x * item_bytes;
+    // The depth rows of the first patch rows are on the critical path of the whole CTA (nothing streams before the pool
+    // groups have published a row): let them reach DRAM before the ring's 100+ KB of token loads queue up in front
+    mbar_wait_addr(dbar0, 0u);
     uint32_t slot = 0, use_parity = 0;  // parity of the `empty` phase that frees the slot for its next use (first lap: none)
     bool first_lap = true;
     for (int ord = 0; ord < nk; ++ord, src += src_step) {

@@ -6,18 +6,24 @@
 // The 512-wide hidden activations are produced inside the kernel and never touch HBM; the 512 -> E
 // contraction (the only dense contraction on the path) runs on the 5th-generation tensor cores.
 //
-// One persistent CTA per SM, 256 threads, warp-specialised:
+// One persistent CTA per SM, warp-specialised (640 threads in the shipped variant):
 //   warp 0    TMA producer: W2 tiles (BLOCK_N rows x 64 k, 128-byte swizzle) through a ring of mbarriers
 //   warp 1    MMA issuer  : tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16; owns TMEM alloc
-//   warps 4-11 (two per TMEM lane quadrant: one for each half of the k range / of an N tile's columns)
+//   warps 4.. (PARTS per TMEM lane quadrant -- 4 in the shipped variant -- each with a 1/PARTS share of the k range when the
+//             A operand is built and of an N tile's columns in the epilogue)
 //             (a) build the A operand of an M tile (128 tokens x 512 hidden, bf16): Linear(3,512) + LayerNorm
 //             + ReLU per token, one thread per token row = one TMEM lane, written with tcgen05.st straight
-//             into TENSOR MEMORY (256 columns: two bf16 per 32-bit cell), from where the MMA reads it;
-//             (b) epilogue: tcgen05.ld the fp32 accumulator, + bias, round to bf16, + tokens, store.
+//             into TENSOR MEMORY (256 columns: two bf16 per 32-bit cell), from where the MMA reads it.  The A operand of
+//             the NEXT M tile is built as soon as the last accumulator of the current one is full, before it is drained;
+//             (b) epilogue: tcgen05.ld the fp32 accumulator, + bias, round to bf16, + tokens, store.  Token blocks arrive
+//             in per-warp staging tiles by cp.async.bulk.tensor (two tiles per warp, the next N tile's block in flight),
+//             results leave from the same tiles by TMA stores; the (128 x BLOCK_N) token block of an N tile is pulled
+//             into L2 two tiles ahead by cp.async.bulk.prefetch.tensor.
 // TMEM map (512 columns): [0, 2*BLOCK_N) double-buffered fp32 accumulators (the MMAs of N tile i+1 overlap
 // the epilogue of N tile i), [256, 512) the A operand, resident for all N tiles of its M tile.  Keeping A out
 // of shared memory leaves room for a deep W2 ring: with A in smem (128 KB) only 3 x 16 KB of W2 fitted in
-// flight and the tensor pipe starved on W2 tiles (24 % active, profiles/r1i_*).
+// flight and the tensor pipe starved on W2 tiles (24 % active, profiles/r1i_*).  Measured limits and what was tried:
+// DESIGN.md section 4.4.
 #include <cuda.h>
 
 #include "v3d_common.cuh"
