@@ -351,7 +351,7 @@ def reference_call_sequence(scene, tokens, pe_module, patch):
     return tokens + pe_module(d.flatten(1, 2).detach())
 
 
-def e2e_leg(rank, world, dev, vp, samples, tokens, steps: int, batch_scenes: int, threads: int):
+def e2e_leg(rank, world, dev, vp, samples, tokens, steps: int, batch_scenes: int, threads: int, pinned_cache: bool = False):
     """End to end through the public API, host work inside the timed loop (see the module docstring).  Returns
     (frames/s over all ranks, h2d bytes, d2h bytes, note)."""
     import torch.distributed as dist
@@ -361,7 +361,8 @@ def e2e_leg(rank, world, dev, vp, samples, tokens, steps: int, batch_scenes: int
 
     pe = PositionEmbeddingSine3D(EMB)
     pe.defer_add = True
-    loader = VU.SceneBatchLoader(vp, samples, batch_scenes=batch_scenes, threads=threads, prefetch=2, loop=True)
+    loader = VU.SceneBatchLoader(vp, samples, batch_scenes=batch_scenes, threads=threads, prefetch=2, loop=True, pinned_cache=pinned_cache,
+                                 device=dev)
     it = iter(loader)
     up = torch.cuda.Stream(device=dev)
     cur = torch.cuda.current_stream(dev)
@@ -387,6 +388,7 @@ def e2e_leg(rank, world, dev, vp, samples, tokens, steps: int, batch_scenes: int
             probe[b].copy_(out[:, 0, :64])
         for t in (hd.depth, hd.poses, hd.intrinsics):
             t.record_stream(cur)
+        loader.mark_consumed(hd)
         h_probe[i % 2].copy_(probe, non_blocking=True)
         read[i % 2] = torch.cuda.Event()
         read[i % 2].record(cur)
@@ -976,6 +978,9 @@ def run_ours(args):
         e2e_value, h2d, d2h, e2e_ms = e2e_leg(rank, world, dev, vp, samples, tokens, Ke, SCENES, threads)
         # BASELINE configs[0]: one 32-frame scene per step (what per_device_train_batch_size 1 launches), same path
         c1_e2e, c1_h2d, c1_d2h, c1_ms = e2e_leg(rank, world, dev, vp, samples, tokens, 4 * Ke, 1, threads)
+        # the same loop with the scenes' resampled depth held in pinned memory (ScenePack.pin): batches are gathered by the DMA
+        # engines, the CPU copies nothing -- the PCIe-bound ceiling of the end-to-end path for datasets that fit in host memory
+        pc_e2e, pc_h2d, pc_d2h, pc_ms = e2e_leg(rank, world, dev, vp, samples, tokens, Ke, SCENES, threads, pinned_cache=True)
     finally:
         shutil.rmtree(root, ignore_errors=True)
     limits = host_limits_leg(rank, world, dev, threads)
@@ -1070,6 +1075,11 @@ def run_ours(args):
                             "(average_coordinate_in_patch -> discrete_coords -> tokens + world_position_embedding) = one fused launch "
                             "reading the resampled depth in place -> D2H of a result slice; one step in flight; vision tokens are "
                             "produced on the device by the vision tower and stay resident"},
+            "e2e_pinned_scene_cache": {"value": pc_e2e, "unit": "frames/s", "ms_per_step": pc_ms, "h2d_bytes_per_step": int(pc_h2d),
+                                       "d2h_bytes_per_step": int(pc_d2h),
+                                       "note": "as e2e, but every scene's resampled depth sits in pinned host memory (copied there once, "
+                                               "ScenePack.pin; 286 KB per frame): a batch is 512 DMAs straight out of it (v3d_h2d_gather), the "
+                                               "CPU moves no depth"},
             "gpu_launches": K,  # timed region: K launches of k_fused_ring (e2e: 16 per step; mc: 4 per step)
             "clocks": clk,
             "config1": config1,

@@ -101,6 +101,12 @@ int v3d_scatter_resampled_depth(const void* packed_dev, void* depth_dev, int dep
  * loop of llava/video_utils.py:212-218 on the packed-scene path. */
 int v3d_host_gather(void* dst_host, const void* const* src_host, size_t bytes_each, int n_blocks, int n_threads);
 
+/* The same gather with the copy done by the DMA engines: n_blocks blocks of bytes_each bytes, block i from the PINNED host
+ * address src_host[i], to dst_dev + i * bytes_each, stream-ordered (one cudaMemcpyAsync per run of blocks that are adjacent
+ * in host memory).  For loaders that keep their packed scenes in pinned memory (scene_pack.ScenePack.pin()): the CPU
+ * then moves no depth at all.  No reference equivalent. */
+int v3d_h2d_gather(void* dst_dev, const void* const* src_host, size_t bytes_each, int n_blocks, v3d_stream_t stream);
+
 /* ---- helpers on materialised coordinates (API parity with the reference's call structure) --
  * v3d_pool_coords replaces llava/model/llava_arch.py:213-223 `average_coordinate_in_patch`,
  * :225-239 `minmax_coordinate_in_patch`, :241-257 `sample_n_points`.

@@ -896,3 +896,38 @@ def test_algebraic_patch_means_equal_the_operator_sequence(patch, E):
             assert torch.equal(inplace.view(torch.int16), b.view(torch.int16))
         cases += 1
     assert cases == 7
+
+
+def test_scene_batch_loader_pinned_cache_equals_the_host_path(dataset, tmp_path):
+    """SceneBatchLoader(pinned_cache=True): scenes held in pinned memory, batches gathered by the DMA engines into device
+    buffers (v3d_h2d_gather) -- the same bytes as the host-gather path, over more batches than ring slots (slot reuse waits
+    for mark_consumed), and the fused front end gives the same tokens from either handle."""
+    from video_3d_llm_b200 import scene_pack
+    from video_3d_llm_b200 import video_utils as VU
+
+    kw = dict(video_folder=os.path.join(dataset, "data"), annotation_dir=os.path.join(dataset, "data", "embodiedscan"), voxel_size=0.1,
+              min_xyz_range=[-15, -15, -5], max_xyz_range=[15, 15, 5], frame_sampling_strategy="uniform",
+              metadata_dir=os.path.join(dataset, "data", "metadata"))
+    vp = VU.VideoProcessor(**kw)
+    video_id = "scannet/scene0003_00"  # 480 x 640
+    scene_pack.pack_scene(vp, video_id, scene_pack.pack_path(str(tmp_path), video_id), resample=(384, "center_crop"))
+    vp_pack = VU.VideoProcessor(pack_dir=str(tmp_path), lazy=True, **kw)
+    picks = [vp_pack.sample_frame_files(video_id, force_sample=True, frames_upbound=n) for n in (3, 3, 3)]
+    all_files = vp_pack.sample_frame_files(video_id, force_sample=True, frames_upbound=4)
+    samples = [(video_id, all_files[i:i + 3] if len(all_files[i:i + 3]) == 3 else all_files[:3]) for i in range(2)] + [(video_id, picks[0])]
+    host = VU.SceneBatchLoader(vp_pack, samples, batch_scenes=1, threads=2, prefetch=2, loop=True, pin=True)
+    dev = VU.SceneBatchLoader(vp_pack, samples, batch_scenes=1, threads=2, prefetch=2, loop=True, pinned_cache=True, device=DEV)
+    fe = FrontEnd(device=DEV, patch_size=14, embedding_size=1152)
+    tok = synthetic.make_tokens(5, 3, fe.tokens_per_frame, 1152).to(DEV)
+    ih, idv = iter(host), iter(dev)
+    for n in range(9):  # more than the 4 device ring slots
+        a, b = next(ih), next(idv)
+        assert b.depth.is_cuda and "_ready_event" in b.__dict__
+        bd = b.to(DEV)  # waits for the loader's copy stream
+        assert torch.equal(a.depth.to(DEV), bd.depth) and torch.equal(a.poses.to(DEV), bd.poses) and torch.equal(a.intrinsics.to(DEV), bd.intrinsics)
+        out_a = fe.from_resampled(a.depth[0], a.poses[0], a.intrinsics[0], tokens=tok)
+        out_b = fe.from_resampled(bd.depth[0], bd.poses[0], bd.intrinsics[0], tokens=tok)
+        assert torch.equal(out_a.view(torch.int16), out_b.view(torch.int16))
+        dev.mark_consumed(bd)
+    host.close()
+    dev.close()

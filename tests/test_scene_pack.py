@@ -168,3 +168,37 @@ def test_stored_resampled_stack_and_lazy_handle(dataset, tmp_path):
     v1.write_bytes(bytes(hdr) + body)
     pk1 = scene_pack.ScenePack(str(v1))
     assert pk1.resampled is None and np.array_equal(pk1.depth, pk.depth)
+
+
+def test_scene_batch_loader_batches_and_thread_safety(dataset, tmp_path):
+    """SceneBatchLoader (host path): every batch holds exactly the frames pack.load_resampled gives, batches come in order and
+    wrap with loop=True, and loader threads racing for the same scene get ONE mapping (a replaced ScenePack would be
+    unmapped under a running native gather -- the segfault of round 2)."""
+    import threading
+
+    vp = _vp(dataset)
+    ids = [v for v in vp.scene if vp.scene[v]["images"]][:2]
+    for video_id in ids:
+        scene_pack.pack_scene(vp, video_id, scene_pack.pack_path(str(tmp_path), video_id), resample=(384, "center_crop"))
+    vp_pack = _vp(dataset, pack_dir=str(tmp_path), lazy=True)
+    sizes = {v: scene_pack.ScenePack(scene_pack.pack_path(str(tmp_path), v)) for v in ids}
+    ids = [v for v in ids if (sizes[v].H, sizes[v].W) == (sizes[ids[0]].H, sizes[ids[0]].W)]
+    samples = [(v, vp_pack.sample_frame_files(v, force_sample=True, frames_upbound=3)) for v in ids] * 2
+    # the race: many threads ask for the same scene's pack at once
+    got = []
+    vp_race = _vp(dataset, pack_dir=str(tmp_path), lazy=True)
+    ts = [threading.Thread(target=lambda: got.append(vp_race._pack(ids[0]))) for _ in range(16)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert all(g is got[0] for g in got)
+    loader = VU.SceneBatchLoader(vp_pack, samples, batch_scenes=1, threads=3, prefetch=2, loop=True, pin=False)
+    it = iter(loader)
+    for n in range(2 * len(samples) + 1):
+        h = next(it)
+        video_id, files = samples[n % len(samples)]
+        d, p, k = vp_pack._pack(video_id).load_resampled([scene_pack.frame_number(f) for f in files])
+        assert h.batched and h.resampled and tuple(h.depth.shape) == (1, 3, 384, 384)
+        assert torch.equal(h.depth[0], d) and torch.equal(h.poses[0], p) and torch.equal(h.intrinsics[0], k)
+    loader.close()
+    with pytest.raises(ValueError):
+        VU.SceneBatchLoader(vp_pack, [], batch_scenes=1)

@@ -26,7 +26,7 @@ MC_RECORD_INTS = 2 * MC_MAX_PICK + 4
 
 # every symbol include/v3d.h declares (tests check that the library exports them all)
 SYMBOLS = (
-    "v3d_version", "v3d_last_error", "v3d_selftest_division", "v3d_pool_points", "v3d_unproject", "v3d_upload_depth_window", "v3d_expand_depth_window", "v3d_scatter_resampled_depth", "v3d_host_gather",
+    "v3d_version", "v3d_last_error", "v3d_selftest_division", "v3d_pool_points", "v3d_unproject", "v3d_upload_depth_window", "v3d_expand_depth_window", "v3d_scatter_resampled_depth", "v3d_host_gather", "v3d_h2d_gather",
     "v3d_boundary", "v3d_pool_coords",
     "v3d_discretize", "v3d_pe_table_bytes", "v3d_pe_table_build", "v3d_pe_sine3d", "v3d_frontend_pe",
     "v3d_mc_hash_slots", "v3d_mc_sample", "v3d_mc_voxelize", "v3d_mc_greedy", "v3d_mc_voxel_ids", "v3d_pe_mlp", "v3d_object_patch_masks", "v3d_object_patch_masks_depth", "v3d_masked_token_mean",
@@ -106,6 +106,7 @@ def load():
     lib.v3d_expand_depth_window.argtypes = [vp, vp, sz, sz, sz, sz, sz, sz, vp]
     lib.v3d_scatter_resampled_depth.argtypes = [vp, vp, i, i, i, i, vp, vp, i, i, vp]
     lib.v3d_host_gather.argtypes = [vp, vp, sz, i, i]
+    lib.v3d_h2d_gather.argtypes = [vp, vp, sz, i, vp]
     lib.v3d_pool_coords.argtypes = [vp, i, i, i, i, i, vp, vp]
     lib.v3d_discretize.argtypes = [vp, sz, vp, vp, i, f, i, i, vp, vp]
     lib.v3d_pe_table_bytes.argtypes, lib.v3d_pe_table_bytes.restype = [i, i, i, i], sz

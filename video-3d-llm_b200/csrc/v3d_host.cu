@@ -1,4 +1,4 @@
-// v3d_host.cu -- host-side loader helper (C ABI: include/v3d.h).  No device code.
+// v3d_host.cu -- host-side loader helpers (C ABI: include/v3d.h).  No device code.
 //
 // The model-side front end runs at microseconds per frame, so the end-to-end rate is set by how fast a training
 // sample's depth frames get from the page cache (packed scenes, scene_pack.py) into pinned memory.  Python threads
@@ -120,6 +120,24 @@ int v3d_host_gather(void* dst_host, const void* const* src_host, size_t bytes_ea
     const size_t len = off + piece <= bytes_each ? piece : bytes_each - off;
     memcpy(dst + (size_t)b * bytes_each + off, static_cast<const unsigned char*>(src_host[b]) + off, len);
   });
+  return V3D_OK;
+}
+
+
+int v3d_h2d_gather(void* dst_dev, const void* const* src_host, size_t bytes_each, int n_blocks, v3d_stream_t stream) {
+  if (n_blocks == 0) return V3D_OK;
+  V3D_REQUIRE(dst_dev && src_host, V3D_E_ARG, "v3d_h2d_gather: null pointer");
+  V3D_REQUIRE(n_blocks > 0 && bytes_each > 0, V3D_E_ARG, "v3d_h2d_gather: bad sizes");
+  unsigned char* dst = static_cast<unsigned char*>(dst_dev);
+  cudaStream_t s = (cudaStream_t)stream;
+  // consecutive blocks that are also consecutive in host memory go out as one DMA
+  int i = 0;
+  while (i < n_blocks) {
+    int j = i + 1;
+    while (j < n_blocks && static_cast<const unsigned char*>(src_host[j]) == static_cast<const unsigned char*>(src_host[j - 1]) + bytes_each) ++j;
+    V3D_CUDA(cudaMemcpyAsync(dst + (size_t)i * bytes_each, src_host[i], (size_t)(j - i) * bytes_each, cudaMemcpyHostToDevice, s));
+    i = j;
+  }
   return V3D_OK;
 }
 

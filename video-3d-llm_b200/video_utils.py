@@ -178,11 +178,15 @@ class LazyWorldCoords:
         return self.shape[0]
 
     def _like(self, depth=None, poses=None, intrinsics=None, dtype=None, batched=None, clamp="same"):
-        return LazyWorldCoords(self.depth if depth is None else depth, self.poses if poses is None else poses,
-                               self.intrinsics if intrinsics is None else intrinsics, self.crop_size, self.strategy,
-                               self.clamp if isinstance(clamp, str) else clamp,
-                               self.dtype if dtype is None else dtype, self.batched if batched is None else batched,
-                               resampled=self.resampled, src_hw=self.src_hw)
+        out = LazyWorldCoords(self.depth if depth is None else depth, self.poses if poses is None else poses,
+                              self.intrinsics if intrinsics is None else intrinsics, self.crop_size, self.strategy,
+                              self.clamp if isinstance(clamp, str) else clamp,
+                              self.dtype if dtype is None else dtype, self.batched if batched is None else batched,
+                              resampled=self.resampled, src_hw=self.src_hw)
+        for name in ("_ready_event", "_loader_slot"):  # set by SceneBatchLoader(pinned_cache=True) on device-resident batches
+            if name in self.__dict__:  # (not hasattr: unknown public names fall through to the materialised tensor)
+                out.__dict__[name] = self.__dict__[name]
+        return out
 
     def _scene(self, b: int):
         """Scene b of a batched handle, with its own clamp."""
@@ -200,6 +204,9 @@ class LazyWorldCoords:
                 device, dtype = a.device, a.dtype
         out = self
         if device is not None:
+            ev = self.__dict__.get("_ready_event")
+            if ev is not None and self.depth.is_cuda:
+                torch.cuda.current_stream(self.depth.device).wait_event(ev)  # filled by a loader's copy stream
             nb = bool(kwargs.get("non_blocking", False))
             out = out._like(self.depth.to(device, non_blocking=nb), self.poses.to(device, non_blocking=nb),
                             self.intrinsics.to(device, non_blocking=nb))
@@ -631,7 +638,7 @@ class SceneBatchLoader:
     (crop_size, strategy) the handles carry those samples (48 % of the bytes of full ScanNet frames)."""
 
     def __init__(self, vp: "VideoProcessor", samples, batch_scenes: int, crop_size: int = 384, strategy: str = "center_crop",
-                 threads: int = 8, prefetch: int = 2, loop: bool = False, pin: bool = True):
+                 threads: int = 8, prefetch: int = 2, loop: bool = False, pin: bool = True, pinned_cache: bool = False, device=None):
         from concurrent.futures import ThreadPoolExecutor
 
         from . import scene_pack
@@ -651,9 +658,22 @@ class SceneBatchLoader:
         shape = (crop_size, crop_size) if self.resampled else (p0.H, p0.W)
         store = torch.int16 if p0.depth_dtype == np.uint16 else torch.int32
         self._frame_numbers = [[scene_pack.frame_number(f) for f in files] for _, files in self.samples]
-        self._ring = [(torch.empty((self.B, self.V) + shape, dtype=store, pin_memory=pin),
-                       torch.empty((self.B, self.V, 4, 4), dtype=torch.float32, pin_memory=pin),
-                       torch.empty((self.B, self.V, 4, 4), dtype=torch.float32, pin_memory=pin)) for _ in range(self.prefetch + 1)]
+        # pinned_cache: every scene's stack is copied into pinned memory once (ScenePack.pin) and a batch is gathered by the
+        # DMA engines straight into a ring of DEVICE buffers on the loader's own stream -- no CPU copy per batch; the
+        # yielded handles are device-resident and carry the event to wait for (LazyWorldCoords.to does)
+        self.pinned_cache = bool(pinned_cache)
+        self._dev = None
+        if self.pinned_cache:
+            self._dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+            self._stream = torch.cuda.Stream(device=self._dev)
+            self._consumed = [None] * (self.prefetch + 2)
+            self._ring = [(torch.empty((self.B, self.V) + shape, dtype=store, device=self._dev),
+                           torch.empty((self.B, self.V, 4, 4), dtype=torch.float32, pin_memory=True),
+                           torch.empty((self.B, self.V, 4, 4), dtype=torch.float32, pin_memory=True)) for _ in range(self.prefetch + 2)]
+        else:
+            self._ring = [(torch.empty((self.B, self.V) + shape, dtype=store, pin_memory=pin),
+                           torch.empty((self.B, self.V, 4, 4), dtype=torch.float32, pin_memory=pin),
+                           torch.empty((self.B, self.V, 4, 4), dtype=torch.float32, pin_memory=pin)) for _ in range(self.prefetch + 1)]
         # batches are assembled by `prefetch` Python threads, each issuing ONE native multi-threaded gather per batch
         self._pool = ThreadPoolExecutor(max_workers=self.prefetch, thread_name_prefix="v3d-load")
         self.threads = max(1, int(threads))
@@ -679,6 +699,8 @@ class SceneBatchLoader:
             pack = self.vp._pack(video_id)
             if pack is None or (pack.H, pack.W) != self.src_hw or (pack.resampled_for == (self.crop_size, self.strategy)) != self.resampled:
                 raise ValueError(f"{video_id}: packed scene missing or of a different layout than the first sample's")
+            if self.pinned_cache and not pack.pinned:
+                pack.pin()  # once per scene
             rows = pack.rows(self._frame_numbers[idx])
             src = pack.resampled if self.resampled else pack.depth
             base = src.ctypes.data
@@ -687,6 +709,16 @@ class SceneBatchLoader:
             poses[b].numpy()[...] = pack.poses[rows]
             intr[b].numpy()[...] = pack.intr[None]
             clamps.append(self.vp._clamp_for(video_id, self._do_norm))
+        if self.pinned_cache:
+            with torch.cuda.device(self._dev):
+                if self._consumed[slot] is not None:
+                    self._stream.wait_event(self._consumed[slot])  # the consumer's kernels on the slot's previous batch
+                cabi.check(self._lib.v3d_h2d_gather(depth.data_ptr(), srcs, frame_bytes, self.B * self.V, self._stream.cuda_stream), "v3d_h2d_gather")
+                with torch.cuda.stream(self._stream):
+                    poses_d, intr_d = poses.to(self._dev, non_blocking=True), intr.to(self._dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._stream)
+            return clamps, poses_d, intr_d, ev
         cabi.check(self._lib.v3d_host_gather(depth.data_ptr(), srcs, frame_bytes, self.B * self.V, self.threads), "v3d_host_gather")
         return clamps
 
@@ -707,10 +739,28 @@ class SceneBatchLoader:
             if not pending:
                 return
             slot, fut = pending.pop(0)
-            clamps = fut.result()
+            res = fut.result()
             depth, poses, intr = self._ring[slot]
-            yield LazyWorldCoords(depth, poses, intr, self.crop_size, self.strategy, None if all(c is None for c in clamps) else clamps,
-                                  batched=True, resampled=self.resampled, src_hw=self.src_hw)
+            ev = None
+            if self.pinned_cache:
+                clamps, poses, intr, ev = res
+            else:
+                clamps = res
+            h = LazyWorldCoords(depth, poses, intr, self.crop_size, self.strategy, None if all(c is None for c in clamps) else clamps,
+                                batched=True, resampled=self.resampled, src_hw=self.src_hw)
+            if ev is not None:
+                h._ready_event, h._loader_slot = ev, slot
+            yield h
+
+    def mark_consumed(self, handle) -> None:
+        """pinned_cache mode: call after the last launch that reads a yielded handle (on the current stream); the loader's
+        copies into the handle's ring slot wait for it.  Without it a handle must not be in use any more when
+        prefetch + 1 further batches have been requested."""
+        slot = handle.__dict__.get("_loader_slot")
+        if self.pinned_cache and slot is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self._dev))
+            self._consumed[slot] = ev
 
     def close(self):
         """Cancel queued batches and WAIT for the one being gathered: it writes into the pinned ring, which must outlive it."""
