@@ -15,6 +15,8 @@ Printed JSON line (rank 0):
              VideoProcessor(pack_dir) / SceneBatchLoader (host copies into pinned memory INSIDE the timed loop) -> H2D ->
              the reference's call sequence per scene (average_coordinate_in_patch -> discrete_coords ->
              tokens + world_position_embedding(coords)) -> D2H read of a result slice
+  e2e_pinned_scene_cache   the e2e loop with the scenes' resampled depth held in pinned host memory (copied there once):
+             batches are gathered by the DMA engines, no CPU copy per batch -- the PCIe-bound ceiling of the path
   roofline   algorithmic bytes per launch / average launch time vs the measured HBM copy peak
   cpu_baseline  the reference's torch-CPU operator sequence (oracle/torch_port.py) on the host cores
   overlay_path  device-resident cost of that call sequence (what the unchanged scripts launch under the overlay) for
