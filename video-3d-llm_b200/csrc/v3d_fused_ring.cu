@@ -205,6 +205,7 @@ __device__ __noinline__ bool finalize_patch(int a, int j, int item, int gi, int 
   const int o = pe_row_offset(pv, a, g, true);
   const bool ok = mono && pv == pv_hi && o >= 0;  // NaN (camera not ok, non-finite pose) fails the comparison
   if (ok) {
+    V3D_CHECK(j >= 0 && j < G && a >= 0 && a < 3);
     s_off_item[j * 4 + a] = o * 2;  // byte offset into the table
     if (pe_coords_out) pe_coords_out[((size_t)item * G + j) * 3 + a] = pv;
   } else {
@@ -232,6 +233,7 @@ __device__ __noinline__ void exact_coord(int a, int j, int item, int f, int gi, 
     const float d = (float)*reinterpret_cast<const uint16_t*>(s_depth_item + (size_t)dy * span + (stored * 2 - col_lo_byte));
     float w[3];
     unproject_px(cam, d, __fsub_rn((float)sc, cam.cx), __fsub_rn((float)sr, cam.cy), ds, w[0], w[1], w[2]);
+    V3D_CHECK(stored * 2 - col_lo_byte >= 0 && stored * 2 - col_lo_byte + 2 <= span && dy < P);
     scratch[px] = (a == 0) ? w[0] : (a == 1 ? w[1] : w[2]);
   }
   __syncwarp();
@@ -324,6 +326,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_fused_ring(const FusedParam
       for (int j = 0; j < r.n_stage; ++j, c0 += r.stage_chunks) {
         if (!first_lap) mbar_wait_addr(empty0 + 8u * slot, use_parity);
         const uint32_t bytes = (uint32_t)min(r.stage_chunks, r.item_chunks - c0) * 16u;
+        V3D_CHECK(slot < (uint32_t)r.slots && bytes <= stage_bytes && bytes > 0u);
+        V3D_CHECK((size_t)(src - reinterpret_cast<const unsigned char*>(p.tokens_in)) + (size_t)c0 * 16 + bytes <= (size_t)r.n_items * item_bytes);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + 8u * slot), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ring_base + slot * stage_bytes),
                      "l"(src + (size_t)c0 * 16), "r"(bytes), "r"(full0 + 8u * slot)
@@ -399,11 +403,14 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_fused_ring(const FusedParam
           const int c1 = c0 + GT;
           const bool has1 = c1 < p.Sp;
           uint32_t a0 = dbase + 2u * (uint32_t)(p.resampled ? c0 : __ldg(p.col_map + c0));
-          uint32_t a1 = dbase + 2u * (uint32_t)(has1 ? (p.resampled ? c1 : __ldg(p.col_map + c1)) : 0);
+          uint32_t a1 = has1 ? dbase + 2u * (uint32_t)(p.resampled ? c1 : __ldg(p.col_map + c1)) : a0;  // no second column: re-read the first
           unsigned s00 = 0u, s20 = 0u, mx0 = 0u, s01 = 0u, s21 = 0u, mx1 = 0u;
           uint32_t dvp = dv0;
 #pragma unroll 4
           for (int dy = 0; dy < P; ++dy, dvp += 4u, a0 += (uint32_t)p.span, a1 += (uint32_t)p.span) {
+            V3D_CHECK(a0 >= smem_u32(s_depth) + (uint32_t)(b * m.depth_stride) && a0 + 2u <= smem_u32(s_depth) + (uint32_t)((b + 1) * m.depth_stride));
+            V3D_CHECK(a1 >= smem_u32(s_depth) + (uint32_t)(b * m.depth_stride) && a1 + 2u <= smem_u32(s_depth) + (uint32_t)((b + 1) * m.depth_stride));
+            V3D_CHECK(dvp + 4u <= smem_u32(s_dv + p.Sp));
             const unsigned dv = (unsigned)lds_i32(dvp);
             const unsigned d0 = lds_u16(a0), d1 = lds_u16(a1);
             s00 += d0;
@@ -413,6 +420,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_fused_ring(const FusedParam
             s21 += d1 * dv;
             mx1 = max(mx1, d1);
           }
+          V3D_CHECK(c0 < p.Sp && grp < r.pool_groups);
           cs[c0] = s00;
           cs[p.Sp + c0] = s20;
           cs[2 * p.Sp + c0] = mx0;
@@ -480,9 +488,12 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_fused_ring(const FusedParam
     for (int u = 0; u < 2; ++u) {
       act[u] = valid[u] && tok0 + tl[u] < G;
       if (act[u]) {
+        V3D_CHECK(off_stage + oa[u] + 4u <= smem_u32(s_off) + (uint32_t)(kItemSlots * G * n_off) * 4u);
+        V3D_CHECK((size_t)(uint32_t)lds_i32(off_stage + oa[u]) + ka[u] + 16 <= pe_table_elems(p.g) * 2);
         pe[u] = ldg_v4(table_bytes + ((uint32_t)lds_i32(off_stage + oa[u]) + ka[u]));
         if (STRADDLE) {
           if (two[u]) {
+            V3D_CHECK((size_t)(uint32_t)lds_i32(off_stage + ob[u]) + kb[u] + 16 <= pe_table_elems(p.g) * 2);
             const uint4 q = ldg_v4(table_bytes + ((uint32_t)lds_i32(off_stage + ob[u]) + kb[u]));
             pe[u].x |= q.x;
             pe[u].y |= q.y;
@@ -512,7 +523,12 @@ __global__ void __launch_bounds__(kRingThreads, 1) k_fused_ring(const FusedParam
         const uint32_t src = ring_t + slot * stage_bytes;
 #pragma unroll
         for (int u = 0; u < 2; ++u)
-          if (act[u]) tv[u] = lds_v4(src + (uint32_t)(u * kStreamThreads * 16));
+          if (act[u]) {
+            V3D_CHECK(slot < (uint32_t)r.slots && src + (uint32_t)(u * kStreamThreads * 16) + 16u <= ring_base + (uint32_t)r.slots * stage_bytes);
+            V3D_CHECK((size_t)(out_stage - reinterpret_cast<unsigned char*>(p.pe_out)) + (size_t)(u * kStreamThreads * 16) + 16 <=
+                      (size_t)r.n_items * item_bytes);
+            tv[u] = lds_v4(src + (uint32_t)(u * kStreamThreads * 16));
+          }
         __syncwarp();
         if (lane == 0) mbar_arrive_addr(empty0 + 8u * slot);  // this warp has read its chunks of the slot
 #pragma unroll
