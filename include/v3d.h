@@ -289,6 +289,13 @@ int v3d_object_patch_masks_depth(const void* depth, int depth_dtype, const float
                                  float depth_scale, const int32_t* row_map, const int32_t* col_map, const float* clamp_lo_hi_host,
                                  int coord_dtype, int patch, int grid, const float* boxes, int K, int threshold, uint8_t* masks_out,
                                  v3d_stream_t stream);
+/* the same with the K boxes given as (min x, min y, min z, max x, max y, max z) -- the bounds the reference's loop forms per
+ * object (llava_arch.py:363-364), in whatever dtype it forms them, widened to fp32 by the caller: what the overlay's lazy
+ * handle launches when the unchanged loop compares against a slice of world_coords */
+int v3d_object_patch_masks_depth_bounds(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
+                                        float depth_scale, const int32_t* row_map, const int32_t* col_map, const float* clamp_lo_hi_host,
+                                        int coord_dtype, int patch, int grid, const float* min_max_xyz, int K, int threshold,
+                                        uint8_t* masks_out, v3d_stream_t stream);
 int v3d_masked_token_mean(const void* tokens_bf16, int T, int C, const uint8_t* masks, int K, void* out_bf16, v3d_stream_t stream);
 
 /* ---- learned-projection PE (tensor cores) ----------------------------------------------------

@@ -53,7 +53,7 @@ class LaunchLog:
     """Names of the library entry points called while active (wraps the ctypes functions of the loaded library)."""
 
     NAMES = ("v3d_frontend_pe", "v3d_pe_sine3d", "v3d_pool_pe_grid", "v3d_unproject", "v3d_pool_coords", "v3d_discretize", "v3d_pe_mlp",
-             "v3d_object_patch_masks_depth", "v3d_object_patch_masks", "v3d_masked_token_mean")
+             "v3d_object_patch_masks_depth", "v3d_object_patch_masks_depth_bounds", "v3d_object_patch_masks", "v3d_masked_token_mean")
 
     def __enter__(self):
         from video_3d_llm_b200 import cabi
@@ -166,6 +166,24 @@ def test_mlp_pe_and_object_proposals(dataset, monkeypatch):
     o_ref, o_got = ref[2].float(), got[2].float()
     assert o_got.shape == o_ref.shape and float((o_got - o_ref).abs().max()) <= 2.0 ** -5 * max(1.0, float(o_ref.abs().max()))
     assert "v3d_pe_mlp" in calls
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("object_feature_type", ["patch14", "patch27"])
+def test_object_proposal_loop_ends_in_one_mask_launch(dataset, monkeypatch, object_feature_type, dtype):
+    """The reference's inlined object loop (llava_arch.py:351-378) on a lazy handle: slice, reshape, transpose, flatten, the two
+    comparisons, all / sum / >= are recorded (lazy_objects.py) and the first `.view()` of a mask (:485 / :487) evaluates every
+    object's mask in ONE v3d_object_patch_masks_depth_bounds launch straight from depth -- no (V,384,384,3) tensor
+    (no v3d_unproject), and object features equal to the reference arm's."""
+    ref, got, calls = _arms(dataset, monkeypatch, "avg-discrete-sin3d", dtype, use_objects=True, object_feature_type=object_feature_type)
+    assert calls.count("v3d_object_patch_masks_depth_bounds") == 1, calls
+    assert "v3d_unproject" not in calls, calls
+    _assert_embeds(ref, got, dtype)
+    o_ref, o_got = ref[2].float(), got[2].float()
+    assert o_got.shape == o_ref.shape
+    tol = {torch.float32: 2.0 ** -18, torch.bfloat16: 2.0 ** -6}[dtype]
+    assert float((o_got - o_ref).abs().max()) <= tol * max(1.0, float(o_ref.abs().max()))
+    assert float(o_ref.abs().max()) > 0  # some object selected some patches
 
 
 def test_mrope_positions_from_deferred_coordinates(dataset, monkeypatch):

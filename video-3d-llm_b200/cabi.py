@@ -29,7 +29,7 @@ SYMBOLS = (
     "v3d_version", "v3d_last_error", "v3d_selftest_division", "v3d_pool_points", "v3d_unproject", "v3d_upload_depth_window", "v3d_expand_depth_window", "v3d_scatter_resampled_depth", "v3d_host_gather", "v3d_h2d_gather",
     "v3d_boundary", "v3d_pool_coords",
     "v3d_discretize", "v3d_pe_table_bytes", "v3d_pe_table_build", "v3d_pe_sine3d", "v3d_frontend_pe",
-    "v3d_mc_hash_slots", "v3d_mc_sample", "v3d_mc_voxelize", "v3d_mc_greedy", "v3d_mc_voxel_ids", "v3d_pe_mlp", "v3d_object_patch_masks", "v3d_object_patch_masks_depth", "v3d_masked_token_mean",
+    "v3d_mc_hash_slots", "v3d_mc_sample", "v3d_mc_voxelize", "v3d_mc_greedy", "v3d_mc_voxel_ids", "v3d_pe_mlp", "v3d_object_patch_masks", "v3d_object_patch_masks_depth", "v3d_object_patch_masks_depth_bounds", "v3d_masked_token_mean",
     "v3d_token_pool_out_grid", "v3d_pool_pe_grid",
 )
 
@@ -121,6 +121,7 @@ def load():
     lib.v3d_pe_mlp.argtypes = [vp, i, i, vp, vp, vp, vp, f, vp, vp, vp, vp, vp]
     lib.v3d_object_patch_masks.argtypes = [vp, i, i, i, i, vp, i, i, vp, vp]
     lib.v3d_object_patch_masks_depth.argtypes = [vp, i, vp, vp, i, i, i, f, vp, vp, vp, i, i, i, vp, i, i, vp, vp]
+    lib.v3d_object_patch_masks_depth_bounds.argtypes = [vp, i, vp, vp, i, i, i, f, vp, vp, vp, i, i, i, vp, i, i, vp, vp]
     lib.v3d_masked_token_mean.argtypes = [vp, i, i, vp, i, vp, vp]
     lib.v3d_token_pool_out_grid.argtypes = [i, i, i]
     lib.v3d_pool_pe_grid.argtypes = [C.POINTER(PoolDesc), vp]

@@ -16,7 +16,7 @@ static constexpr int kObjThreads = 128;
 
 // the patch's pixels are in shared memory ([3][n_px]); every warp tests its share of the boxes.  The patch's own
 // bounding box (NaN coordinates ignored: they are inside no box) rejects most boxes without looking at the pixels.
-__device__ __forceinline__ void count_boxes(const float* s_px, float* s_bbox, int n_px, const float* __restrict__ boxes, int K, int threshold,
+__device__ __forceinline__ void count_boxes(const float* s_px, float* s_bbox, int n_px, const float* __restrict__ boxes, int K, int bounds, int threshold,
                                             uint8_t* __restrict__ masks, size_t cell_stride, size_t cell_off) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp < 3) {  // warp a reduces axis a
@@ -42,9 +42,14 @@ __device__ __forceinline__ void count_boxes(const float* s_px, float* s_bbox, in
     bool disjoint = false;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const float c = __ldg(boxes + 6 * k + a), h = __fdiv_rn(__ldg(boxes + 6 * k + 3 + a), 2.0f);
-      lo[a] = __fsub_rn(c, h);
-      hi[a] = __fadd_rn(c, h);
+      if (bounds) {  // (min xyz, max xyz) as the caller computed them
+        lo[a] = __ldg(boxes + 6 * k + a);
+        hi[a] = __ldg(boxes + 6 * k + 3 + a);
+      } else {
+        const float c = __ldg(boxes + 6 * k + a), h = __fdiv_rn(__ldg(boxes + 6 * k + 3 + a), 2.0f);
+        lo[a] = __fsub_rn(c, h);
+        hi[a] = __fadd_rn(c, h);
+      }
       disjoint = disjoint || hi[a] < s_bbox[2 * a] || lo[a] > s_bbox[2 * a + 1];
     }
     int cnt = 0;
@@ -61,7 +66,7 @@ __device__ __forceinline__ void count_boxes(const float* s_px, float* s_bbox, in
 
 // one CTA per (frame, patch): the patch's pixels are staged once, then every warp tests its share of the boxes
 __global__ void __launch_bounds__(kObjThreads) k_object_masks(const float* __restrict__ coords, int V, int S, int patch, int grid,
-                                                             const float* __restrict__ boxes, int K, int threshold,
+                                                             const float* __restrict__ boxes, int K, int bounds, int threshold,
                                                              uint8_t* __restrict__ masks) {
   extern __shared__ float s_px[];  // [3][patch*patch] + the patch's bounding box [6]
   const int n_px = patch * patch;
@@ -75,7 +80,7 @@ __global__ void __launch_bounds__(kObjThreads) k_object_masks(const float* __res
     s_px[2 * n_px + i] = __ldg(src + 2);
   }
   __syncthreads();
-  count_boxes(s_px, s_px + 3 * n_px, n_px, boxes, K, threshold, masks, (size_t)V * grid * grid, (size_t)f * grid * grid + gi * grid + gj);
+  count_boxes(s_px, s_px + 3 * n_px, n_px, boxes, K, bounds, threshold, masks, (size_t)V * grid * grid, (size_t)f * grid * grid + gi * grid + gj);
 }
 
 // The same masks straight from depth: the patch's pixels are unprojected in the kernel (same device function and
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(kObjThreads) k_object_masks_depth(const void* 
                                                                    const float* __restrict__ intr, int V, int H, int W, float depth_scale,
                                                                    const int32_t* __restrict__ row_map, const int32_t* __restrict__ col_map,
                                                                    Clamp clamp, int coord_dtype, int patch, int grid,
-                                                                   const float* __restrict__ boxes, int K, int threshold,
+                                                                   const float* __restrict__ boxes, int K, int bounds, int threshold,
                                                                    uint8_t* __restrict__ masks) {
   extern __shared__ float s_px[];  // [3][patch*patch] + the patch's bounding box [6]
   const int n_px = patch * patch;
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(kObjThreads) k_object_masks_depth(const void* 
     s_px[2 * n_px + i] = z;
   }
   __syncthreads();
-  count_boxes(s_px, s_px + 3 * n_px, n_px, boxes, K, threshold, masks, (size_t)V * grid * grid, (size_t)f * grid * grid + gi * grid + gj);
+  count_boxes(s_px, s_px + 3 * n_px, n_px, boxes, K, bounds, threshold, masks, (size_t)V * grid * grid, (size_t)f * grid * grid + gi * grid + gj);
 }
 
 // one CTA per (object, block of 256*8 channels): compact the selected tokens chunk by chunk, accumulate in fp32
@@ -185,14 +190,14 @@ int v3d_object_patch_masks(const float* coords, int V, int S, int patch, int gri
   V3D_REQUIRE(S > 0 && patch > 0 && grid > 0 && patch * grid <= S, V3D_E_ARG, "v3d_object_patch_masks: patch*grid=%d exceeds S=%d", patch * grid, S);
   const size_t smem = ((size_t)3 * patch * patch + 8) * sizeof(float);
   V3D_REQUIRE(smem <= 48 * 1024, V3D_E_UNSUPPORTED, "v3d_object_patch_masks: patch %d too large", patch);
-  k_object_masks<<<V * grid * grid, kObjThreads, smem, (cudaStream_t)stream>>>(coords, V, S, patch, grid, boxes, K, threshold, masks_out);
+  k_object_masks<<<V * grid * grid, kObjThreads, smem, (cudaStream_t)stream>>>(coords, V, S, patch, grid, boxes, K, 0, threshold, masks_out);
   return check_launch("k_object_masks");
 }
 
-int v3d_object_patch_masks_depth(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
-                                 float depth_scale, const int32_t* row_map, const int32_t* col_map, const float* clamp_lo_hi_host,
-                                 int coord_dtype, int patch, int grid, const float* boxes, int K, int threshold, uint8_t* masks_out,
-                                 v3d_stream_t stream) {
+static int object_masks_depth(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
+                              float depth_scale, const int32_t* row_map, const int32_t* col_map, const float* clamp_lo_hi_host,
+                              int coord_dtype, int patch, int grid, const float* boxes, int K, int bounds, int threshold, uint8_t* masks_out,
+                              v3d_stream_t stream) {
   if (V == 0 || K == 0) return V3D_OK;
   V3D_REQUIRE(depth && poses && intr && row_map && col_map && boxes && masks_out, V3D_E_ARG, "v3d_object_patch_masks_depth: null pointer");
   V3D_REQUIRE(H > 0 && W > 0 && patch > 0 && grid > 0, V3D_E_ARG, "v3d_object_patch_masks_depth: bad sizes");
@@ -209,17 +214,33 @@ int v3d_object_patch_masks_depth(const void* depth, int depth_dtype, const float
   cudaStream_t s = (cudaStream_t)stream;
   switch (depth_dtype) {
     case V3D_DEPTH_U16:
-      k_object_masks_depth<V3D_DEPTH_U16><<<blocks, kObjThreads, smem, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, cl, coord_dtype, patch, grid, boxes, K, threshold, masks_out);
+      k_object_masks_depth<V3D_DEPTH_U16><<<blocks, kObjThreads, smem, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, cl, coord_dtype, patch, grid, boxes, K, bounds, threshold, masks_out);
       break;
     case V3D_DEPTH_I32:
-      k_object_masks_depth<V3D_DEPTH_I32><<<blocks, kObjThreads, smem, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, cl, coord_dtype, patch, grid, boxes, K, threshold, masks_out);
+      k_object_masks_depth<V3D_DEPTH_I32><<<blocks, kObjThreads, smem, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, cl, coord_dtype, patch, grid, boxes, K, bounds, threshold, masks_out);
       break;
     case V3D_DEPTH_F32:
-      k_object_masks_depth<V3D_DEPTH_F32><<<blocks, kObjThreads, smem, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, cl, coord_dtype, patch, grid, boxes, K, threshold, masks_out);
+      k_object_masks_depth<V3D_DEPTH_F32><<<blocks, kObjThreads, smem, s>>>(depth, poses, intr, V, H, W, depth_scale, row_map, col_map, cl, coord_dtype, patch, grid, boxes, K, bounds, threshold, masks_out);
       break;
     default: set_error("v3d_object_patch_masks_depth: unknown depth dtype %d", depth_dtype); return V3D_E_ARG;
   }
   return check_launch("k_object_masks_depth");
+}
+
+int v3d_object_patch_masks_depth(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
+                                 float depth_scale, const int32_t* row_map, const int32_t* col_map, const float* clamp_lo_hi_host,
+                                 int coord_dtype, int patch, int grid, const float* boxes, int K, int threshold, uint8_t* masks_out,
+                                 v3d_stream_t stream) {
+  return object_masks_depth(depth, depth_dtype, poses, intr, V, H, W, depth_scale, row_map, col_map, clamp_lo_hi_host, coord_dtype, patch, grid,
+                            boxes, K, 0, threshold, masks_out, stream);
+}
+
+int v3d_object_patch_masks_depth_bounds(const void* depth, int depth_dtype, const float* poses, const float* intr, int V, int H, int W,
+                                        float depth_scale, const int32_t* row_map, const int32_t* col_map, const float* clamp_lo_hi_host,
+                                        int coord_dtype, int patch, int grid, const float* min_max_xyz, int K, int threshold,
+                                        uint8_t* masks_out, v3d_stream_t stream) {
+  return object_masks_depth(depth, depth_dtype, poses, intr, V, H, W, depth_scale, row_map, col_map, clamp_lo_hi_host, coord_dtype, patch, grid,
+                            min_max_xyz, K, 1, threshold, masks_out, stream);
 }
 
 int v3d_masked_token_mean(const void* tokens_bf16, int T, int C, const uint8_t* masks, int K, void* out_bf16, v3d_stream_t stream) {

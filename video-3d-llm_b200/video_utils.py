@@ -241,6 +241,14 @@ class LazyWorldCoords:
     def __getitem__(self, idx):
         if self.batched and isinstance(idx, int):
             return self._scene(idx)
+        # world_coords[:, :n, :n, :] of a scene (llava_arch.py:367, 372): the start of the object-proposal chain, deferred so
+        # that the unchanged loop ends in one mask kernel straight from depth (lazy_objects.py)
+        if (not self.batched and self._full is None and isinstance(idx, tuple) and len(idx) == 4 and all(isinstance(i, slice) for i in idx)
+                and idx[0] == slice(None) and idx[3] == slice(None) and idx[1] == idx[2] and idx[1].start is None and idx[1].step is None
+                and isinstance(idx[1].stop, int) and 0 < idx[1].stop <= self.crop_size):
+            from .lazy_objects import PatchGrid
+
+            return PatchGrid(self, idx[1].stop)
         return self.materialize()[idx]
 
     def view(self, *shape):
