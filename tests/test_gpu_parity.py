@@ -931,3 +931,44 @@ def test_scene_batch_loader_pinned_cache_equals_the_host_path(dataset, tmp_path)
         dev.mark_consumed(bd)
     host.close()
     dev.close()
+
+
+def test_deferred_object_chain_falls_back_to_real_tensors():
+    """lazy_objects.py records exactly the expressions of llava_arch.py:360-376; anything else on the same objects must behave
+    like the materialised tensor (same values), and the recorded chain must equal the reference's expressions evaluated on it."""
+    from video_3d_llm_b200 import video_utils as VU
+    from video_3d_llm_b200.lazy_objects import BoxTest, ObjectMask, PatchGrid, PatchPixels
+
+    sc = synthetic.make_scene(41, 3, n_total=30, device=DEV)
+    h = VU.LazyWorldCoords(sc.depth, sc.poses, sc.intrinsics, src_hw=(480, 640))
+    full = VU.LazyWorldCoords(sc.depth, sc.poses, sc.intrinsics, src_hw=(480, 640)).materialize()
+    boxes = torch.tensor([[0.5, 0.2, 1.0, 2.5, 2.0, 2.0], [-1.0, 1.0, 0.8, 1.5, 1.5, 1.6], [9.0, 9.0, 9.0, 0.1, 0.1, 0.1]], device=DEV)
+    ref_masks, got = [], []
+    for patch, grid, thr in ((14, 27, int(14 * 14 * 0.5)), (27, 14, int(27 * 27 * 0.25))):
+        for box in boxes:
+            lo, hi = box[:3] - box[3:] / 2, box[:3] + box[3:] / 2
+            w_ref = full[:, :378, :378, :].reshape(-1, grid, patch, grid, patch, 3).transpose(2, 3).flatten(3, 4)
+            ref_masks.append(torch.all((lo <= w_ref) & (w_ref <= hi), dim=-1).sum(dim=3) >= thr)
+            w = h[:, :378, :378, :]
+            assert isinstance(w, PatchGrid)
+            w = w.reshape(-1, grid, patch, grid, patch, 3).transpose(2, 3).flatten(3, 4)
+            assert isinstance(w, PatchPixels)
+            t = (lo <= w) & (w <= hi)
+            assert isinstance(t, BoxTest)
+            m = torch.all(t, dim=-1).sum(dim=3) >= thr
+            assert isinstance(m, ObjectMask) and m._val is None
+            got.append(m)
+    assert h._full is None  # nothing materialised so far
+    for m, r in zip(got, ref_masks):
+        assert torch.equal(m.view(-1, r.shape[-1] * r.shape[-2]), r.view(-1, r.shape[-1] * r.shape[-2]))
+    assert h._full is None and any(bool(r.any()) for r in ref_masks)
+    # unmodelled uses: same values as the tensor expressions
+    w = h[:, :378, :378, :]
+    assert torch.equal(w.reshape(-1, 3).sum(0), full[:, :378, :378, :].reshape(-1, 3).sum(0))
+    wp = h[:, :378, :378, :].reshape(-1, 27, 14, 27, 14, 3).transpose(2, 3).flatten(3, 4)
+    lo = torch.tensor([0.0, 0.0, 0.0], device=DEV)
+    t_ref = full[:, :378, :378, :].reshape(-1, 27, 14, 27, 14, 3).transpose(2, 3).flatten(3, 4)
+    assert torch.equal((lo <= wp).float().mean(), (lo <= t_ref).float().mean())           # a lone comparison, then tensor methods
+    assert torch.equal(torch.all(lo <= wp, dim=-1).sum(), torch.all(lo <= t_ref, dim=-1).sum())  # all() of a half-open test
+    assert torch.equal((wp <= 1.5).sum(), (t_ref <= 1.5).sum())                                # scalar bound: not a box
+    assert torch.equal(h[:, :100, :378, :], full[:, :100, :378, :])                             # another slice: plain indexing
