@@ -972,3 +972,21 @@ def test_deferred_object_chain_falls_back_to_real_tensors():
     assert torch.equal(torch.all(lo <= wp, dim=-1).sum(), torch.all(lo <= t_ref, dim=-1).sum())  # all() of a half-open test
     assert torch.equal((wp <= 1.5).sum(), (t_ref <= 1.5).sum())                                # scalar bound: not a box
     assert torch.equal(h[:, :100, :378, :], full[:, :100, :378, :])                             # another slice: plain indexing
+
+
+@pytest.mark.parametrize("patch,E,dtype", [(42, 1152, torch.bfloat16), (54, 1152, torch.bfloat16), (63, 96, torch.float16), (14, 8192, torch.bfloat16),
+                                           (27, 64, torch.bfloat16), (18, 3584, torch.float16)])
+def test_streaming_kernel_geometries_and_fallback(patch, E, dtype):
+    """Geometries around the edges of what k_fused_ring takes (few ring slots next to large depth buffers, one-row stages for
+    wide embeddings, a whole patch row in one stage for narrow ones, fp16 tokens) and the ones it must hand to k_fused
+    (patch 54 / 63: the depth buffers alone exceed shared memory): the result equals the operator-sequence kernel bit for bit,
+    for one frame (fewer patch rows than SMs) and for enough frames that every CTA loops."""
+    fe = FrontEnd(device=DEV, patch_size=patch, embedding_size=E, dtype=dtype)
+    fe_exact = FrontEnd(device=DEV, patch_size=patch, embedding_size=E, dtype=dtype)
+    fe_exact.exact_pooling = True
+    for n_frames in (1, 40):
+        sc = synthetic.make_scene(60 + n_frames, n_frames, n_total=60, device=DEV)
+        tok = synthetic.make_tokens(n_frames, n_frames, fe.tokens_per_frame, E).to(DEV).to(dtype)
+        a = fe(sc.depth, sc.poses, sc.intrinsics, tokens=tok)
+        b = fe_exact(sc.depth, sc.poses, sc.intrinsics, tokens=tok)
+        assert a.dtype == dtype and torch.equal(a.view(torch.int16), b.view(torch.int16)), (patch, E, n_frames)

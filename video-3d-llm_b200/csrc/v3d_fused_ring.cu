@@ -583,7 +583,10 @@ bool fused_ring_supported(const FusedParams& p, int depth_dtype, bool use_tma, i
   if ((p.g.E & 7) != 0 || p.g.n_slots != 3 || p.patch > 64 || p.grid > 128) return false;
   if ((reinterpret_cast<uintptr_t>(p.tokens_in) & 15) != 0) return false;
   RingGeom r;
-  return ring_geom(p, &r) != 0;
+  if (!ring_geom(p, &r)) return false;
+  // the pool groups' depth buffers and at least three ring slots must fit in one CTA's shared memory (large patches do not)
+  r.slots = 3;
+  return ring_smem(p, r).total <= (size_t)227 * 1024;
 }
 
 template <typename OutT, bool STRADDLE>
@@ -596,8 +599,8 @@ static int launch_ring(const FusedParams& p, RingGeom r, cudaStream_t s) {
     V3D_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   }
   // one CTA per SM with as many ring slots as fit (the slots are what keeps bytes in flight)
-  r.slots = 2;
-  for (int sl = kMaxRingSlots; sl >= 2; --sl) {
+  r.slots = 3;
+  for (int sl = kMaxRingSlots; sl >= 3; --sl) {
     r.slots = sl;
     if (ring_smem(p, r).total <= (size_t)max_smem) break;
   }
