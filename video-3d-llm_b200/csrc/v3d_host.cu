@@ -5,6 +5,8 @@
 // doing that with numpy copies hand the interpreter lock back and forth once per frame; this gathers a whole batch
 // in one call on a small persistent pool of native threads (the caller's interpreter lock is released by ctypes
 // for the duration).
+#include <emmintrin.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -103,6 +105,29 @@ class CopyPool {
 
 using namespace v3d;
 
+// memcpy whose stores bypass the cache (movntdq): the destination is a pinned staging buffer that only the DMA engine reads
+// next, so pulling its lines into the cache first (read-for-ownership) would be a third pass over host DRAM per byte --
+// and host DRAM is what bounds the loader when several ranks gather at once.  dst 16-byte aligned; any src.
+static void copy_streaming(unsigned char* dst, const unsigned char* src, size_t len) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) != 0 || len < 256) {
+    memcpy(dst, src, len);
+    return;
+  }
+  size_t i = 0;
+  for (; i + 64 <= len; i += 64) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
+    const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+  }
+  if (i < len) memcpy(dst + i, src + i, len - i);
+  _mm_sfence();
+}
+
 extern "C" {
 
 int v3d_host_gather(void* dst_host, const void* const* src_host, size_t bytes_each, int n_blocks, int n_threads) {
@@ -118,7 +143,7 @@ int v3d_host_gather(void* dst_host, const void* const* src_host, size_t bytes_ea
     const int b = i / per_block, p = i - b * per_block;
     const size_t off = (size_t)p * piece;
     const size_t len = off + piece <= bytes_each ? piece : bytes_each - off;
-    memcpy(dst + (size_t)b * bytes_each + off, static_cast<const unsigned char*>(src_host[b]) + off, len);
+    copy_streaming(dst + (size_t)b * bytes_each + off, static_cast<const unsigned char*>(src_host[b]) + off, len);
   });
   return V3D_OK;
 }
