@@ -630,8 +630,6 @@ def config4_leg(rank: int, world: int, dev, scenes, sampler, plan):
 def host_limits_leg(rank: int, world: int, dev, threads: int):
     """The two host-side ceilings of `e2e`, measured with every rank of the node active at the same time: pinned H2D
     bandwidth per rank, and the loader's page-cache -> pinned-memory copy bandwidth with `threads` threads."""
-    import concurrent.futures as cf
-
     import torch.distributed as dist
 
     n = 256 << 20
@@ -648,22 +646,28 @@ def host_limits_leg(rank: int, world: int, dev, threads: int):
     e1.record()
     torch.cuda.synchronize()
     h2d = 4 * n / (e0.elapsed_time(e1) / 1e3) / 1e9
-    # host copy: `threads` threads each copying slices of a 256 MB buffer into pinned memory (what SceneBatchLoader does)
+    # host copy: the loader's own gather (v3d_host_gather: `threads` native threads, non-temporal stores) of frame-sized blocks
+    # of a 256 MB pageable buffer into pinned memory -- what SceneBatchLoader does per batch
+    import ctypes as C
+
+    from video_3d_llm_b200 import cabi
+
+    lib = cabi.load()
     a = np.ones(n, np.uint8)
-    b = src.numpy()
-    parts = [(i * n // threads, (i + 1) * n // threads) for i in range(threads)]
+    blk = 378 * 378 * 2
+    nb = n // blk
+    srcs = (C.c_void_p * nb)(*[a.ctypes.data + i * blk for i in range(nb)])
 
-    def cp(lo_hi):
-        b[lo_hi[0]:lo_hi[1]] = a[lo_hi[0]:lo_hi[1]]
+    def gather():
+        cabi.check(lib.v3d_host_gather(src.data_ptr(), srcs, blk, nb, threads), "v3d_host_gather")
 
-    with cf.ThreadPoolExecutor(threads) as ex:
-        list(ex.map(cp, parts))
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            list(ex.map(cp, parts))
-        memcpy = 3 * n / (time.perf_counter() - t0) / 1e9
+    gather()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        gather()
+    memcpy = 3 * nb * blk / (time.perf_counter() - t0) / 1e9
     vals = torch.tensor([h2d, memcpy], device=dev)
     if world > 1:
         mn = vals.clone()
