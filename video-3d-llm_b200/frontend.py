@@ -268,7 +268,7 @@ class FrontEnd:
             d.pe_out = out.data_ptr()
         else:
             d.pe_mode = cabi.PE_NONE
-        with torch.cuda.device(self.device):
+        with cabi.on_device(self.device):
             cabi.check(self.lib.v3d_frontend_pe(C.byref(d), cabi.stream_ptr(self.device)), "v3d_frontend_pe")
         if want_coords:
             return (out if use_pe else None), pooled, pe_coords
