@@ -15,7 +15,8 @@
 //   * persistent CTAs pull the token rows through a ring of shared-memory stages with cp.async.bulk (TMA) running
 //     S-1 stages ahead -- across patch rows -- so that ~100 KB per SM are in flight without a single scoreboard stall;
 //     the add reads the stage with 128-bit shared loads and streams the result out with 128-bit stores;
-//   * the depth rows of the next patch row are staged (TMA) while the current one streams.
+//   * the depth rows of the patch rows ahead are staged (TMA) by the pool warps while the current ones stream.
+// Measurements, the ablation and what was tried and rejected: DESIGN.md section 4.1.
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -248,9 +249,10 @@ __device__ __noinline__ void exact_coord(int a, int j, int item, int f, int gi, 
 }
 
 // Warp-specialised, one CTA per SM:
-//   * 8 pool warps in 2 or 4 independent groups form the patch means of the patch rows up to kItemSlots ahead (depth
-//     rows staged by TMA, two buffers per group),
-//     publish the table-row offsets of every token and whether the row is settled (`iready`);
+//   * 8 pool warps in 4 independent groups form the patch means of the patch rows up to kItemSlots ahead (depth rows
+//     staged by TMA, one buffer per group: a group requests its next patch row's depth when it has published the current
+//     one), recompute the coordinates the algebra cannot settle with the operator sequence, and publish the table-row
+//     offsets of every token (`iready`);
 //   * the producer warp's lane 0 keeps the token ring full, looking across patch rows (`full` / `empty`);
 //   * 16 stream warps add: table rows of the NEXT stage are requested before the current stage is waited for, a warp
 //     never waits for another warp -- it reads its chunks of a stage, arrives on `empty`, adds and stores.
