@@ -388,12 +388,21 @@ __global__ void __launch_bounds__(kMcThreads, V3D_MC_MIN_BLOCKS) k_mc_voxelize(c
   const int rows_per_warp = (rows_per_slab + kMcThreads / 32 - 1) / (kMcThreads / 32);
   if (threadIdx.x == 0) s_qn[0] = s_qn[1] = 0;
   if (threadIdx.x < kMcThreads / 32) s_wqn[threadIdx.x] = 0;
-  for (int item = blockIdx.x; item < sc.n_frames * slabs_per_frame; item += gridDim.x) {
+  // A CTA takes a CONTIGUOUS range of (frame, slab) items: consecutive slabs of a frame share the frame's setup (camera,
+  // fp64 coefficient divisions, guard-band constants: ~2 k cycles on one thread with the other 255 waiting), which
+  // strided items recomputed for every slab -- 12 % of all stall samples sat at these two barriers.
+  const long total_items = (long)sc.n_frames * slabs_per_frame;
+  const int item0 = (int)(total_items * blockIdx.x / gridDim.x), item1 = (int)(total_items * (blockIdx.x + 1) / gridDim.x);
+  int f_set = -1;
+  for (int item = item0; item < item1; ++item) {
     const int f = item / slabs_per_frame, r0 = (item - f * slabs_per_frame) * rows_per_slab;
     const int r1 = min(r0 + rows_per_slab, H);
-    __syncthreads();  // the previous item's readers of s_set are done
-    if (threadIdx.x == 0) mc_setup_frame(&s_set, sc, f, H, W, depth_scale, voxel, div_mode, layout_ok);
-    __syncthreads();
+    if (f != f_set) {
+      __syncthreads();  // the previous frame's readers of s_set are done
+      if (threadIdx.x == 0) mc_setup_frame(&s_set, sc, f, H, W, depth_scale, voxel, div_mode, layout_ok);
+      __syncthreads();
+      f_set = f;
+    }
     uint32_t* bits = sc.bitsets + (size_t)f * words;
     if (s_set.fast) {
       if constexpr (DT == V3D_DEPTH_U16) {
