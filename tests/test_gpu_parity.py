@@ -990,3 +990,50 @@ def test_streaming_kernel_geometries_and_fallback(patch, E, dtype):
         a = fe(sc.depth, sc.poses, sc.intrinsics, tokens=tok)
         b = fe_exact(sc.depth, sc.poses, sc.intrinsics, tokens=tok)
         assert a.dtype == dtype and torch.equal(a.view(torch.int16), b.view(torch.int16)), (patch, E, n_frames)
+
+
+def test_mc_dense_voxeliser_equals_the_hash_path(monkeypatch):
+    """k_mc_voxelize_dense (cell bitset of the universe's box in shared memory) against k_mc_voxelize alone (V3D_MC_DENSE=0:
+    queue + hash probes): identical coverage bitsets for full-size scenes, a universe with duplicates, a universe that is
+    too large for the cell bitset (hash path for that scene only), one non-rigid frame (hash path for that frame only) and
+    an empty universe."""
+    scenes = []
+    for s in range(5):
+        seed = 720 + s
+        n = 40 if s < 3 else 7
+        sc = synthetic.make_scene(seed, n, n_total=300, frame_indices=np.arange(0, 2 * n, 2), device=DEV)
+        pc = synthetic.mesh_voxels(sc.room, sc.boxes, seed)
+        poses = sc.poses.clone()
+        if s == 1:
+            pc = np.concatenate([pc, pc[:300], pc[100:200]])  # duplicates own one bit
+        if s == 2:
+            pc = np.concatenate([pc, np.array([[3000, 0, 0], [-3000, 5, 1]], dtype=pc.dtype)])  # box of 6001 cells in x
+            poses[3, 3, :] = torch.tensor([0.0, 0.0, 1e-3, 1.0], device=DEV)  # projective frame
+        if s == 3:
+            poses[2, 3, :] = torch.tensor([0.0, 1e-3, 0.0, 1.0], device=DEV)  # one frame for the hash kernel
+        if s == 4:
+            pc = pc[:0]
+        scenes.append({"depth": sc.depth, "poses": poses, "intrinsics": sc.intrinsics,
+                       "pc_voxels": torch.from_numpy(np.ascontiguousarray(pc)).to(DEV), "seed": seed})
+    sampler = mc_sampling.MCSampler(device=DEV)
+    plan = sampler.plan(scenes)
+    monkeypatch.setenv("V3D_MC_DENSE", "0")
+    sampler.run(plan, "voxelize")
+    ref = [sampler.bitsets(plan, i).copy() for i in range(len(scenes))]
+    res_ref = sampler.decode(sampler.run(plan))
+    monkeypatch.setenv("V3D_MC_DENSE", "1")
+    sampler.run(plan, "voxelize")
+    for i in range(len(scenes)):
+        got = sampler.bitsets(plan, i)
+        if i == 1:  # which of the duplicates owns the bit is the hash build's choice: compare per distinct voxel
+            pc = scenes[i]["pc_voxels"].cpu().numpy()
+            _, inv = np.unique(pc, axis=0, return_inverse=True)
+            for f in range(got.shape[0]):
+                a = np.unpackbits(got[f].view(np.uint8), bitorder="little")[: len(pc)]
+                b = np.unpackbits(ref[i][f].view(np.uint8), bitorder="little")[: len(pc)]
+                np.testing.assert_array_equal(np.bincount(inv.ravel(), a), np.bincount(inv.ravel(), b))
+                assert np.bincount(inv.ravel(), a).max() <= 1
+        else:
+            np.testing.assert_array_equal(got, ref[i])
+        assert ref[i].any() or i == 4
+    assert sampler.decode(sampler.run(plan)) == res_ref

@@ -9,6 +9,7 @@
 //                   argmax with the ascending-order tie list (:72-82), CPython-compatible
 //                   MT19937 random.choice (:84), used |= bits (:86) -- bit-exact selection.
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include <math_constants.h>
 
 #include "v3d_common.cuh"
@@ -37,13 +38,21 @@ __global__ void __launch_bounds__(kMcThreads) k_mc_clear(const v3d_mc_scene* __r
   int4* tab = reinterpret_cast<int4*>(sc.hash_table);
   for (size_t i = (size_t)blockIdx.x * kMcThreads + threadIdx.x; i < (size_t)sc.hash_slots; i += (size_t)gridDim.x * kMcThreads)
     tab[i] = make_int4(0, 0, 0, -1);
+  // workspace of the dense voxeliser inside `record` (the greedy stage overwrites the whole record later):
+  // [0..2] / [3..5] = smallest / largest voxel triple of the universe, [6] = the universe has duplicates,
+  // [7] = frames the dense kernel left to the hash kernel
+  if (blockIdx.x == 0 && threadIdx.x < 8)
+    sc.record[threadIdx.x] = threadIdx.x < 3 ? 0x7fffffff : (threadIdx.x < 6 ? (int)0x80000000 : 0);
 }
 
 __global__ void __launch_bounds__(kMcThreads) k_mc_build(const v3d_mc_scene* __restrict__ scenes) {
   const v3d_mc_scene sc = scenes[blockIdx.y];
   const uint32_t mask = (uint32_t)sc.hash_slots - 1u;
+  int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
   for (int b = blockIdx.x * kMcThreads + threadIdx.x; b < sc.n_pc; b += gridDim.x * kMcThreads) {
     const int i = sc.pc_voxels[3 * b], j = sc.pc_voxels[3 * b + 1], k = sc.pc_voxels[3 * b + 2];
+    lo[0] = min(lo[0], i), lo[1] = min(lo[1], j), lo[2] = min(lo[2], k);
+    hi[0] = max(hi[0], i), hi[1] = max(hi[1], j), hi[2] = max(hi[2], k);
     uint32_t h = hash3(i, j, k) & mask;
     for (;;) {
       const int prev = atomicCAS(sc.hash_table + 4 * (size_t)h + 3, -1, b);
@@ -54,8 +63,20 @@ __global__ void __launch_bounds__(kMcThreads) k_mc_build(const v3d_mc_scene* __r
         break;
       }
       // occupied: a duplicate of the same voxel keeps the first index (set semantics)
-      if (sc.pc_voxels[3 * prev] == i && sc.pc_voxels[3 * prev + 1] == j && sc.pc_voxels[3 * prev + 2] == k) break;
+      if (sc.pc_voxels[3 * prev] == i && sc.pc_voxels[3 * prev + 1] == j && sc.pc_voxels[3 * prev + 2] == k) {
+        sc.record[6] = 1;
+        break;
+      }
       h = (h + 1) & mask;
+    }
+  }
+  // bounding box of the universe (all lanes take part: a lane without a voxel contributes the neutral element)
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int l = __reduce_min_sync(0xffffffffu, lo[a]), h = __reduce_max_sync(0xffffffffu, hi[a]);
+    if ((threadIdx.x & 31) == 0 && l <= h) {
+      atomicMin(sc.record + a, l);
+      atomicMax(sc.record + 3 + a, h);
     }
   }
 }
@@ -129,8 +150,11 @@ struct McSetup {
 static constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
 static constexpr int kWarpQueue = 32 + 32 * kPxPerThread;  // leftovers of the previous iteration + one iteration
 
+// `base` (NULL or three integers): the estimate is made in the shifted frame t_i - base_i (the dense voxeliser's cell
+// coordinates).  The shifted constant D_i - base_i is rounded from fp64 like D_i, so the bound above holds with
+// max(|D_i|, |D_i - base_i|) in the place of |D_i|.
 __device__ __noinline__ void mc_setup_frame(McSetup* s, const v3d_mc_scene& sc, int f, int H, int W, float depth_scale, float voxel, int div_mode,
-                               bool layout_ok) {
+                               bool layout_ok, const int* base = nullptr) {
   const Camera cam = load_camera(sc.poses, sc.intr, f);
   s->cam = cam;
   s->ds = make_divisor(depth_scale);
@@ -147,9 +171,11 @@ __device__ __noinline__ void mc_setup_frame(McSetup* s, const v3d_mc_scene& sc, 
     double c[4];
     for (int j = 0; j < 4; ++j) {
       c[j] = (double)cam.P[4 * i + j] / den[j];
-      s->coef[4 * i + j] = (float)c[j];
       finite = finite && (fabs(c[j]) < 1.0e30);
     }
+    d_max = fmax(d_max, fabs(c[3]));
+    if (base) c[3] -= (double)base[i];
+    for (int j = 0; j < 4; ++j) s->coef[4 * i + j] = (float)c[j];
     r_max = fmax(r_max, fabs(c[0]) * um_max + fabs(c[1]) * vm_max + fabs(c[2]));
     d_max = fmax(d_max, fabs(c[3]));
   }
@@ -368,11 +394,259 @@ __device__ __forceinline__ void mc_slab_generic(const v3d_mc_scene& sc, const Mc
   }
 }
 
+// ---- dense voxeliser ---------------------------------------------------------------------------------------
+// The universe of a scene (mesh voxels of one room) sits in a small box: 128 x 128 x 33 cells for a 12.8 m x 12.8 m x 3.3 m
+// room at 0.1 m.  One bit per CELL of that box fits in shared memory, so a pixel needs no hash probe, no queue and no
+// global atomic: estimate the cell (the same verified FMA estimate as above, made in the box's own frame), test that it
+// lies inside the box, set its bit with one shared-memory atomic unless the previous pixel of the lane set the same one.
+// After the last row of a frame the CTA walks the universe once (n_pc cells) and ORs the coverage words into the frame's
+// bitset.  Pixels outside the box cannot be in the universe and are dropped; guard-band pixels take the exact operator
+// sequence and the hash probe as before.  Scenes whose box does not fit (or whose frames are not `fast`) are left to
+// k_mc_voxelize, which skips everything this kernel has done -- both derive the split from mc_dense_plan.
+#ifndef V3D_DENSE_THREADS
+#define V3D_DENSE_THREADS 512
+#endif
+#ifndef V3D_DENSE_BLOCKS
+#define V3D_DENSE_BLOCKS 2
+#endif
+static constexpr int kDenseThreads = V3D_DENSE_THREADS;
+static constexpr int kDenseRows = 2;  // rows per warp task: 2 x 640 / 8 = 160 chunks = 5 full warp iterations
+static constexpr int kDenseSmemBytes = (V3D_DENSE_BLOCKS == 1 ? 208 : 104) * 1024;  // two CTAs per SM
+static constexpr uint32_t kMagicBits = 0x4B400000u;  // bits of kMagic: (t + kMagic) has the bits kMagicBits + rint(t)
+
+struct McDense {
+  int ok;
+  int base[3];   // smallest voxel triple of the universe
+  int px, pxy;   // cells per x row (power of two), per z slice (px * py, py a power of two)
+  int dimz;
+  int words;     // 32-bit words of the cell bitset, a multiple of 4
+};
+
+__device__ __forceinline__ int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+__device__ __forceinline__ McDense mc_dense_plan(const v3d_mc_scene& sc, int smem_bits) {
+  McDense d;
+  d.ok = 0;
+  if (sc.n_pc <= 0 || smem_bits <= 0) return d;
+  long ext[3];
+  for (int a = 0; a < 3; ++a) {
+    const int lo = sc.record[a], hi = sc.record[3 + a];
+    if (lo > hi || lo < -(1 << 20) || hi > (1 << 20)) return d;
+    d.base[a] = lo;
+    ext[a] = (long)hi - lo + 1;
+  }
+  if (ext[0] > 4096 || ext[1] > 4096 || ext[2] > 4096) return d;
+  d.px = pow2_ceil((int)ext[0]);
+  d.pxy = d.px * pow2_ceil((int)ext[1]);
+  d.dimz = (int)ext[2];
+  const long bits = (long)d.pxy * d.dimz;
+  if (bits > smem_bits - 8 * 256) return d;  // 128 bytes behind the bitset: the dummy words of mc_dense_set
+  d.words = (int)((bits + 127) / 128) * 4;
+  d.ok = 1;
+  return d;
+}
+
+// Set bit (key & 31) of the shared-memory word at byte address (key >> 3) & 0x7fffc unless key is the invalid key (all
+// ones) or equal to the previous pixel's.  No predicate on the atomic (ptxas wraps a predicated shared atomic into a
+// divergent branch: three more issue slots per pixel): a lane with nothing to set ORs into its own dummy word.
+__device__ __forceinline__ void mc_dense_set(uint32_t key, uint32_t prev, uint32_t dummy_addr) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      ".reg .u32 a, b;\n\t"
+      "setp.ne.u32 q, %0, %1;\n\t"
+      "setp.ne.and.u32 q, %0, 0xffffffff, q;\n\t"
+      "shr.u32 a, %0, 3;\n\t"
+      "and.b32 a, a, 0x7fffc;\n\t"
+      "selp.u32 a, a, %2, q;\n\t"
+      "shf.l.wrap.b32 b, 0, 1, %0;\n\t"  // (1 << (key & 31)): high word of {1, 0} << n
+      "red.shared.or.b32 [a], b;\n\t"
+      "}" ::"r"(key),
+      "r"(prev), "r"(dummy_addr)
+      : "memory");
+}
+
+// One warp voxelises rows [y0, y0 + nr) of frame f into the CTA's cell bitset.
+__device__ __forceinline__ void mc_dense_rows(const McSetup* __restrict__ s, const v3d_mc_scene* __restrict__ scp, const McDense& dn, int f, int H,
+                                              int W, int gpr, uint32_t gpr_magic, int y0, int nr, uint32_t* __restrict__ s_bits) {
+  const int lane = threadIdx.x & 31;
+  const int n = nr * gpr;
+  float A[3], D[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    A[i] = s->coef[4 * i];
+    D[i] = s->coef[4 * i + 3];
+  }
+  const float k1n = -s->k1, hmk0 = s->half_minus_k0;
+  const uint32_t mx = ~(uint32_t)(dn.px - 1), my = ~(uint32_t)(dn.pxy / dn.px - 1);
+  const uint32_t px = (uint32_t)dn.px, pxy = (uint32_t)dn.pxy, dimz = (uint32_t)dn.dimz;
+  uint32_t sbase8 = smem_u32(s_bits) << 3, dummy = smem_u32(s_bits) + (uint32_t)dn.words * 4u + (uint32_t)lane * 4u;
+  asm volatile("" : "+r"(sbase8), "+r"(dummy));  // plain registers (not re-derived from uniform registers at every use)
+  const uint16_t* rows = reinterpret_cast<const uint16_t*>(scp->depth) + ((size_t)f * H + y0) * W;
+  // No software prefetch: with 32 resident warps per SM the other warps cover a chunk's load, and the four registers of a
+  // second chunk are what makes the loop spill at 64 registers.  Lanes past the end of a ragged last iteration redo the
+  // last chunk (setting a bit twice is harmless).
+  for (int g0 = 0; g0 < n; g0 += 32) {
+    const int ch = min(g0 + lane, n - 1);
+    const uint4 w = ld_stream_v4(rows + (size_t)ch * kPxPerThread);
+    const int r = (int)__umulhi((uint32_t)ch, gpr_magic);
+    const int c0 = (ch - r * gpr) * kPxPerThread;
+    float ray0[3];
+    {
+      const float vm = __fsub_rn((float)(y0 + r), s->cam.cy), um0 = __fsub_rn((float)c0, s->cam.cx);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ray0[i] = __fmaf_rn(A[i], um0, __fmaf_rn(s->coef[4 * i + 1], vm, s->coef[4 * i + 2]));
+    }
+    // A good pixel's key is never all ones: its low 22 bits are 8 * (byte address of the word) + bit number < 2^22 - 1.
+    uint32_t prev = 0xffffffffu;
+    bool all_ok = true;
+    // two halves of four pixels, not unrolled: eight pixels in flight need more than 64 registers
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t wa = h ? w.z : w.x, wb = h ? w.w : w.y;
+      const float fh = h ? 4.0f : 0.0f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t word = (e & 2) ? wb : wa;
+        const float df = (float)((e & 1) ? (word >> 16) : (word & 0xffffu));
+        const float fe = fh + (float)e;  // exact
+        const float m = __fmaf_rn(df, k1n, hmk0);
+        float t[3], tm[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          t[i] = __fmaf_rn(df, __fmaf_rn(A[i], fe, ray0[i]), D[i]);
+          tm[i] = __fadd_rn(t[i], kMagic);
+        }
+        const float dev = fmaxf(fmaxf(fabsf(__fsub_rn(t[0], __fsub_rn(tm[0], kMagic))), fabsf(__fsub_rn(t[1], __fsub_rn(tm[1], kMagic)))),
+                                fabsf(__fsub_rn(t[2], __fsub_rn(tm[2], kMagic))));
+        const bool ok = dev < m;
+        all_ok = all_ok && ok;
+        // tm = kMagicBits + cell coordinate: inside the box iff x and y have no bit above their power-of-two extent (the
+        // fast-frame test keeps |t| < 2^21, so a negative coordinate always shows such a bit) and 0 <= z < dimz
+        const uint32_t bx = __float_as_uint(tm[0]), by = __float_as_uint(tm[1]), bz = __float_as_uint(tm[2]);
+        const bool good = ok && (((bx & mx) | (by & my)) == kMagicBits) && ((bz - kMagicBits) < dimz);
+        // kMagicBits * (1 + px + pxy) is a multiple of 2^22: the low 22 bits of the key are 8*sbase + x + px*y + pxy*z,
+        // i.e. 8 * (byte address of the cell's word) + bit number (sbase is a multiple of 4)
+        const uint32_t key = good ? (bx + sbase8) + by * px + bz * pxy : 0xffffffffu;
+        mc_dense_set(key, prev, dummy);
+        prev = key;
+      }
+    }
+    if (!all_ok) {  // 2-3 pixels in 10^4: find them again, exact operator sequence, probed through the hash
+      const uint32_t w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll 1
+      for (int e = 0; e < kPxPerThread; ++e) {
+        const uint32_t lo = (e & 4) ? w4[2] : w4[0], hi = (e & 4) ? w4[3] : w4[1];
+        const uint32_t word = (e & 2) ? hi : lo;
+        const uint32_t raw = (e & 1) ? (word >> 16) : (word & 0xffffu);
+        float ray[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ray[i] = __fmaf_rn(A[i], (float)e, ray0[i]);
+        if (!mc_estimate((float)raw, ray, D, k1n, hmk0).ok) mc_exact_probe(s, scp, f, raw, c0 + e, y0 + r);
+      }
+    }
+  }
+}
+
+// Coverage words of frame f from the cell bitset, in universe order; clears the cell bitset afterwards.
+__device__ __forceinline__ void mc_dense_flush(const v3d_mc_scene& sc, const McDense& dn, int f, uint32_t* __restrict__ s_bits, int has_dup) {
+  __syncthreads();  // every warp has set its bits
+  const int lane = threadIdx.x & 31;
+  uint32_t* bits = sc.bitsets + (size_t)f * ((sc.n_pc + 31) / 32);
+  for (int p0 = 0; p0 < sc.n_pc; p0 += kDenseThreads) {
+    const int p = p0 + threadIdx.x;
+    bool b = false;
+    if (p < sc.n_pc) {
+      const int i = sc.pc_voxels[3 * p], j = sc.pc_voxels[3 * p + 1], k = sc.pc_voxels[3 * p + 2];
+      const uint32_t cell = (uint32_t)(i - dn.base[0]) + (uint32_t)(j - dn.base[1]) * (uint32_t)dn.px + (uint32_t)(k - dn.base[2]) * (uint32_t)dn.pxy;
+      V3D_CHECK(cell < (uint32_t)dn.words * 32u);
+      b = (s_bits[cell >> 5] >> (cell & 31u)) & 1u;
+      // a duplicated voxel owns one bit: that of the index the hash kept
+      if (b && has_dup) b = hash_find(reinterpret_cast<const int4*>(sc.hash_table), (uint32_t)sc.hash_slots - 1u, i, j, k) == p;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, b);
+    if (lane == 0 && word) atomicOr(bits + (p >> 5), word);
+  }
+  __syncthreads();
+  uint4* z = reinterpret_cast<uint4*>(s_bits);
+  for (int i = threadIdx.x; i < dn.words / 4; i += kDenseThreads) z[i] = make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(kDenseThreads, V3D_DENSE_BLOCKS) k_mc_voxelize_dense(const v3d_mc_scene* __restrict__ scenes, int n_scenes, int H, int W,
+                                                                         float depth_scale, float voxel, int div_mode, int items_per_frame,
+                                                                         int rows_per_item, long total_items, int smem_bits,
+                                                                         uint32_t gpr_magic) {
+  extern __shared__ __align__(16) uint32_t s_bits[];
+  __shared__ McSetup s_set;
+  __shared__ int s_next;  // next warp task of the frame (two rows each): warps take tasks as they finish
+  // a CTA takes a contiguous range of the (scene, frame, row block) items of the whole batch
+  const long item0 = total_items * blockIdx.x / gridDim.x, item1 = total_items * (blockIdx.x + 1) / gridDim.x;
+  long item = item0, first = 0;  // first = first item of scene s
+  int s = 0;
+  while (item < item1 && s < n_scenes) {
+    const long cnt = (long)scenes[s].n_frames * items_per_frame;
+    if (item >= first + cnt) {
+      first += cnt;
+      ++s;
+      continue;
+    }
+    const long send = item1 < first + cnt ? item1 : first + cnt;
+    const v3d_mc_scene sc = scenes[s];
+    const McDense dn = mc_dense_plan(sc, smem_bits);
+    if (!dn.ok) {  // k_mc_voxelize takes the whole scene
+      item = send;
+      continue;
+    }
+    const bool layout_ok = (W % kPxPerThread) == 0 && (reinterpret_cast<uintptr_t>(sc.depth) & 15) == 0;
+    const int has_dup = sc.record[6];
+    __syncthreads();
+    {
+      uint4* z = reinterpret_cast<uint4*>(s_bits);
+      for (int i = threadIdx.x; i < dn.words / 4; i += kDenseThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    while (item < send) {
+      const int li = (int)(item - first);
+      const int f = li / items_per_frame, i0 = li - f * items_per_frame;
+      const long left = send - item;
+      const int i1 = left < (long)(items_per_frame - i0) ? i0 + (int)left : items_per_frame;
+      const int ra = i0 * rows_per_item, rb = min(i1 * rows_per_item, H);
+      __syncthreads();  // the previous frame's readers of s_set are done; the cleared bitset is visible
+      if (threadIdx.x == 0) {
+        mc_setup_frame(&s_set, sc, f, H, W, depth_scale, voxel, div_mode, layout_ok, dn.base);
+        s_next = 0;
+      }
+      __syncthreads();
+      if (s_set.fast) {
+        for (;;) {
+          int task = 0;
+          if ((threadIdx.x & 31) == 0) task = atomicAdd(&s_next, 1);
+          task = __shfl_sync(0xffffffffu, task, 0);
+          const int y0 = ra + task * kDenseRows;
+          if (y0 >= rb) break;
+          mc_dense_rows(&s_set, scenes + s, dn, f, H, W, W / kPxPerThread, gpr_magic, y0, min(kDenseRows, rb - y0), s_bits);
+        }
+        mc_dense_flush(sc, dn, f, s_bits, has_dup);
+      } else if (threadIdx.x == 0 && i0 == 0) {
+        atomicAdd(sc.record + 7, 1);  // a frame for k_mc_voxelize
+      }
+      item += i1 - i0;
+    }
+  }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(kMcThreads, V3D_MC_MIN_BLOCKS) k_mc_voxelize(const v3d_mc_scene* __restrict__ scenes, int H, int W,
                                                             float depth_scale, float voxel, int div_mode, int slabs_per_frame,
-                                                            int rows_per_slab) {
+                                                            int rows_per_slab, int dense_smem_bits) {
   const v3d_mc_scene sc = scenes[blockIdx.y];
+  // what k_mc_voxelize_dense has done already (dense_smem_bits = 0: it did not run): every `fast` frame of a scene
+  // whose universe box fits its shared-memory cell bitset
+  const McDense dn = mc_dense_plan(sc, dense_smem_bits);
+  if (dn.ok && sc.record[7] == 0) return;
   const int words = (sc.n_pc + 31) / 32;
   const uint32_t mask = (uint32_t)sc.hash_slots - 1u;
   const int4* tab = reinterpret_cast<const int4*>(sc.hash_table);
@@ -399,10 +673,11 @@ __global__ void __launch_bounds__(kMcThreads, V3D_MC_MIN_BLOCKS) k_mc_voxelize(c
     const int r1 = min(r0 + rows_per_slab, H);
     if (f != f_set) {
       __syncthreads();  // the previous frame's readers of s_set are done
-      if (threadIdx.x == 0) mc_setup_frame(&s_set, sc, f, H, W, depth_scale, voxel, div_mode, layout_ok);
+      if (threadIdx.x == 0) mc_setup_frame(&s_set, sc, f, H, W, depth_scale, voxel, div_mode, layout_ok, dn.ok ? dn.base : nullptr);
       __syncthreads();
       f_set = f;
     }
+    if (dn.ok && s_set.fast) continue;
     uint32_t* bits = sc.bitsets + (size_t)f * words;
     if (s_set.fast) {
       if constexpr (DT == V3D_DEPTH_U16) {
@@ -629,11 +904,12 @@ __global__ void __launch_bounds__(kGreedyThreads) k_mc_greedy(const v3d_mc_scene
 
 // ---- host side -------------------------------------------------------------------------------------
 static int stage_scenes(const v3d_mc_scene* scenes_host, int n_scenes, void* scratch, cudaStream_t s, int* max_frames,
-                        int* max_pc) {
+                        int* max_pc, long* total_frames = nullptr) {
   V3D_REQUIRE(scenes_host && scratch, V3D_E_ARG, "mc: null scene array / scratch");
   V3D_REQUIRE(n_scenes > 0 && n_scenes <= 65535, V3D_E_ARG, "mc: n_scenes=%d out of range", n_scenes);
   *max_frames = 0;
   *max_pc = 0;
+  if (total_frames) *total_frames = 0;
   for (int i = 0; i < n_scenes; ++i) {
     const v3d_mc_scene& sc = scenes_host[i];
     V3D_REQUIRE(sc.depth && sc.poses && sc.intr && sc.bitsets && sc.hash_table && sc.record, V3D_E_ARG, "mc: scene %d has a null pointer", i);
@@ -642,6 +918,7 @@ static int stage_scenes(const v3d_mc_scene* scenes_host, int n_scenes, void* scr
     V3D_REQUIRE(sc.hash_slots >= v3d_mc_hash_slots(sc.n_pc) && (sc.hash_slots & (sc.hash_slots - 1)) == 0, V3D_E_ARG,
                 "mc: scene %d hash_slots=%d must be a power of two >= %d", i, sc.hash_slots, v3d_mc_hash_slots(sc.n_pc));
     V3D_REQUIRE((reinterpret_cast<uintptr_t>(sc.hash_table) & 15) == 0, V3D_E_ALIGN, "mc: scene %d hash_table not 16-byte aligned", i);
+    if (total_frames) *total_frames += sc.n_frames;
     if (sc.n_frames > *max_frames) *max_frames = sc.n_frames;
     if (sc.n_pc > *max_pc) *max_pc = sc.n_pc;
   }
@@ -649,8 +926,8 @@ static int stage_scenes(const v3d_mc_scene* scenes_host, int n_scenes, void* scr
   return V3D_OK;
 }
 
-static int launch_voxelize(const v3d_mc_scene* dev_scenes, int n_scenes, int max_frames, int max_pc, int H, int W, int depth_dtype,
-                           float depth_scale, float voxel, int div_mode, cudaStream_t s) {
+static int launch_voxelize(const v3d_mc_scene* dev_scenes, int n_scenes, int max_frames, long total_frames, int max_pc, int H, int W,
+                           int depth_dtype, float depth_scale, float voxel, int div_mode, cudaStream_t s) {
   V3D_REQUIRE(H > 0 && W > 0 && voxel > 0.f, V3D_E_ARG, "mc: bad H/W/voxel");
   if (max_frames == 0) return V3D_OK;
   // clear + build
@@ -663,6 +940,27 @@ static int launch_voxelize(const v3d_mc_scene* dev_scenes, int n_scenes, int max
     bx = bx < 1 ? 1 : (bx > 1024 ? 1024 : bx);
     k_mc_build<<<dim3(bx, n_scenes), kMcThreads, 0, s>>>(dev_scenes);
   }
+  // dense voxeliser first (uint16 depth in whole 8-pixel groups; anything it leaves is done by k_mc_voxelize below)
+  int dense_bits = 0;
+  const char* dense_env = getenv("V3D_MC_DENSE");  // "0": hash kernel only (tests compare the two, tools/time_mc.py times both)
+  if (!(dense_env && dense_env[0] == '0') && depth_dtype == V3D_DEPTH_U16 && (W % kPxPerThread) == 0 && W / kPxPerThread < 65536 / kDenseRows && total_frames > 0) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      V3D_CUDA(cudaFuncSetAttribute(k_mc_voxelize_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemBytes));
+      attr_set = true;
+    }
+    dense_bits = kDenseSmemBytes * 8;
+    const int rows_per_item = (kDenseThreads / 32) * kDenseRows;
+    const int items_per_frame = (H + rows_per_item - 1) / rows_per_item;
+    const long total_items = total_frames * items_per_frame;
+    long g = (long)num_sms() * V3D_DENSE_BLOCKS;
+    if (g > total_items) g = total_items;
+    const uint32_t gpr_magic = 0xffffffffu / (uint32_t)(W / kPxPerThread) + 1u;  // g / gpr == umulhi(g, magic) for g < 2^16
+    k_mc_voxelize_dense<<<(unsigned)g, kDenseThreads, kDenseSmemBytes, s>>>(dev_scenes, n_scenes, H, W, depth_scale, voxel, div_mode, items_per_frame,
+                                                                           rows_per_item, total_items, dense_bits, gpr_magic);
+    int rc = check_launch("k_mc_voxelize_dense");
+    if (rc != V3D_OK) return rc;
+  }
   // 48 rows = 6 per warp; 6 x (640/8) groups = 15 full warp iterations for ScanNet-shaped depth
   const int rows_per_slab = 48;
   const int slabs = (H + rows_per_slab - 1) / rows_per_slab;
@@ -673,9 +971,9 @@ static int launch_voxelize(const v3d_mc_scene* dev_scenes, int n_scenes, int max
   if (gx < 1) gx = 1;
   dim3 grid(gx, n_scenes);
   switch (depth_dtype) {
-    case V3D_DEPTH_U16: k_mc_voxelize<V3D_DEPTH_U16><<<grid, kMcThreads, 0, s>>>(dev_scenes, H, W, depth_scale, voxel, div_mode, slabs, rows_per_slab); break;
-    case V3D_DEPTH_I32: k_mc_voxelize<V3D_DEPTH_I32><<<grid, kMcThreads, 0, s>>>(dev_scenes, H, W, depth_scale, voxel, div_mode, slabs, rows_per_slab); break;
-    case V3D_DEPTH_F32: k_mc_voxelize<V3D_DEPTH_F32><<<grid, kMcThreads, 0, s>>>(dev_scenes, H, W, depth_scale, voxel, div_mode, slabs, rows_per_slab); break;
+    case V3D_DEPTH_U16: k_mc_voxelize<V3D_DEPTH_U16><<<grid, kMcThreads, 0, s>>>(dev_scenes, H, W, depth_scale, voxel, div_mode, slabs, rows_per_slab, dense_bits); break;
+    case V3D_DEPTH_I32: k_mc_voxelize<V3D_DEPTH_I32><<<grid, kMcThreads, 0, s>>>(dev_scenes, H, W, depth_scale, voxel, div_mode, slabs, rows_per_slab, dense_bits); break;
+    case V3D_DEPTH_F32: k_mc_voxelize<V3D_DEPTH_F32><<<grid, kMcThreads, 0, s>>>(dev_scenes, H, W, depth_scale, voxel, div_mode, slabs, rows_per_slab, dense_bits); break;
     default: set_error("mc: unknown depth dtype %d", depth_dtype); return V3D_E_ARG;
   }
   return check_launch("k_mc_voxelize");
@@ -724,10 +1022,11 @@ int v3d_mc_hash_slots(int n_pc) {
 int v3d_mc_voxelize(const v3d_mc_scene* scenes_host, int n_scenes, int H, int W, int depth_dtype, float depth_scale,
                     float voxel_size, int div_mode, void* scratch, v3d_stream_t stream) {
   int mf, mp;
+  long tf;
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = stage_scenes(scenes_host, n_scenes, scratch, s, &mf, &mp);
+  int rc = stage_scenes(scenes_host, n_scenes, scratch, s, &mf, &mp, &tf);
   if (rc != V3D_OK) return rc;
-  return launch_voxelize(reinterpret_cast<const v3d_mc_scene*>(scratch), n_scenes, mf, mp, H, W, depth_dtype, depth_scale, voxel_size, div_mode, s);
+  return launch_voxelize(reinterpret_cast<const v3d_mc_scene*>(scratch), n_scenes, mf, tf, mp, H, W, depth_dtype, depth_scale, voxel_size, div_mode, s);
 }
 
 int v3d_mc_greedy(const v3d_mc_scene* scenes_host, int n_scenes, int max_pick, void* scratch, v3d_stream_t stream) {
@@ -741,11 +1040,12 @@ int v3d_mc_greedy(const v3d_mc_scene* scenes_host, int n_scenes, int max_pick, v
 int v3d_mc_sample(const v3d_mc_scene* scenes_host, int n_scenes, int H, int W, int depth_dtype, float depth_scale,
                   float voxel_size, int div_mode, int max_pick, void* scratch, v3d_stream_t stream) {
   int mf, mp;
+  long tf;
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = stage_scenes(scenes_host, n_scenes, scratch, s, &mf, &mp);
+  int rc = stage_scenes(scenes_host, n_scenes, scratch, s, &mf, &mp, &tf);
   if (rc != V3D_OK) return rc;
   const v3d_mc_scene* dev = reinterpret_cast<const v3d_mc_scene*>(scratch);
-  rc = launch_voxelize(dev, n_scenes, mf, mp, H, W, depth_dtype, depth_scale, voxel_size, div_mode, s);
+  rc = launch_voxelize(dev, n_scenes, mf, tf, mp, H, W, depth_dtype, depth_scale, voxel_size, div_mode, s);
   if (rc != V3D_OK) return rc;
   return launch_greedy(dev, n_scenes, mf, mp, max_pick, s);
 }
