@@ -411,7 +411,7 @@ __device__ __forceinline__ void mc_slab_generic(const v3d_mc_scene& sc, const Mc
 #endif
 static constexpr int kDenseThreads = V3D_DENSE_THREADS;
 static constexpr int kDenseRows = 2;  // rows per warp task: 2 x 640 / 8 = 160 chunks = 5 full warp iterations
-static constexpr int kDenseSmemBytes = (V3D_DENSE_BLOCKS == 1 ? 208 : 104) * 1024;  // two CTAs per SM
+static constexpr int kDenseSmemBytes = (V3D_DENSE_BLOCKS == 1 ? 192 : 96) * 1024;  // cell bitset; two CTAs per SM with their staging rings
 static constexpr uint32_t kMagicBits = 0x4B400000u;  // bits of kMagic: (t + kMagic) has the bits kMagicBits + rint(t)
 
 struct McDense {
@@ -444,7 +444,7 @@ __device__ __forceinline__ McDense mc_dense_plan(const v3d_mc_scene& sc, int sme
   d.pxy = d.px * pow2_ceil((int)ext[1]);
   d.dimz = (int)ext[2];
   const long bits = (long)d.pxy * d.dimz;
-  if (bits > smem_bits - 8 * 256) return d;  // 128 bytes behind the bitset: the dummy words of mc_dense_set
+  if (bits > smem_bits - 8 * 1024) return d;  // alignment of the bitset (512 B) and, behind it, the 128 B of dummy words of mc_dense_set
   d.words = (int)((bits + 127) / 128) * 4;
   d.ok = 1;
   return d;
@@ -470,11 +470,59 @@ __device__ __forceinline__ void mc_dense_set(uint32_t key, uint32_t prev, uint32
       : "memory");
 }
 
-// One warp voxelises rows [y0, y0 + nr) of frame f into the CTA's cell bitset.
-__device__ __forceinline__ void mc_dense_rows(const McSetup* __restrict__ s, const v3d_mc_scene* __restrict__ scp, const McDense& dn, int f, int H,
-                                              int W, int gpr, uint32_t gpr_magic, int y0, int nr, uint32_t* __restrict__ s_bits) {
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+
+// packed fp32 pairs (sm_100: fma/add/sub.rn.f32x2)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float half2f(uint64_t v, int hi) {
+  float a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  return hi ? b : a;
+}
+__device__ __forceinline__ uint32_t half2u(uint64_t v, int hi) { return __float_as_uint(half2f(v, hi)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+static constexpr int kDenseTaskIters = 5;  // warp iterations per task: 5 x 32 chunks of 8 pixels = two rows of 640
+
+// One warp voxelises its share of rows [ra, rb) of frame f into the CTA's cell bitset.  The rows are one flat run of
+// 8-pixel chunks; warps take tasks of 160 chunks from a shared counter as they finish (no end-of-frame skew), and a lane
+// stages the chunk of its next iteration -- also across tasks -- in shared memory with cp.async while it works on the
+// current one (no registers held by the load in flight).
+__device__ __forceinline__ void mc_dense_part(const McSetup* __restrict__ s, const v3d_mc_scene* __restrict__ scp, const McDense& dn, int f, int H,
+                                              int W, int gpr, uint32_t gpr_magic, int ra, int rb, uint32_t* __restrict__ s_bits,
+                                              int* __restrict__ s_next, uint4* __restrict__ stage) {
   const int lane = threadIdx.x & 31;
-  const int n = nr * gpr;
+  const int n = (rb - ra) * gpr;
   float A[3], D[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -482,74 +530,119 @@ __device__ __forceinline__ void mc_dense_rows(const McSetup* __restrict__ s, con
     D[i] = s->coef[4 * i + 3];
   }
   const float k1n = -s->k1, hmk0 = s->half_minus_k0;
+  uint64_t A2[3], D2[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) A2[i] = pack2(A[i], A[i]), D2[i] = pack2(D[i], D[i]);
+  const uint64_t k1n2 = pack2(k1n, k1n), hmk02 = pack2(hmk0, hmk0);
   const uint32_t mx = ~(uint32_t)(dn.px - 1), my = ~(uint32_t)(dn.pxy / dn.px - 1);
   const uint32_t px = (uint32_t)dn.px, pxy = (uint32_t)dn.pxy, dimz = (uint32_t)dn.dimz;
-  uint32_t sbase8 = smem_u32(s_bits) << 3, dummy = smem_u32(s_bits) + (uint32_t)dn.words * 4u + (uint32_t)lane * 4u;
-  asm volatile("" : "+r"(sbase8), "+r"(dummy));  // plain registers (not re-derived from uniform registers at every use)
-  const uint16_t* rows = reinterpret_cast<const uint16_t*>(scp->depth) + ((size_t)f * H + y0) * W;
-  // No software prefetch: with 32 resident warps per SM the other warps cover a chunk's load, and the four registers of a
-  // second chunk are what makes the loop spill at 64 registers.  Lanes past the end of a ragged last iteration redo the
-  // last chunk (setting a bit twice is harmless).
-  for (int g0 = 0; g0 < n; g0 += 32) {
-    const int ch = min(g0 + lane, n - 1);
-    const uint4 w = ld_stream_v4(rows + (size_t)ch * kPxPerThread);
-    const int r = (int)__umulhi((uint32_t)ch, gpr_magic);
-    const int c0 = (ch - r * gpr) * kPxPerThread;
-    float ray0[3];
+  // The x estimate is rounded with kMagic + 8*sbase (sbase = shared-memory address of the bitset, a multiple of 512 below
+  // 2^18): exact like kMagic itself (integers below 2^24), and the bits of the sum are kMagicBits + 8*sbase + x -- the
+  // key below then holds the word's address without another add.
+  const uint32_t sbase8 = smem_u32(s_bits) << 3;
+  const float magic_x = kMagic + (float)sbase8;
+  const uint32_t bits_x = kMagicBits | sbase8;
+  uint32_t dummy = smem_u32(s_bits) + (uint32_t)dn.words * 4u + (uint32_t)lane * 4u;
+  uint32_t st_addr = smem_u32(stage + lane);
+  asm volatile("" : "+r"(dummy), "+r"(st_addr));  // plain registers (not re-derived from uniform registers at every use)
+  const uint16_t* rows = reinterpret_cast<const uint16_t*>(scp->depth) + ((size_t)f * H + ra) * W;
+  int cur;  // first chunk of the warp's task
+  {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(s_next, 1);
+    cur = __shfl_sync(0xffffffffu, t, 0) * (32 * kDenseTaskIters);
+  }
+  if (cur >= n) return;
+  // lanes past the end of the run redo its last chunk (setting a bit twice is harmless)
+  cp_async16(st_addr, rows + (size_t)min(cur + lane, n - 1) * kPxPerThread);
+  cp_async_commit();
+  uint32_t k = 0;
+  while (cur < n) {
+    int nxt;
     {
-      const float vm = __fsub_rn((float)(y0 + r), s->cam.cy), um0 = __fsub_rn((float)c0, s->cam.cx);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) ray0[i] = __fmaf_rn(A[i], um0, __fmaf_rn(s->coef[4 * i + 1], vm, s->coef[4 * i + 2]));
+      int t = 0;
+      if (lane == 0) t = atomicAdd(s_next, 1);
+      nxt = __shfl_sync(0xffffffffu, t, 0) * (32 * kDenseTaskIters);
     }
+    const int iters = min(kDenseTaskIters, (n - cur + 31) / 32);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it, ++k) {
+      const int pf = it + 1 < iters ? cur + (it + 1) * 32 : nxt;
+      if (pf < n) cp_async16(st_addr + (((k + 1u) & 1u) << 9), rows + (size_t)min(pf + lane, n - 1) * kPxPerThread);
+      cp_async_commit();
+      cp_async_wait<1>();
+      const uint4 w = lds_v4(st_addr + ((k & 1u) << 9));
+      const int ch = min(cur + it * 32 + lane, n - 1);
+      const int r = (int)__umulhi((uint32_t)ch, gpr_magic);
+      const int c0 = (ch - r * gpr) * kPxPerThread;
+      const int y0 = ra;
+      uint64_t ray02[3];
+      {
+        const float vm = __fsub_rn((float)(y0 + r), s->cam.cy), um0 = __fsub_rn((float)c0, s->cam.cx);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float ray0 = __fmaf_rn(A[i], um0, __fmaf_rn(s->coef[4 * i + 1], vm, s->coef[4 * i + 2]));
+          ray02[i] = pack2(ray0, ray0);
+        }
+      }
     // A good pixel's key is never all ones: its low 22 bits are 8 * (byte address of the word) + bit number < 2^22 - 1.
-    uint32_t prev = 0xffffffffu;
-    bool all_ok = true;
-    // two halves of four pixels, not unrolled: eight pixels in flight need more than 64 registers
+    uint32_t prev = 0xffffffffu, slow = 0;
+    // Two halves of four pixels, not unrolled (eight pixels in flight need more than 64 registers); inside a half the
+    // pixels go in pairs through the packed fp32 instructions (fma/add/sub.rn.f32x2, SASS FFMA2 / FADD2: two lanes of the
+    // same IEEE operation, so the estimate is bit for bit mc_estimate's) -- half the issue slots for the arithmetic.
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       const uint32_t wa = h ? w.z : w.x, wb = h ? w.w : w.y;
       const float fh = h ? 4.0f : 0.0f;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t word = (e & 2) ? wb : wa;
-        const float df = (float)((e & 1) ? (word >> 16) : (word & 0xffffu));
-        const float fe = fh + (float)e;  // exact
-        const float m = __fmaf_rn(df, k1n, hmk0);
-        float t[3], tm[3];
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t word = j ? wb : wa;
+        const uint64_t df2 = pack2((float)(word & 0xffffu), (float)(word >> 16));
+        const uint64_t fe2 = pack2(fh + (float)(2 * j), fh + (float)(2 * j + 1));  // exact
+        const uint64_t m2 = fma2(df2, k1n2, hmk02);
+        uint64_t t2[3], tm2[3], dv2[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          t[i] = __fmaf_rn(df, __fmaf_rn(A[i], fe, ray0[i]), D[i]);
-          tm[i] = __fadd_rn(t[i], kMagic);
+          t2[i] = fma2(df2, fma2(A2[i], fe2, ray02[i]), D2[i]);
+          const float mg = i == 0 ? magic_x : kMagic;
+          tm2[i] = add2(t2[i], pack2(mg, mg));
+          dv2[i] = sub2(t2[i], sub2(tm2[i], pack2(mg, mg)));
         }
-        const float dev = fmaxf(fmaxf(fabsf(__fsub_rn(t[0], __fsub_rn(tm[0], kMagic))), fabsf(__fsub_rn(t[1], __fsub_rn(tm[1], kMagic)))),
-                                fabsf(__fsub_rn(t[2], __fsub_rn(tm[2], kMagic))));
-        const bool ok = dev < m;
-        all_ok = all_ok && ok;
-        // tm = kMagicBits + cell coordinate: inside the box iff x and y have no bit above their power-of-two extent (the
-        // fast-frame test keeps |t| < 2^21, so a negative coordinate always shows such a bit) and 0 <= z < dimz
-        const uint32_t bx = __float_as_uint(tm[0]), by = __float_as_uint(tm[1]), bz = __float_as_uint(tm[2]);
-        const bool good = ok && (((bx & mx) | (by & my)) == kMagicBits) && ((bz - kMagicBits) < dimz);
-        // kMagicBits * (1 + px + pxy) is a multiple of 2^22: the low 22 bits of the key are 8*sbase + x + px*y + pxy*z,
-        // i.e. 8 * (byte address of the cell's word) + bit number (sbase is a multiple of 4)
-        const uint32_t key = good ? (bx + sbase8) + by * px + bz * pxy : 0xffffffffu;
-        mc_dense_set(key, prev, dummy);
-        prev = key;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int e = 2 * j + q;
+          const float dev = fmaxf(fmaxf(fabsf(half2f(dv2[0], q)), fabsf(half2f(dv2[1], q))), fabsf(half2f(dv2[2], q)));
+          const bool ok = dev < half2f(m2, q);
+          if (!ok) slow |= 1u << e;  // bit e of the half
+          // tm = kMagicBits + cell coordinate (+ 8*sbase for x, a multiple of the x extent): inside the box iff x and y
+          // have no bit above their power-of-two extent other than those constants (the fast-frame test keeps |t| < 2^21,
+          // so a negative coordinate always shows such a bit) and 0 <= z < dimz
+          const uint32_t bx = half2u(tm2[0], q), by = half2u(tm2[1], q), bz = half2u(tm2[2], q);
+          const bool good = ok && (((bx & mx) | (by & my)) == bits_x) && ((bz - kMagicBits) < dimz);
+          // kMagicBits * (1 + px + pxy) is a multiple of 2^22: the low 22 bits of the key are 8*sbase + x + px*y + pxy*z,
+          // i.e. 8 * (byte address of the cell's word) + bit number
+          const uint32_t key = good ? bx + by * px + bz * pxy : 0xffffffffu;
+          mc_dense_set(key, prev, dummy);
+          prev = key;
+        }
       }
+      slow <<= 4 * (1 - h);  // the first half's four bits move up: bits 4..7 = pixels 0..3, bits 0..3 = pixels 4..7
     }
-    if (!all_ok) {  // 2-3 pixels in 10^4: find them again, exact operator sequence, probed through the hash
+    if (slow) {  // 2-3 pixels in 10^4: exact operator sequence, probed through the hash
       const uint32_t w4[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll 1
-      for (int e = 0; e < kPxPerThread; ++e) {
+      for (uint32_t rest = slow; rest; rest &= rest - 1) {
+        const int b = __ffs(rest) - 1;
+        const int e = b ^ 4;
         const uint32_t lo = (e & 4) ? w4[2] : w4[0], hi = (e & 4) ? w4[3] : w4[1];
         const uint32_t word = (e & 2) ? hi : lo;
-        const uint32_t raw = (e & 1) ? (word >> 16) : (word & 0xffffu);
-        float ray[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) ray[i] = __fmaf_rn(A[i], (float)e, ray0[i]);
-        if (!mc_estimate((float)raw, ray, D, k1n, hmk0).ok) mc_exact_probe(s, scp, f, raw, c0 + e, y0 + r);
+        mc_exact_probe(s, scp, f, (e & 1) ? (word >> 16) : (word & 0xffffu), c0 + e, y0 + r);
       }
     }
+    }
+    cur = nxt;
   }
+  cp_async_wait<0>();
 }
 
 // Coverage words of frame f from the cell bitset, in universe order; clears the cell bitset afterwards.
@@ -580,9 +673,13 @@ __global__ void __launch_bounds__(kDenseThreads, V3D_DENSE_BLOCKS) k_mc_voxelize
                                                                          float depth_scale, float voxel, int div_mode, int items_per_frame,
                                                                          int rows_per_item, long total_items, int smem_bits,
                                                                          uint32_t gpr_magic) {
-  extern __shared__ __align__(16) uint32_t s_bits[];
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  // 512-byte aligned: 8 * (shared-memory address of the bitset) is then a multiple of every power-of-two x extent up to
+  // 4096, which lets the x coordinate carry the address (mc_dense_part)
+  uint32_t* s_bits = s_dyn + ((512u - (smem_u32(s_dyn) & 511u)) & 511u) / 4u;
   __shared__ McSetup s_set;
-  __shared__ int s_next;  // next warp task of the frame (two rows each): warps take tasks as they finish
+  __shared__ int s_next;  // next warp task of the frame: warps take tasks as they finish
+  __shared__ __align__(16) uint4 s_stage[kDenseThreads / 32][2][32];
   // a CTA takes a contiguous range of the (scene, frame, row block) items of the whole batch
   const long item0 = total_items * blockIdx.x / gridDim.x, item1 = total_items * (blockIdx.x + 1) / gridDim.x;
   long item = item0, first = 0;  // first = first item of scene s
@@ -621,14 +718,7 @@ __global__ void __launch_bounds__(kDenseThreads, V3D_DENSE_BLOCKS) k_mc_voxelize
       }
       __syncthreads();
       if (s_set.fast) {
-        for (;;) {
-          int task = 0;
-          if ((threadIdx.x & 31) == 0) task = atomicAdd(&s_next, 1);
-          task = __shfl_sync(0xffffffffu, task, 0);
-          const int y0 = ra + task * kDenseRows;
-          if (y0 >= rb) break;
-          mc_dense_rows(&s_set, scenes + s, dn, f, H, W, W / kPxPerThread, gpr_magic, y0, min(kDenseRows, rb - y0), s_bits);
-        }
+        mc_dense_part(&s_set, scenes + s, dn, f, H, W, W / kPxPerThread, gpr_magic, ra, rb, s_bits, &s_next, &s_stage[threadIdx.x >> 5][0][0]);
         mc_dense_flush(sc, dn, f, s_bits, has_dup);
       } else if (threadIdx.x == 0 && i0 == 0) {
         atomicAdd(sc.record + 7, 1);  // a frame for k_mc_voxelize
@@ -943,7 +1033,7 @@ static int launch_voxelize(const v3d_mc_scene* dev_scenes, int n_scenes, int max
   // dense voxeliser first (uint16 depth in whole 8-pixel groups; anything it leaves is done by k_mc_voxelize below)
   int dense_bits = 0;
   const char* dense_env = getenv("V3D_MC_DENSE");  // "0": hash kernel only (tests compare the two, tools/time_mc.py times both)
-  if (!(dense_env && dense_env[0] == '0') && depth_dtype == V3D_DEPTH_U16 && (W % kPxPerThread) == 0 && W / kPxPerThread < 65536 / kDenseRows && total_frames > 0) {
+  if (!(dense_env && dense_env[0] == '0') && depth_dtype == V3D_DEPTH_U16 && (W % kPxPerThread) == 0 && (long)H * (W / kPxPerThread) * (W / kPxPerThread) < (1L << 32) && total_frames > 0) {
     static bool attr_set = false;
     if (!attr_set) {
       V3D_CUDA(cudaFuncSetAttribute(k_mc_voxelize_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemBytes));
@@ -955,7 +1045,7 @@ static int launch_voxelize(const v3d_mc_scene* dev_scenes, int n_scenes, int max
     const long total_items = total_frames * items_per_frame;
     long g = (long)num_sms() * V3D_DENSE_BLOCKS;
     if (g > total_items) g = total_items;
-    const uint32_t gpr_magic = 0xffffffffu / (uint32_t)(W / kPxPerThread) + 1u;  // g / gpr == umulhi(g, magic) for g < 2^16
+    const uint32_t gpr_magic = 0xffffffffu / (uint32_t)(W / kPxPerThread) + 1u;  // g / gpr == umulhi(g, magic) while g * gpr < 2^32
     k_mc_voxelize_dense<<<(unsigned)g, kDenseThreads, kDenseSmemBytes, s>>>(dev_scenes, n_scenes, H, W, depth_scale, voxel, div_mode, items_per_frame,
                                                                            rows_per_item, total_items, dense_bits, gpr_magic);
     int rc = check_launch("k_mc_voxelize_dense");
