@@ -411,7 +411,7 @@ __device__ __forceinline__ void mc_slab_generic(const v3d_mc_scene& sc, const Mc
 #endif
 static constexpr int kDenseThreads = V3D_DENSE_THREADS;
 static constexpr int kDenseRows = 2;  // rows per warp task: 2 x 640 / 8 = 160 chunks = 5 full warp iterations
-static constexpr int kDenseSmemBytes = (V3D_DENSE_BLOCKS == 1 ? 192 : 96) * 1024;  // cell bitset; two CTAs per SM with their staging rings
+static constexpr int kDenseSmemBytes = (V3D_DENSE_BLOCKS == 1 ? 160 : 80) * 1024;  // cell bitset; two CTAs per SM with their staging rings
 static constexpr uint32_t kMagicBits = 0x4B400000u;  // bits of kMagic: (t + kMagic) has the bits kMagicBits + rint(t)
 
 struct McDense {
@@ -512,12 +512,13 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
   return d;
 }
 
-static constexpr int kDenseTaskIters = 5;  // warp iterations per task: 5 x 32 chunks of 8 pixels = two rows of 640
+static constexpr int kDensePx = 16;        // pixels of a lane per warp iteration: two 16-byte pieces
+static constexpr int kDenseTaskIters = 2;  // warp iterations per task: 2 x 32 x 16 = 1024 pixels
 
 // One warp voxelises its share of rows [ra, rb) of frame f into the CTA's cell bitset.  The rows are one flat run of
-// 8-pixel chunks; warps take tasks of 160 chunks from a shared counter as they finish (no end-of-frame skew), and a lane
+// 16-pixel chunks; warps take tasks of 64 chunks from a shared counter as they finish (no end-of-frame skew), and a lane
 // stages the chunk of its next iteration -- also across tasks -- in shared memory with cp.async while it works on the
-// current one (no registers held by the load in flight).
+// current one (no registers held by the load in flight).  gpr = W / 16 chunks per row, gpr_magic its reciprocal.
 __device__ __forceinline__ void mc_dense_part(const McSetup* __restrict__ s, const v3d_mc_scene* __restrict__ scp, const McDense& dn, int f, int H,
                                               int W, int gpr, uint32_t gpr_magic, int ra, int rb, uint32_t* __restrict__ s_bits,
                                               int* __restrict__ s_next, uint4* __restrict__ stage) {
@@ -530,22 +531,20 @@ __device__ __forceinline__ void mc_dense_part(const McSetup* __restrict__ s, con
     D[i] = s->coef[4 * i + 3];
   }
   const float k1n = -s->k1, hmk0 = s->half_minus_k0;
-  uint64_t A2[3], D2[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) A2[i] = pack2(A[i], A[i]), D2[i] = pack2(D[i], D[i]);
-  const uint64_t k1n2 = pack2(k1n, k1n), hmk02 = pack2(hmk0, hmk0);
   const uint32_t mx = ~(uint32_t)(dn.px - 1), my = ~(uint32_t)(dn.pxy / dn.px - 1);
   const uint32_t px = (uint32_t)dn.px, pxy = (uint32_t)dn.pxy, dimz = (uint32_t)dn.dimz;
   // The x estimate is rounded with kMagic + 8*sbase (sbase = shared-memory address of the bitset, a multiple of 512 below
   // 2^18): exact like kMagic itself (integers below 2^24), and the bits of the sum are kMagicBits + 8*sbase + x -- the
   // key below then holds the word's address without another add.
   const uint32_t sbase8 = smem_u32(s_bits) << 3;
-  const float magic_x = kMagic + (float)sbase8;
-  const uint32_t bits_x = kMagicBits | sbase8;
+  float magic_x = kMagic + (float)sbase8;
+  uint32_t bits_x = kMagicBits | sbase8;
   uint32_t dummy = smem_u32(s_bits) + (uint32_t)dn.words * 4u + (uint32_t)lane * 4u;
-  uint32_t st_addr = smem_u32(stage + lane);
-  asm volatile("" : "+r"(dummy), "+r"(st_addr));  // plain registers (not re-derived from uniform registers at every use)
+  // a stage = two planes of 512 bytes: piece p (pixels 8p..8p+7) of lane l at p*512 + l*16
+  uint32_t st_addr = smem_u32(stage) + (uint32_t)lane * 16u;
   const uint16_t* rows = reinterpret_cast<const uint16_t*>(scp->depth) + ((size_t)f * H + ra) * W;
+  // plain registers (otherwise re-derived from uniform registers and special registers in every iteration)
+  asm volatile("" : "+r"(dummy), "+r"(st_addr), "+f"(magic_x), "+r"(bits_x), "+l"(rows));
   int cur;  // first chunk of the warp's task
   {
     int t = 0;
@@ -554,8 +553,12 @@ __device__ __forceinline__ void mc_dense_part(const McSetup* __restrict__ s, con
   }
   if (cur >= n) return;
   // lanes past the end of the run redo its last chunk (setting a bit twice is harmless)
-  cp_async16(st_addr, rows + (size_t)min(cur + lane, n - 1) * kPxPerThread);
-  cp_async_commit();
+  {
+    const uint16_t* src = rows + (size_t)min(cur + lane, n - 1) * kDensePx;
+    cp_async16(st_addr, src);
+    cp_async16(st_addr + 512u, src + 8);
+    cp_async_commit();
+  }
   uint32_t k = 0;
   while (cur < n) {
     int nxt;
@@ -568,77 +571,77 @@ __device__ __forceinline__ void mc_dense_part(const McSetup* __restrict__ s, con
 #pragma unroll 1
     for (int it = 0; it < iters; ++it, ++k) {
       const int pf = it + 1 < iters ? cur + (it + 1) * 32 : nxt;
-      if (pf < n) cp_async16(st_addr + (((k + 1u) & 1u) << 9), rows + (size_t)min(pf + lane, n - 1) * kPxPerThread);
+      if (pf < n) {
+        const uint16_t* src = rows + (size_t)min(pf + lane, n - 1) * kDensePx;
+        const uint32_t dst = st_addr + (((k + 1u) & 1u) << 10);
+        cp_async16(dst, src);
+        cp_async16(dst + 512u, src + 8);
+      }
       cp_async_commit();
       cp_async_wait<1>();
-      const uint4 w = lds_v4(st_addr + ((k & 1u) << 9));
+      const uint32_t st_cur = st_addr + ((k & 1u) << 10);
       const int ch = min(cur + it * 32 + lane, n - 1);
       const int r = (int)__umulhi((uint32_t)ch, gpr_magic);
-      const int c0 = (ch - r * gpr) * kPxPerThread;
+      const int c0 = (ch - r * gpr) * kDensePx;
       const int y0 = ra;
-      uint64_t ray02[3];
+      float ray0[3];
       {
         const float vm = __fsub_rn((float)(y0 + r), s->cam.cy), um0 = __fsub_rn((float)c0, s->cam.cx);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const float ray0 = __fmaf_rn(A[i], um0, __fmaf_rn(s->coef[4 * i + 1], vm, s->coef[4 * i + 2]));
-          ray02[i] = pack2(ray0, ray0);
-        }
+        for (int i = 0; i < 3; ++i) ray0[i] = __fmaf_rn(A[i], um0, __fmaf_rn(s->coef[4 * i + 1], vm, s->coef[4 * i + 2]));
       }
-    // A good pixel's key is never all ones: its low 22 bits are 8 * (byte address of the word) + bit number < 2^22 - 1.
-    uint32_t prev = 0xffffffffu, slow = 0;
-    // Two halves of four pixels, not unrolled (eight pixels in flight need more than 64 registers); inside a half the
-    // pixels go in pairs through the packed fp32 instructions (fma/add/sub.rn.f32x2, SASS FFMA2 / FADD2: two lanes of the
-    // same IEEE operation, so the estimate is bit for bit mc_estimate's) -- half the issue slots for the arithmetic.
+      uint32_t prev = 0xffffffffu, slow = 0;
+      // Four quarters of four pixels, not unrolled (more pixels in flight need more than 64 registers); inside a quarter
+      // the pixels go in pairs through the packed fp32 instructions (fma/add/sub.rn.f32x2, SASS FFMA2 / FADD2: two lanes
+      // of the same IEEE operation, so the estimate is bit for bit mc_estimate's) -- half the issue slots for the arithmetic.
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      const uint32_t wa = h ? w.z : w.x, wb = h ? w.w : w.y;
-      const float fh = h ? 4.0f : 0.0f;
+      for (int h = 0; h < kDensePx / 4; ++h) {
+        uint32_t wa, wb;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wa), "=r"(wb) : "r"(st_cur + ((uint32_t)(h >> 1) << 9) + ((uint32_t)(h & 1) << 3)) : "memory");
+        const float fh = (float)(4 * h);
+        slow <<= 4;  // in the end bits 15..12 = pixels 0..3, ..., bits 3..0 = pixels 12..15
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t word = j ? wb : wa;
-        const uint64_t df2 = pack2((float)(word & 0xffffu), (float)(word >> 16));
-        const uint64_t fe2 = pack2(fh + (float)(2 * j), fh + (float)(2 * j + 1));  // exact
-        const uint64_t m2 = fma2(df2, k1n2, hmk02);
-        uint64_t t2[3], tm2[3], dv2[3];
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t word = j ? wb : wa;
+          const uint64_t df2 = pack2((float)(word & 0xffffu), (float)(word >> 16));
+          const uint64_t fe2 = pack2(fh + (float)(2 * j), fh + (float)(2 * j + 1));  // exact
+          const uint64_t m2 = fma2(df2, pack2(k1n, k1n), pack2(hmk0, hmk0));
+          uint64_t t2[3], tm2[3], dv2[3];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          t2[i] = fma2(df2, fma2(A2[i], fe2, ray02[i]), D2[i]);
-          const float mg = i == 0 ? magic_x : kMagic;
-          tm2[i] = add2(t2[i], pack2(mg, mg));
-          dv2[i] = sub2(t2[i], sub2(tm2[i], pack2(mg, mg)));
-        }
+          for (int i = 0; i < 3; ++i) {
+            const float mg = i == 0 ? magic_x : kMagic;
+            t2[i] = fma2(df2, fma2(pack2(A[i], A[i]), fe2, pack2(ray0[i], ray0[i])), pack2(D[i], D[i]));
+            tm2[i] = add2(t2[i], pack2(mg, mg));
+            dv2[i] = sub2(t2[i], sub2(tm2[i], pack2(mg, mg)));
+          }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int e = 2 * j + q;
-          const float dev = fmaxf(fmaxf(fabsf(half2f(dv2[0], q)), fabsf(half2f(dv2[1], q))), fabsf(half2f(dv2[2], q)));
-          const bool ok = dev < half2f(m2, q);
-          if (!ok) slow |= 1u << e;  // bit e of the half
-          // tm = kMagicBits + cell coordinate (+ 8*sbase for x, a multiple of the x extent): inside the box iff x and y
-          // have no bit above their power-of-two extent other than those constants (the fast-frame test keeps |t| < 2^21,
-          // so a negative coordinate always shows such a bit) and 0 <= z < dimz
-          const uint32_t bx = half2u(tm2[0], q), by = half2u(tm2[1], q), bz = half2u(tm2[2], q);
-          const bool good = ok && (((bx & mx) | (by & my)) == bits_x) && ((bz - kMagicBits) < dimz);
-          // kMagicBits * (1 + px + pxy) is a multiple of 2^22: the low 22 bits of the key are 8*sbase + x + px*y + pxy*z,
-          // i.e. 8 * (byte address of the cell's word) + bit number
-          const uint32_t key = good ? bx + by * px + bz * pxy : 0xffffffffu;
-          mc_dense_set(key, prev, dummy);
-          prev = key;
+          for (int q = 0; q < 2; ++q) {
+            const int e = 2 * j + q;
+            const float dev = fmaxf(fmaxf(fabsf(half2f(dv2[0], q)), fabsf(half2f(dv2[1], q))), fabsf(half2f(dv2[2], q)));
+            const bool ok = dev < half2f(m2, q);
+            if (!ok) slow |= 1u << e;
+            // tm = kMagicBits + cell coordinate (+ 8*sbase for x, a multiple of the x extent): inside the box iff x and y
+            // have no bit above their power-of-two extent other than those constants (the fast-frame test keeps
+            // |t| < 2^21, so a negative coordinate always shows such a bit) and 0 <= z < dimz
+            const uint32_t bx = half2u(tm2[0], q), by = half2u(tm2[1], q), bz = half2u(tm2[2], q);
+            const bool good = ok && (((bx & mx) | (by & my)) == bits_x) && ((bz - kMagicBits) < dimz);
+            // kMagicBits * (1 + px + pxy) is a multiple of 2^22: the low 22 bits of the key are 8*sbase + x + px*y + pxy*z,
+            // i.e. 8 * (byte address of the cell's word) + bit number
+            const uint32_t key = good ? bx + by * px + bz * pxy : 0xffffffffu;
+            mc_dense_set(key, prev, dummy);
+            prev = key;
+          }
         }
       }
-      slow <<= 4 * (1 - h);  // the first half's four bits move up: bits 4..7 = pixels 0..3, bits 0..3 = pixels 4..7
-    }
-    if (slow) {  // 2-3 pixels in 10^4: exact operator sequence, probed through the hash
-      const uint32_t w4[4] = {w.x, w.y, w.z, w.w};
+      if (slow) {  // 2-3 pixels in 10^4: exact operator sequence, probed through the hash
 #pragma unroll 1
-      for (uint32_t rest = slow; rest; rest &= rest - 1) {
-        const int b = __ffs(rest) - 1;
-        const int e = b ^ 4;
-        const uint32_t lo = (e & 4) ? w4[2] : w4[0], hi = (e & 4) ? w4[3] : w4[1];
-        const uint32_t word = (e & 2) ? hi : lo;
-        mc_exact_probe(s, scp, f, (e & 1) ? (word >> 16) : (word & 0xffffu), c0 + e, y0 + r);
+        for (uint32_t rest = slow; rest; rest &= rest - 1) {
+          const int e = (__ffs(rest) - 1) ^ 12;
+          uint32_t raw;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(raw) : "r"(st_cur + ((uint32_t)(e >> 3) << 9) + ((uint32_t)(e & 7) << 1)) : "memory");
+          mc_exact_probe(s, scp, f, raw, c0 + e, y0 + r);
+        }
       }
-    }
     }
     cur = nxt;
   }
@@ -679,7 +682,7 @@ __global__ void __launch_bounds__(kDenseThreads, V3D_DENSE_BLOCKS) k_mc_voxelize
   uint32_t* s_bits = s_dyn + ((512u - (smem_u32(s_dyn) & 511u)) & 511u) / 4u;
   __shared__ McSetup s_set;
   __shared__ int s_next;  // next warp task of the frame: warps take tasks as they finish
-  __shared__ __align__(16) uint4 s_stage[kDenseThreads / 32][2][32];
+  __shared__ __align__(16) uint4 s_stage[kDenseThreads / 32][2][64];
   // a CTA takes a contiguous range of the (scene, frame, row block) items of the whole batch
   const long item0 = total_items * blockIdx.x / gridDim.x, item1 = total_items * (blockIdx.x + 1) / gridDim.x;
   long item = item0, first = 0;  // first = first item of scene s
@@ -718,7 +721,7 @@ __global__ void __launch_bounds__(kDenseThreads, V3D_DENSE_BLOCKS) k_mc_voxelize
       }
       __syncthreads();
       if (s_set.fast) {
-        mc_dense_part(&s_set, scenes + s, dn, f, H, W, W / kPxPerThread, gpr_magic, ra, rb, s_bits, &s_next, &s_stage[threadIdx.x >> 5][0][0]);
+        mc_dense_part(&s_set, scenes + s, dn, f, H, W, W / kDensePx, gpr_magic, ra, rb, s_bits, &s_next, &s_stage[threadIdx.x >> 5][0][0]);
         mc_dense_flush(sc, dn, f, s_bits, has_dup);
       } else if (threadIdx.x == 0 && i0 == 0) {
         atomicAdd(sc.record + 7, 1);  // a frame for k_mc_voxelize
@@ -1030,10 +1033,10 @@ static int launch_voxelize(const v3d_mc_scene* dev_scenes, int n_scenes, int max
     bx = bx < 1 ? 1 : (bx > 1024 ? 1024 : bx);
     k_mc_build<<<dim3(bx, n_scenes), kMcThreads, 0, s>>>(dev_scenes);
   }
-  // dense voxeliser first (uint16 depth in whole 8-pixel groups; anything it leaves is done by k_mc_voxelize below)
+  // dense voxeliser first (uint16 depth in whole 16-pixel chunks; anything it leaves is done by k_mc_voxelize below)
   int dense_bits = 0;
   const char* dense_env = getenv("V3D_MC_DENSE");  // "0": hash kernel only (tests compare the two, tools/time_mc.py times both)
-  if (!(dense_env && dense_env[0] == '0') && depth_dtype == V3D_DEPTH_U16 && (W % kPxPerThread) == 0 && (long)H * (W / kPxPerThread) * (W / kPxPerThread) < (1L << 32) && total_frames > 0) {
+  if (!(dense_env && dense_env[0] == '0') && depth_dtype == V3D_DEPTH_U16 && (W % kDensePx) == 0 && (long)H * (W / kDensePx) * (W / kDensePx) < (1L << 32) && total_frames > 0) {
     static bool attr_set = false;
     if (!attr_set) {
       V3D_CUDA(cudaFuncSetAttribute(k_mc_voxelize_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemBytes));
@@ -1045,7 +1048,7 @@ static int launch_voxelize(const v3d_mc_scene* dev_scenes, int n_scenes, int max
     const long total_items = total_frames * items_per_frame;
     long g = (long)num_sms() * V3D_DENSE_BLOCKS;
     if (g > total_items) g = total_items;
-    const uint32_t gpr_magic = 0xffffffffu / (uint32_t)(W / kPxPerThread) + 1u;  // g / gpr == umulhi(g, magic) while g * gpr < 2^32
+    const uint32_t gpr_magic = 0xffffffffu / (uint32_t)(W / kDensePx) + 1u;  // g / gpr == umulhi(g, magic) while g * gpr < 2^32
     k_mc_voxelize_dense<<<(unsigned)g, kDenseThreads, kDenseSmemBytes, s>>>(dev_scenes, n_scenes, H, W, depth_scale, voxel, div_mode, items_per_frame,
                                                                            rows_per_item, total_items, dense_bits, gpr_magic);
     int rc = check_launch("k_mc_voxelize_dense");
