@@ -1086,7 +1086,7 @@ def run_ours(args):
                                        "note": "as e2e, but every scene's resampled depth sits in pinned host memory (copied there once, "
                                                "ScenePack.pin; 286 KB per frame): a batch is 512 DMAs straight out of it (v3d_h2d_gather), the "
                                                "CPU moves no depth"},
-            "gpu_launches": K,  # timed region: K launches of k_fused_ring (e2e: 16 per step; mc: 4 per step)
+            "gpu_launches": K,  # timed region: K launches of k_fused_ring (e2e: 16 per step; mc: 5 per step)
             "clocks": clk,
             "config1": config1,
             "overlay_path": overlay,

@@ -222,7 +222,9 @@ typedef struct v3d_mc_scene {
   int pad_;
   uint32_t* bitsets;        /* (n_frames, words), words = ceil(n_pc/32): frame coverage over pc order */
   /* output */
-  int32_t* record;          /* V3D_MC_RECORD_INTS int32: order[32], gains[32] (-1 padded), n_picked, n_all, n_sel, 0 */
+  int32_t* record;          /* V3D_MC_RECORD_INTS int32: order[32], gains[32] (-1 padded), n_picked, n_all, n_sel, 0.
+                               The voxelise stage uses record[0..7] as workspace (bounding box of the universe, flags);
+                               the greedy stage overwrites the whole record afterwards. */
 } v3d_mc_scene;
 
 #define V3D_MC_MAX_PICK 32
@@ -235,7 +237,9 @@ int v3d_mc_hash_slots(int n_pc);
  * staged in (stream-ordered copy).  All scenes share H, W, depth dtype, voxel size. */
 int v3d_mc_sample(const v3d_mc_scene* scenes_host, int n_scenes, int H, int W, int depth_dtype, float depth_scale,
                   float voxel_size, int div_mode, int max_pick, void* scratch, v3d_stream_t stream);
-/* the two stages separately (tests, profiling) */
+/* the two stages separately (tests, profiling).  Voxelise = k_mc_clear, k_mc_build, k_mc_voxelize_dense (uint16 depth in
+ * whole 16-pixel rows, universe box small enough for one bit per cell in shared memory) and k_mc_voxelize (everything the
+ * dense kernel left: other scenes / frames, other depth types).  Environment V3D_MC_DENSE=0 runs k_mc_voxelize alone. */
 int v3d_mc_voxelize(const v3d_mc_scene* scenes_host, int n_scenes, int H, int W, int depth_dtype, float depth_scale,
                     float voxel_size, int div_mode, void* scratch, v3d_stream_t stream);
 int v3d_mc_greedy(const v3d_mc_scene* scenes_host, int n_scenes, int max_pick, void* scratch, v3d_stream_t stream);
