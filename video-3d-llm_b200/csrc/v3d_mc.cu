@@ -428,10 +428,12 @@ __device__ __forceinline__ int pow2_ceil(int v) {
   return p;
 }
 
-__device__ __forceinline__ McDense mc_dense_plan(const v3d_mc_scene& sc, int smem_bits) {
+__device__ __forceinline__ McDense mc_dense_plan(const v3d_mc_scene& sc, int smem_bits, int frame_pixels) {
   McDense d;
   d.ok = 0;
   if (sc.n_pc <= 0 || smem_bits <= 0) return d;
+  // the walk over the universe after every frame must stay small next to the frame itself
+  if (sc.n_pc > 65536 && sc.n_pc > frame_pixels / 2) return d;
   long ext[3];
   for (int a = 0; a < 3; ++a) {
     const int lo = sc.record[a], hi = sc.record[3 + a];
@@ -653,6 +655,7 @@ __device__ __forceinline__ void mc_dense_flush(const v3d_mc_scene& sc, const McD
   __syncthreads();  // every warp has set its bits
   const int lane = threadIdx.x & 31;
   uint32_t* bits = sc.bitsets + (size_t)f * ((sc.n_pc + 31) / 32);
+#pragma unroll 2
   for (int p0 = 0; p0 < sc.n_pc; p0 += kDenseThreads) {
     const int p = p0 + threadIdx.x;
     bool b = false;
@@ -696,7 +699,7 @@ __global__ void __launch_bounds__(kDenseThreads, V3D_DENSE_BLOCKS) k_mc_voxelize
     }
     const long send = item1 < first + cnt ? item1 : first + cnt;
     const v3d_mc_scene sc = scenes[s];
-    const McDense dn = mc_dense_plan(sc, smem_bits);
+    const McDense dn = mc_dense_plan(sc, smem_bits, H * W);
     if (!dn.ok) {  // k_mc_voxelize takes the whole scene
       item = send;
       continue;
@@ -738,7 +741,7 @@ __global__ void __launch_bounds__(kMcThreads, V3D_MC_MIN_BLOCKS) k_mc_voxelize(c
   const v3d_mc_scene sc = scenes[blockIdx.y];
   // what k_mc_voxelize_dense has done already (dense_smem_bits = 0: it did not run): every `fast` frame of a scene
   // whose universe box fits its shared-memory cell bitset
-  const McDense dn = mc_dense_plan(sc, dense_smem_bits);
+  const McDense dn = mc_dense_plan(sc, dense_smem_bits, H * W);
   if (dn.ok && sc.record[7] == 0) return;
   const int words = (sc.n_pc + 31) / 32;
   const uint32_t mask = (uint32_t)sc.hash_slots - 1u;
