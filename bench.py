@@ -84,10 +84,11 @@ def measured_peaks():
 
 
 def csrc_hash() -> str:
-    """Identifies the kernel sources a profile was taken on (profiles/traffic.json records it)."""
+    """Identifies the sources of the headline kernel (k_fused_ring and what it includes) a profile was taken on
+    (profiles/traffic.json records it); the other kernels' sources do not enter."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "video-3d-llm_b200", "csrc")
-    for fn in sorted(os.listdir(d)) + ["../../include/v3d.h"]:
+    for fn in ["v3d_common.cuh", "v3d_frontend.cu", "v3d_fused.cuh", "v3d_fused_ring.cu", "v3d_pe.cuh", "../../include/v3d.h"]:
         with open(os.path.join(d, fn), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]

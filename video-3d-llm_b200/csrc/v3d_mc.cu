@@ -630,6 +630,7 @@ __device__ __forceinline__ void mc_dense_part(const McSetup* __restrict__ s, con
             // kMagicBits * (1 + px + pxy) is a multiple of 2^22: the low 22 bits of the key are 8*sbase + x + px*y + pxy*z,
             // i.e. 8 * (byte address of the cell's word) + bit number
             const uint32_t key = good ? bx + by * px + bz * pxy : 0xffffffffu;
+            V3D_CHECK(!good || (((key >> 3) & 0x7fffcu) - smem_u32(s_bits)) < (uint32_t)dn.words * 4u);
             mc_dense_set(key, prev, dummy);
             prev = key;
           }
