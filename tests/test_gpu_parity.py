@@ -996,7 +996,7 @@ def test_mc_dense_voxeliser_equals_the_hash_path(monkeypatch):
     """k_mc_voxelize_dense (cell bitset of the universe's box in shared memory) against k_mc_voxelize alone (V3D_MC_DENSE=0:
     queue + hash probes): identical coverage bitsets for full-size scenes, a universe with duplicates, a universe that is
     too large for the cell bitset (hash path for that scene only), one non-rigid frame (hash path for that frame only) and
-    an empty universe."""
+    an empty universe; a universe that covers only the middle of the room (pixels outside the box on every side)."""
     scenes = []
     for s in range(5):
         seed = 720 + s
@@ -1004,6 +1004,10 @@ def test_mc_dense_voxeliser_equals_the_hash_path(monkeypatch):
         sc = synthetic.make_scene(seed, n, n_total=300, frame_indices=np.arange(0, 2 * n, 2), device=DEV)
         pc = synthetic.mesh_voxels(sc.room, sc.boxes, seed)
         poses = sc.poses.clone()
+        if s == 0:  # the universe is a slab of the room: many pixels fall outside its box, below and above in x, y and z
+            lo, hi = np.percentile(pc, 30, axis=0), np.percentile(pc, 75, axis=0)
+            pc = np.ascontiguousarray(pc[(pc[:, 0] >= lo[0]) & (pc[:, 0] <= hi[0]) & (pc[:, 1] <= hi[1]) & (pc[:, 2] >= 2) & (pc[:, 2] <= pc[:, 2].max() - 2)])
+            assert len(pc) > 500
         if s == 1:
             pc = np.concatenate([pc, pc[:300], pc[100:200]])  # duplicates own one bit
         if s == 2:
