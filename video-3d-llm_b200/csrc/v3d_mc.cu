@@ -1041,11 +1041,8 @@ static int launch_voxelize(const v3d_mc_scene* dev_scenes, int n_scenes, int max
   int dense_bits = 0;
   const char* dense_env = getenv("V3D_MC_DENSE");  // "0": hash kernel only (tests compare the two, tools/time_mc.py times both)
   if (!(dense_env && dense_env[0] == '0') && depth_dtype == V3D_DEPTH_U16 && (W % kDensePx) == 0 && (long)H * (W / kDensePx) * (W / kDensePx) < (1L << 32) && total_frames > 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      V3D_CUDA(cudaFuncSetAttribute(k_mc_voxelize_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemBytes));
-      attr_set = true;
-    }
+    // per device and cheap: set at every launch (a process may drive several devices)
+    V3D_CUDA(cudaFuncSetAttribute(k_mc_voxelize_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemBytes));
     dense_bits = kDenseSmemBytes * 8;
     const int rows_per_item = (kDenseThreads / 32) * kDenseRows;
     const int items_per_frame = (H + rows_per_item - 1) / rows_per_item;
