@@ -2,9 +2,11 @@
 //
 // Replaces scripts/3d/preprocessing/max_coverage_sampling.py:39-104:
 //   k_mc_build    : open-addressing hash of the mesh universe pc_voxel (:65), clears bitsets
-//   k_mc_voxelize : unproject every pixel of every candidate frame, vox = int(round(w/voxel))
-//                   (:44-45), look it up, atomicOr the frame's coverage bit -> per-frame
-//                   bitsets = set(frame voxels) & pc_voxel (:47-50, :75)
+//   k_mc_voxelize_dense / k_mc_voxelize :
+//                   unproject every pixel of every candidate frame, vox = int(round(w/voxel))
+//                   (:44-45), look it up (a bit per cell of the universe's box in shared memory / the
+//                   hash), set the frame's coverage bit -> per-frame bitsets = set(frame voxels) &
+//                   pc_voxel (:47-50, :75)
 //   k_mc_greedy   : one CTA per scene; each round = popcount(bits & ~used) per remaining frame,
 //                   argmax with the ascending-order tie list (:72-82), CPython-compatible
 //                   MT19937 random.choice (:84), used |= bits (:86) -- bit-exact selection.
@@ -403,6 +405,7 @@ __device__ __forceinline__ void mc_slab_generic(const v3d_mc_scene& sc, const Mc
 // bitset.  Pixels outside the box cannot be in the universe and are dropped; guard-band pixels take the exact operator
 // sequence and the hash probe as before.  Scenes whose box does not fit (or whose frames are not `fast`) are left to
 // k_mc_voxelize, which skips everything this kernel has done -- both derive the split from mc_dense_plan.
+// 512 threads x 2 CTAs per SM at 64 registers is the measured best (384 x 2 at 80 registers and one CTA per SM are slower).
 #ifndef V3D_DENSE_THREADS
 #define V3D_DENSE_THREADS 512
 #endif
@@ -410,7 +413,7 @@ __device__ __forceinline__ void mc_slab_generic(const v3d_mc_scene& sc, const Mc
 #define V3D_DENSE_BLOCKS 2
 #endif
 static constexpr int kDenseThreads = V3D_DENSE_THREADS;
-static constexpr int kDenseRows = 2;  // rows per warp task: 2 x 640 / 8 = 160 chunks = 5 full warp iterations
+static constexpr int kDenseRows = 2;  // rows per warp in one item of a CTA's range: items are blocks of 32 rows
 static constexpr int kDenseSmemBytes = (V3D_DENSE_BLOCKS == 1 ? 160 : 80) * 1024;  // cell bitset; two CTAs per SM with their staging rings
 static constexpr uint32_t kMagicBits = 0x4B400000u;  // bits of kMagic: (t + kMagic) has the bits kMagicBits + rint(t)
 
