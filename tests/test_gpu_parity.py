@@ -1015,6 +1015,10 @@ def test_mc_dense_voxeliser_equals_the_hash_path(monkeypatch):
             poses[3, 3, :] = torch.tensor([0.0, 0.0, 1e-3, 1.0], device=DEV)  # projective frame
         if s == 3:
             poses[2, 3, :] = torch.tensor([0.0, 1e-3, 0.0, 1.0], device=DEV)  # one frame for the hash kernel
+            # frames far outside the box (4096 cells and more): not for the dense kernel's combined x / y box test
+            poses[4, 1, 3] += 3276.8 + 409.6
+            poses[5, 0, 3] -= 32768 * 0.1
+            poses[6, :3, 3] += torch.tensor([409.6, 819.2, -1638.4], device=DEV)
         if s == 4:
             pc = pc[:0]
         scenes.append({"depth": sc.depth, "poses": poses, "intrinsics": sc.intrinsics,

@@ -167,7 +167,7 @@ __device__ __noinline__ void mc_setup_frame(McSetup* s, const v3d_mc_scene& sc, 
   const double den[4] = {(double)cam.fx.b * sv, (double)cam.fy.b * sv, sv, (double)voxel};
   const double um_max = fmax(fabs(0.0 - (double)cam.cx), fabs((double)(W - 1) - (double)cam.cx));
   const double vm_max = fmax(fabs(0.0 - (double)cam.cy), fabs((double)(H - 1) - (double)cam.cy));
-  double r_max = 0.0, d_max = 0.0;
+  double r_max = 0.0, d_max = 0.0, shifted_max = 0.0;
   bool finite = true;
   for (int i = 0; i < 3; ++i) {
     double c[4];
@@ -176,7 +176,10 @@ __device__ __noinline__ void mc_setup_frame(McSetup* s, const v3d_mc_scene& sc, 
       finite = finite && (fabs(c[j]) < 1.0e30);
     }
     d_max = fmax(d_max, fabs(c[3]));
-    if (base) c[3] -= (double)base[i];
+    if (base) {
+      c[3] -= (double)base[i];
+      shifted_max = fmax(shifted_max, fabs(c[3]));
+    }
     for (int j = 0; j < 4; ++j) s->coef[4 * i + j] = (float)c[j];
     r_max = fmax(r_max, fabs(c[0]) * um_max + fabs(c[1]) * vm_max + fabs(c[2]));
     d_max = fmax(d_max, fabs(c[3]));
@@ -189,6 +192,11 @@ __device__ __noinline__ void mc_setup_frame(McSetup* s, const v3d_mc_scene& sc, 
   // underflow inside the reference sequence that the bound would not see)
   s->fast = layout_ok && finite && cam.rigid && s->ds.ok && cam.fx.ok && cam.fy.ok && s->dv.ok && (65535.0 * r_max + d_max < 2097152.0) &&
             (um_max < 1.0e6) && (vm_max < 1.0e6);
+  // The dense voxeliser's box test (one compare for x and y together, mc_dense_part) is exact only while no coordinate
+  // can carry a bit at or above 2^12, where the bits of the bitset's address sit in x: every cell coordinate any uint16
+  // depth can produce must stay below 4096 in magnitude (a 65.5 m ray is 655 cells at 0.1 m).  Other frames are not
+  // `fast` for either kernel and take the exact path of k_mc_voxelize.
+  if (base) s->fast = s->fast && (65535.0 * r_max + shifted_max < 4095.0);
 }
 
 // exact operator sequence of one pixel (the guard-band pixels), probed right away
@@ -625,9 +633,11 @@ __device__ __forceinline__ void mc_dense_part(const McSetup* __restrict__ s, con
             const float dev = fmaxf(fmaxf(fabsf(half2f(dv2[0], q)), fabsf(half2f(dv2[1], q))), fabsf(half2f(dv2[2], q)));
             const bool ok = dev < half2f(m2, q);
             if (!ok) slow |= 1u << e;
-            // tm = kMagicBits + cell coordinate (+ 8*sbase for x, a multiple of the x extent): inside the box iff x and y
-            // have no bit above their power-of-two extent other than those constants (the fast-frame test keeps
-            // |t| < 2^21, so a negative coordinate always shows such a bit) and 0 <= z < dimz
+            // tm = kMagicBits + cell coordinate (+ 8*sbase for x, a multiple of 4096): inside the box iff x and y have no
+            // bit above their power-of-two extent other than those constants and 0 <= z < dimz.  The fast-frame test
+            // keeps every |coordinate| below 4096: a coordinate outside its extent then shows a bit below 2^12 (too
+            // large) or clears bit 22 and sets bits 12..21 (negative) -- neither can be mistaken for the bits of
+            // 8*sbase, which are all at or above 2^12 and never all of 12..21
             const uint32_t bx = half2u(tm2[0], q), by = half2u(tm2[1], q), bz = half2u(tm2[2], q);
             const bool good = ok && (((bx & mx) | (by & my)) == bits_x) && ((bz - kMagicBits) < dimz);
             // kMagicBits * (1 + px + pxy) is a multiple of 2^22: the low 22 bits of the key are 8*sbase + x + px*y + pxy*z,
