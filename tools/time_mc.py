@@ -3,6 +3,7 @@
     python tools/time_mc.py [reps] [n_scenes] [candidates: 150 (every second frame of 300) or 300 (all frames)]
 
 CUDA events on the launching stream, best and median of `reps` runs per stage after one warm-up.
+V3D_MC_DENSE=0 in the environment times the hash voxeliser alone (k_mc_voxelize without k_mc_voxelize_dense).
 """
 import os
 import statistics

@@ -1053,7 +1053,8 @@ static int launch_voxelize(const v3d_mc_scene* dev_scenes, int n_scenes, int max
   // dense voxeliser first (uint16 depth in whole 16-pixel chunks; anything it leaves is done by k_mc_voxelize below)
   int dense_bits = 0;
   const char* dense_env = getenv("V3D_MC_DENSE");  // "0": hash kernel only (tests compare the two, tools/time_mc.py times both)
-  if (!(dense_env && dense_env[0] == '0') && depth_dtype == V3D_DEPTH_U16 && (W % kDensePx) == 0 && (long)H * (W / kDensePx) * (W / kDensePx) < (1L << 32) && total_frames > 0) {
+  if (!(dense_env && dense_env[0] == '0') && depth_dtype == V3D_DEPTH_U16 && (W % kDensePx) == 0 && (long)H * (W / kDensePx) * (W / kDensePx) < (1L << 32) && total_frames > 0 &&
+      n_scenes <= 4096 /* a CTA finds its first scene by walking the descriptors */) {
     // per device and cheap: set at every launch (a process may drive several devices)
     V3D_CUDA(cudaFuncSetAttribute(k_mc_voxelize_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemBytes));
     dense_bits = kDenseSmemBytes * 8;
