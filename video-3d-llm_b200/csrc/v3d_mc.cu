@@ -814,27 +814,62 @@ struct Mt {
   uint32_t mt[624];
   int idx;
 };
+// One thread; the recurrence is serial, so the previous word stays in a register (a reload of the word just stored
+// would put a shared-memory round trip on every one of the 1871 steps).
 __device__ void mt_seed(Mt* s, uint64_t seed) {  // random.seed(int): init_by_array(32-bit words of |seed|)
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   const int klen = key[1] ? 2 : 1;
   uint32_t* mt = s->mt;
-  mt[0] = 19650218u;
-  for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+  uint32_t p = 19650218u;
+  mt[0] = p;
+  for (int i = 1; i < 624; ++i) {
+    p = 1812433253u * (p ^ (p >> 30)) + (uint32_t)i;
+    mt[i] = p;
+  }
   int i = 1, j = 0;
+  p = 19650218u;  // mt[i - 1] for i = 1
   for (int k = 624; k; --k) {
-    mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+    p = (mt[i] ^ ((p ^ (p >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+    mt[i] = p;
     ++i;
     ++j;
-    if (i >= 624) { mt[0] = mt[623]; i = 1; }
+    if (i >= 624) { mt[0] = p; i = 1; }
     if (j >= klen) j = 0;
   }
   for (int k = 623; k; --k) {
-    mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+    p = (mt[i] ^ ((p ^ (p >> 30)) * 1566083941u)) - (uint32_t)i;
+    mt[i] = p;
     ++i;
-    if (i >= 624) { mt[0] = mt[623]; i = 1; }
+    if (i >= 624) { mt[0] = p; i = 1; }
   }
   mt[0] = 0x80000000u;
   s->idx = 624;
+}
+// The first regeneration of the state after seeding, by the whole CTA (mt_next does it with one thread: 624 steps of three
+// shared-memory loads each).  Words [0,227) depend on old words only, [227,454) on the new [0,227), [454,623) on the new
+// [227,396), the last word on the new words 396 and 0; inside a phase every thread reads before anybody writes.
+__device__ void mt_first_twist(Mt* s, int t, int n_threads) {
+  uint32_t* mt = s->mt;
+  auto mix = [](uint32_t hi, uint32_t lo) {
+    const uint32_t y = (hi & 0x80000000u) | (lo & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+  };
+  const int lo[3] = {0, 227, 454}, hi[3] = {227, 454, 623};
+  for (int ph = 0; ph < 3; ++ph) {
+    for (int k0 = lo[ph]; k0 < hi[ph]; k0 += n_threads) {  // one pass for 512 threads
+      const int kk = k0 + t;
+      uint32_t v = 0;
+      if (kk < hi[ph]) v = mt[kk < 227 ? kk + 397 : kk - 227] ^ mix(mt[kk], mt[kk + 1]);
+      __syncthreads();
+      if (kk < hi[ph]) mt[kk] = v;
+      __syncthreads();
+    }
+  }
+  if (t == 0) {
+    mt[623] = mt[396] ^ mix(mt[623], mt[0]);
+    s->idx = 0;
+  }
+  __syncthreads();
 }
 __device__ uint32_t mt_next(Mt* s) {
   uint32_t* mt = s->mt;
@@ -925,6 +960,7 @@ __global__ void __launch_bounds__(kGreedyThreads) k_mc_greedy(const v3d_mc_scene
     }
   }
   __syncthreads();
+  mt_first_twist(s_mt, t, kGreedyThreads);
 
   int n_picked = 0;
   const int rounds = min(F, max_pick);
