@@ -7,7 +7,7 @@
 //                   (:44-45), look it up (a bit per cell of the universe's box in shared memory / the
 //                   hash), set the frame's coverage bit -> per-frame bitsets = set(frame voxels) &
 //                   pc_voxel (:47-50, :75)
-//   k_mc_greedy   : one CTA per scene; each round = popcount(bits & ~used) per remaining frame,
+//   k_mc_greedy   : one 8-CTA cluster per scene; each round = popcount(bits & ~used) per remaining frame,
 //                   argmax with the ascending-order tie list (:72-82), CPython-compatible
 //                   MT19937 random.choice (:84), used |= bits (:86) -- bit-exact selection.
 #include <cooperative_groups.h>
